@@ -1,0 +1,80 @@
+"""Pins oracle/reference_ports.py against outputs of the REAL reference code (tests/golden/*.npz,
+made by tests/golden/make_golden.py): SURVEY.md rows a1, a8, a9, a10, a11, a12."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import reference_ports as rp
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def test_cameras_match_reference(golden_dir):
+    g = _load(golden_dir, "cameras_abc.npz")
+    assert g["Ks"].shape == (50, 3, 3) and g["viewmats"].shape == (50, 4, 4)
+    assert tuple(g["width_height"]) == (800, 800)
+    # the port needs the meta_data frames; they are re-derivable from the golden viewmats:
+    # cam_to_world = inverse(viewmat) -> port must give the viewmat back (R^T, -R^T t round trip)
+    for i in (0, 7, 23, 49):
+        vm = g["viewmats"][i].astype(np.float64)
+        c2w = np.linalg.inv(vm)
+        K, vm2 = rp.emap_camera(c2w, g["Ks"][i])
+        np.testing.assert_allclose(vm2, g["viewmats"][i], atol=2e-6)
+        np.testing.assert_array_equal(K, g["Ks"][i])
+        np.testing.assert_array_equal(vm2[3], [0, 0, 0, 1])
+
+
+def test_losses_match_reference(golden_dir):
+    g = _load(golden_dir, "losses.npz")
+    for i in range(3):
+        out, gt = g["out"][i], g["gt"][i]
+        mask = rp.edge_mask(gt)
+        np.testing.assert_array_equal(mask, g["edge_masks"][i])
+        wm = rp.weight_mask(mask)
+        np.testing.assert_allclose(wm, g["weight_masks"][i], rtol=1e-6)
+        assert rp.loss_whole(out, gt) == pytest.approx(float(g["whole"][i]), rel=2e-6)
+        assert rp.loss_whole(out, gt, "l2") == pytest.approx(float(g["whole_l2"][i]), rel=2e-6)
+        assert rp.loss_weighted(out, gt, wm) == pytest.approx(float(g["weighted"][i]), rel=2e-6)
+        got = rp.loss_bg_edge_ratio(out, gt, mask, float(g["bg_edge_pixel_ratio"]), g[f"perm{i}"])
+        assert got == pytest.approx(float(g["bg_edge_ratio"][i]), rel=2e-6)
+
+
+def test_absgrads_match_reference(golden_dir):
+    g = _load(golden_dir, "absgrads.npz")
+    acc = np.zeros(g["absgrads"].shape, np.float32)
+    nf = 1
+    for a in g["absgrad_inputs"]:
+        acc, nf = rp.update_absgrads(acc, nf, a)
+    np.testing.assert_allclose(acc, g["absgrads"], rtol=1e-6)
+    assert nf == int(g["normalize_factor"])
+
+
+def test_rotmats_match_reference(golden_dir):
+    g = _load(golden_dir, "regularisers.npz")
+    np.testing.assert_allclose(rp.quats_to_rotmats(g["quats"]), g["rotmats"], atol=1e-6)
+
+
+@pytest.mark.parametrize("method,k", [("enforce_full", 5), ("enforce_half", 4), ("enforce_full", 10)])
+def test_knn_and_direction_loss_match_reference(golden_dir, method, k):
+    g = _load(golden_dir, "regularisers.npz")
+    tag = f"{method}_k{k}"
+    nn = rp.knn_indices(g["means"], k, method)
+    assert nn.dtype == np.float32 and nn.shape == g[f"nn_{tag}"].shape
+    np.testing.assert_array_equal(nn, g[f"nn_{tag}"])
+    loss, vm, vq = rp.direction_loss(g["means"], g["quats"], g["scales"], g[f"nn_{tag}"], k, method)
+    assert loss == pytest.approx(float(g[f"dir_loss_{tag}"]), rel=1e-5)
+    sm = np.abs(g[f"dir_vmeans_{tag}"]).max()
+    sq = np.abs(g[f"dir_vquats_{tag}"]).max()
+    np.testing.assert_allclose(vm, g[f"dir_vmeans_{tag}"], atol=2e-4 * sm, rtol=1e-3)
+    np.testing.assert_allclose(vq, g[f"dir_vquats_{tag}"], atol=2e-4 * sq, rtol=1e-3)
+
+
+def test_ratio_loss_matches_reference(golden_dir):
+    g = _load(golden_dir, "regularisers.npz")
+    loss, vs = rp.ratio_loss(g["scales"])
+    assert loss == pytest.approx(float(g["ratio_loss"]), rel=1e-5)
+    np.testing.assert_allclose(vs, g["ratio_vscales"], atol=1e-8, rtol=1e-4)
