@@ -1,0 +1,70 @@
+"""ctypes binding of libedgegs.so (include/edgegs.h).  PyTorch supplies device memory and streams
+only; every hot-path computation is a hand-written sm_100a kernel behind the C ABI.
+
+There is NO CPU fallback: if the library is missing or no CUDA device is present, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_C", "libedgegs.so")
+
+EG_ST_NISECT, EG_ST_OVERFLOW, EG_ST_BADCOLOR, EG_ST_NVISIBLE, EG_ST_WORDS = 0, 1, 2, 3, 8
+EG_GT_NONE, EG_GT_F32, EG_GT_U8 = 0, 1, 2
+
+EXPORTS = ["eg_last_error", "eg_abi_version", "eg_tile_grid", "eg_project_fwd", "eg_bin", "eg_raster_fwd",
+           "eg_raster_bwd", "eg_project_bwd", "eg_reg_fwd_bwd"]
+
+
+class EgConfig(Structure):
+    _fields_ = [("n", c_int32), ("width", c_int32), ("height", c_int32), ("tile_size", c_int32),
+                ("eps2d", c_float), ("near_plane", c_float), ("far_plane", c_float), ("radius_clip", c_float),
+                ("antialiased", c_int32), ("raw_params", c_int32), ("isect_capacity", c_int64)]
+
+
+_lib = None
+
+
+def load(build_if_missing: bool = True):
+    """Load libedgegs.so, building it in-tree with nvcc when absent. Raises on failure."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if not build_if_missing:
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -m edgegaussians_b200.build`")
+        from . import build as _build
+        _build.build()
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.eg_last_error.restype = c_char_p
+    lib.eg_abi_version.restype = c_int
+    for name in EXPORTS:
+        if not hasattr(lib, name):
+            raise RuntimeError(f"libedgegs.so does not export {name}")
+    P = c_void_p
+    cfgp = POINTER(EgConfig)
+    lib.eg_tile_grid.argtypes = [c_int, c_int, c_int, POINTER(c_int), POINTER(c_int)]
+    lib.eg_project_fwd.argtypes = [cfgp] + [P] * 12
+    lib.eg_bin.argtypes = [cfgp] + [P] * 8
+    lib.eg_raster_fwd.argtypes = [cfgp] + [P] * 9 + [c_int, P, P, P, P]
+    lib.eg_raster_bwd.argtypes = [cfgp] + [P] * 6 + [c_int, P, P, c_float, P, P, P]
+    lib.eg_project_bwd.argtypes = [cfgp] + [P] * 16
+    lib.eg_reg_fwd_bwd.argtypes = [c_int, P, P, P, P, c_int, c_int, c_int, c_float, c_float, P, P, P, P, P]
+    for name in EXPORTS[2:]:
+        getattr(lib, name).restype = c_int
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (rc={rc}): {load().eg_last_error().decode()}")
+
+
+def require_cuda(t, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: edgegaussians_b200 has no CPU path "
+                           "(the CPU oracle under oracle/ is test infrastructure only)")

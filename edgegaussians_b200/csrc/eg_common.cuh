@@ -1,0 +1,84 @@
+// eg_common.cuh -- shared declarations of the sm_100a kernels behind include/edgegs.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/edgegs.h"
+
+#define EG_TILE 16
+#define EG_ALPHA_MAX 0.999f
+#define EG_ALPHA_MIN (1.0f / 255.0f)
+#define EG_T_MIN 1e-4f
+#define EG_LOG2E 1.4426950408889634f
+
+void eg_set_error(const char *fmt, ...);
+int eg_check_launch(const char *what);
+
+// camera block shared by the projection kernels (read from device memory; no host sync)
+struct EgCam {
+    float R[9];
+    float t[3];
+    float fx, fy, cx, cy;
+};
+
+__device__ __forceinline__ EgCam eg_load_cam(const float *__restrict__ vm, const float *__restrict__ K) {
+    EgCam c;
+    c.R[0] = __ldg(vm + 0); c.R[1] = __ldg(vm + 1); c.R[2] = __ldg(vm + 2);  c.t[0] = __ldg(vm + 3);
+    c.R[3] = __ldg(vm + 4); c.R[4] = __ldg(vm + 5); c.R[5] = __ldg(vm + 6);  c.t[1] = __ldg(vm + 7);
+    c.R[6] = __ldg(vm + 8); c.R[7] = __ldg(vm + 9); c.R[8] = __ldg(vm + 10); c.t[2] = __ldg(vm + 11);
+    c.fx = __ldg(K + 0); c.fy = __ldg(K + 4); c.cx = __ldg(K + 2); c.cy = __ldg(K + 5);
+    return c;
+}
+
+// gsplat's (uint32_t)floor(x) on CUDA: cvt.rzi.u32.f32 saturates (negatives, NaN -> 0)
+__device__ __forceinline__ uint32_t eg_sat_u32(float v) { return __float2uint_rz(v); }
+
+// tile rectangle of a Gaussian (gsplat isect_tiles); canonical fp32 order, see DESIGN.md
+__device__ __forceinline__ void eg_tile_rect(float m2x, float m2y, int radius, int tw, int th,
+                                             uint32_t &x0, uint32_t &y0, uint32_t &x1, uint32_t &y1) {
+    const float ts = (float)EG_TILE;
+    const float tr = __fdiv_rn((float)radius, ts);
+    const float txc = __fdiv_rn(m2x, ts), tyc = __fdiv_rn(m2y, ts);
+    x0 = min(eg_sat_u32(floorf(__fsub_rn(txc, tr))), (uint32_t)tw);
+    y0 = min(eg_sat_u32(floorf(__fsub_rn(tyc, tr))), (uint32_t)th);
+    x1 = min(eg_sat_u32(ceilf(__fadd_rn(txc, tr))), (uint32_t)tw);
+    y1 = min(eg_sat_u32(ceilf(__fadd_rn(tyc, tr))), (uint32_t)th);
+}
+
+__device__ __forceinline__ float eg_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__device__ __forceinline__ void eg_red_add_v4(float *addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+                 : "memory");
+}
+
+// sigma and opacity*exp(-sigma) with a FIXED operation order (explicit intrinsics, no compiler
+// contraction) so that the forward and the backward kernels take identical skip decisions
+// (sigma < 0, alpha < 1/255) for every (pixel, Gaussian) pair.
+__device__ __forceinline__ float eg_sigma(float A, float B, float C, float dx, float dy) {
+    const float q = __fmaf_rn(__fmul_rn(A, dx), dx, __fmul_rn(__fmul_rn(C, dy), dy));
+    return __fmaf_rn(0.5f, q, __fmul_rn(__fmul_rn(B, dx), dy));
+}
+__device__ __forceinline__ float eg_vis(float sigma) { return eg_ex2(__fmul_rn(-sigma, EG_LOG2E)); }
+
+// Conservative half-extents (pixels) of the region where a Gaussian can reach alpha >= 1/255:
+// { p : sigma(p) <= tau },  tau = ln(255 * opacity) (+ safety margin).  Returns false when the
+// Gaussian can never contribute (opacity < 1/255).  Used ONLY to skip work whose result the
+// alpha test would discard anyway, so it never changes results.
+__device__ __forceinline__ bool eg_extent(float o, float A, float B, float C, float &hx, float &hy, float &tau) {
+    if (!(o >= EG_ALPHA_MIN)) return false;
+    tau = __logf(255.0f * o) * 1.001f + 0.02f;
+    const float det = A * C - B * B;
+    if (!(det > 0.0f) || !(A > 0.0f) || !(C > 0.0f)) {
+        hx = hy = 1e30f;
+        return true;
+    }
+    const float k = 2.0f * tau / det;
+    hx = sqrtf(k * C) * 1.0001f + 1e-3f;
+    hy = sqrtf(k * A) * 1.0001f + 1e-3f;
+    return true;
+}

@@ -1,0 +1,277 @@
+// eg_raster_fwd.cu -- K3 + K5 (+ fused "whole" L1 edge-map loss): one CTA per 16x16 tile.
+//
+//   phase A  sort the tile's (depth_bits<<32 | id) keys (shared-memory bitonic network; segments
+//            longer than SORT_CAP use a chunked shared/global hybrid of the same network) and write
+//            gsplat's flatten_ids / isect_ids for the segment;
+//   phase B  front-to-back alpha compositing, SURVEY.md Appendix A.3 (gsplat==1.0.0
+//            rasterize_to_pixels fwd behind /root/reference/edgegaussians/models/edge_gs.py:250-268):
+//            batches of 256 Gaussian records are staged in shared memory; each warp owns an 8x4
+//            pixel sub-tile and only walks the Gaussians whose alpha >= 1/255 footprint can reach
+//            that sub-tile (a conservative bounding test done once per (tile, Gaussian) by the
+//            staging thread) -- the sequence of Gaussians each pixel composites is exactly gsplat's;
+//   epilogue alpha = 1 - T, render channel 0, last_ids, and optionally the reference's
+//            clamp -> channel 0 -> mean |render - gt| (edge_gs.py:279,290-296; train_gaussians.py:84-94)
+//            as a per-CTA partial sum plus the per-pixel backward seed.
+//
+// colors == 1 on this path (edge_gs.py:247), so the three render channels are identical; one is stored.
+#include "eg_common.cuh"
+
+namespace {
+
+constexpr int RF_THREADS = 256;
+constexpr int SORT_CAP = 2048;  // keys sorted entirely in shared memory (16 KB)
+typedef unsigned long long u64;
+
+__device__ __forceinline__ void cmpx(u64 &a, u64 &b) {
+    if (a > b) { const u64 t = a; a = b; b = t; }
+}
+
+// ascending-only bitonic network on s[0..n_pad), n_pad a power of two; all 256 threads call it.
+// first_k lets the hybrid path resume at a later merge stage; k_end is the last merge size (incl.).
+__device__ void bitonic_smem(u64 *s, int n_pad, int tid) {
+    for (int k = 2; k <= n_pad; k <<= 1) {
+        const int hk = k >> 1;
+        for (int idx = tid; idx < (n_pad >> 1); idx += RF_THREADS) {
+            const int blk = idx / hk, off = idx - blk * hk;
+            const int i = blk * k + off, j = blk * k + k - 1 - off;
+            cmpx(s[i], s[j]);
+        }
+        __syncthreads();
+        for (int j = k >> 2; j > 0; j >>= 1) {
+            for (int idx = tid; idx < (n_pad >> 1); idx += RF_THREADS) {
+                const int i = 2 * j * (idx / j) + (idx % j);
+                cmpx(s[i], s[i + j]);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// the tail of one merge stage inside a chunk: plain half-cleaners j = SORT_CAP/2 ... 1
+__device__ void bitonic_tail_smem(u64 *s, int tid) {
+    for (int j = SORT_CAP >> 1; j > 0; j >>= 1) {
+        for (int idx = tid; idx < (SORT_CAP >> 1); idx += RF_THREADS) {
+            const int i = 2 * j * (idx / j) + (idx % j);
+            cmpx(s[i], s[i + j]);
+        }
+        __syncthreads();
+    }
+}
+
+// Sort a segment longer than SORT_CAP in place in global memory (rare: > 2048 Gaussians on a tile).
+// Virtual padding with +inf: a comparator whose upper index is >= L is a no-op in an ascending-only
+// network, so it is skipped.
+__device__ void sort_large(u64 *__restrict__ gk, int L, u64 *s, int tid) {
+    int n_pad = SORT_CAP;
+    while (n_pad < L) n_pad <<= 1;
+    const int n_chunks = (L + SORT_CAP - 1) / SORT_CAP;
+    for (int c = 0; c < n_chunks; ++c) {
+        const int base = c * SORT_CAP;
+        for (int i = tid; i < SORT_CAP; i += RF_THREADS) s[i] = (base + i < L) ? gk[base + i] : ~0ull;
+        __syncthreads();
+        bitonic_smem(s, SORT_CAP, tid);
+        for (int i = tid; i < SORT_CAP; i += RF_THREADS)
+            if (base + i < L) gk[base + i] = s[i];
+        __syncthreads();
+    }
+    for (int k = 2 * SORT_CAP; k <= n_pad; k <<= 1) {
+        const int hk = k >> 1;
+        for (int idx = tid; idx < (n_pad >> 1); idx += RF_THREADS) {
+            const int blk = idx / hk, off = idx - blk * hk;
+            const int i = blk * k + off, j = blk * k + k - 1 - off;
+            if (j < L) {
+                u64 a = gk[i], b = gk[j];
+                if (a > b) { gk[i] = b; gk[j] = a; }
+            }
+        }
+        __syncthreads();
+        for (int j = k >> 2; j >= SORT_CAP; j >>= 1) {
+            for (int idx = tid; idx < (n_pad >> 1); idx += RF_THREADS) {
+                const int i = 2 * j * (idx / j) + (idx % j);
+                if (i + j < L) {
+                    u64 a = gk[i], b = gk[i + j];
+                    if (a > b) { gk[i] = b; gk[i + j] = a; }
+                }
+            }
+            __syncthreads();
+        }
+        for (int c = 0; c < n_chunks; ++c) {
+            const int base = c * SORT_CAP;
+            for (int i = tid; i < SORT_CAP; i += RF_THREADS) s[i] = (base + i < L) ? gk[base + i] : ~0ull;
+            __syncthreads();
+            bitonic_tail_smem(s, tid);
+            for (int i = tid; i < SORT_CAP; i += RF_THREADS)
+                if (base + i < L) gk[base + i] = s[i];
+            __syncthreads();
+        }
+    }
+}
+
+template <int GT_KIND>
+__global__ void __launch_bounds__(RF_THREADS) raster_fwd_kernel(
+    const eg_config cfg, int tw, const float4 *__restrict__ rec, const int32_t *__restrict__ tile_offsets,
+    u64 *__restrict__ keys, int32_t *__restrict__ flatten_ids, long long *__restrict__ isect_ids,
+    float *__restrict__ render0, float *__restrict__ alpha_out, int32_t *__restrict__ last_ids,
+    const void *__restrict__ gt, double *__restrict__ loss_sum, float *__restrict__ wpix,
+    const int32_t *__restrict__ status) {
+    __shared__ __align__(16) u64 skeys[SORT_CAP];
+    __shared__ __align__(16) float4 sA[RF_THREADS];  // mean2d.x, mean2d.y, opacity, sub-tile mask bits
+    __shared__ __align__(16) float4 sB[RF_THREADS];  // conic a, b, c, -
+    __shared__ float s_red[RF_THREADS / 32];
+
+    if (status[EG_ST_OVERFLOW]) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x;
+    const int tile_y = tile / tw, tile_x = tile - tile_y * tw;
+    const int start = tile_offsets[tile];
+    const int L = tile_offsets[tile + 1] - start;
+
+    // ---------------- phase A: sort the segment ----------------
+    const bool in_smem = L <= SORT_CAP;
+    if (L > 0) {
+        if (in_smem) {
+            int n_pad = 32;
+            while (n_pad < L) n_pad <<= 1;
+            for (int i = tid; i < n_pad; i += RF_THREADS) skeys[i] = i < L ? keys[start + i] : ~0ull;
+            __syncthreads();
+            bitonic_smem(skeys, n_pad, tid);
+            for (int i = tid; i < L; i += RF_THREADS) {
+                const u64 k = skeys[i];
+                flatten_ids[start + i] = (int32_t)(uint32_t)k;
+                keys[start + i] = k;
+                if (isect_ids) isect_ids[start + i] = ((long long)tile << 32) | (long long)(k >> 32);
+            }
+        } else {
+            sort_large(keys + start, L, skeys, tid);
+            for (int i = tid; i < L; i += RF_THREADS) {
+                const u64 k = keys[start + i];
+                flatten_ids[start + i] = (int32_t)(uint32_t)k;
+                if (isect_ids) isect_ids[start + i] = ((long long)tile << 32) | (long long)(k >> 32);
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---------------- phase B: compositing ----------------
+    const int sub_x = tile_x * EG_TILE + 8 * (warp & 1), sub_y = tile_y * EG_TILE + 4 * (warp >> 1);
+    const int pxi = sub_x + (lane & 7), pyi = sub_y + (lane >> 3);
+    const bool inside = pxi < cfg.width && pyi < cfg.height;
+    const float px = (float)pxi + 0.5f, py = (float)pyi + 0.5f;
+    const float X0 = (float)(tile_x * EG_TILE), Y0 = (float)(tile_y * EG_TILE);
+
+    float T = 1.0f, out = 0.0f;
+    int last = 0;
+    bool done = !inside;
+
+    for (int b0 = 0; b0 < L; b0 += RF_THREADS) {
+        // barrier doubles as "previous batch fully consumed" and the all-pixels-done early exit
+        if (__syncthreads_and(done)) break;
+        const int k = b0 + tid;
+        if (k < L) {
+            const int gid = in_smem ? (int)(uint32_t)skeys[k] : flatten_ids[start + k];
+            const float4 r0 = __ldg(rec + 2 * gid), r1 = __ldg(rec + 2 * gid + 1);
+            int mask = 0;
+            float hx, hy, tau;
+            if (eg_extent(r0.z, r1.x, r1.y, r1.z, hx, hy, tau)) {
+                const float xl = r0.x - hx, xh = r0.x + hx, yl = r0.y - hy, yh = r0.y + hy;
+                int cx = 0, cy = 0;
+                if (xh >= X0 + 0.5f && xl <= X0 + 7.5f) cx |= 1;
+                if (xh >= X0 + 8.5f && xl <= X0 + 15.5f) cx |= 2;
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                    if (yh >= Y0 + 4.0f * r + 0.5f && yl <= Y0 + 4.0f * r + 3.5f) cy |= 1 << r;
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                    if (cy & (1 << r)) mask |= cx << (2 * r);
+            }
+            sA[tid] = make_float4(r0.x, r0.y, r0.z, __int_as_float(mask));
+            sB[tid] = r1;
+        }
+        __syncthreads();
+        const int nb = min(RF_THREADS, L - b0);
+        for (int c = 0; c < nb && !__all_sync(0xffffffffu, done); c += 32) {
+            const int m = (c + lane < nb) ? __float_as_int(sA[c + lane].w) : 0;
+            unsigned bits = __ballot_sync(0xffffffffu, (m >> warp) & 1);
+            while (bits) {
+                const int t = c + __ffs(bits) - 1;
+                bits &= bits - 1;
+                const float4 a = sA[t];
+                const float4 cn = sB[t];
+                const float dx = a.x - px, dy = a.y - py;
+                const float sigma = eg_sigma(cn.x, cn.y, cn.z, dx, dy);
+                const float al = fminf(EG_ALPHA_MAX, __fmul_rn(a.z, eg_vis(sigma)));
+                if (done || sigma < 0.0f || al < EG_ALPHA_MIN) continue;
+                const float nT = T * (1.0f - al);
+                if (nT <= EG_T_MIN) { done = true; continue; }
+                out = fmaf(al, T, out);
+                T = nT;
+                last = start + b0 + t;
+            }
+        }
+    }
+
+    // ---------------- epilogue ----------------
+    float absd = 0.0f;
+    if (inside) {
+        const long long pix = (long long)pyi * cfg.width + pxi;
+        if (alpha_out) alpha_out[pix] = 1.0f - T;
+        if (render0) render0[pix] = out;
+        last_ids[pix] = last;
+        if (GT_KIND != EG_GT_NONE) {
+            float g;
+            if (GT_KIND == EG_GT_F32) g = __ldg(reinterpret_cast<const float *>(gt) + pix);
+            else g = __fdiv_rn((float)__ldg(reinterpret_cast<const unsigned char *>(gt) + pix), 255.0f);
+            const float rc = fminf(fmaxf(out, 0.0f), 1.0f);
+            const float d = rc - g;
+            absd = fabsf(d);
+            const float sgn = (d > 0.0f) ? 1.0f : ((d < 0.0f) ? -1.0f : 0.0f);
+            const float pass = (out >= 0.0f && out <= 1.0f) ? 1.0f : 0.0f;
+            if (wpix) wpix[pix] = sgn * pass * T;
+        }
+    }
+    if (GT_KIND != EG_GT_NONE && loss_sum != nullptr) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) absd += __shfl_xor_sync(0xffffffffu, absd, d);
+        if (lane == 0) s_red[warp] = absd;
+        __syncthreads();
+        if (tid == 0) {
+            float tsum = 0.0f;
+#pragma unroll
+            for (int w = 0; w < RF_THREADS / 32; ++w) tsum += s_red[w];
+            if (tsum != 0.0f) atomicAdd(loss_sum, (double)tsum);
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int eg_raster_fwd(const eg_config *cfg, const float *rec, const int32_t *tile_offsets, uint64_t *keys,
+                             int32_t *flatten_ids, int64_t *isect_ids, float *render0, float *alpha,
+                             int32_t *last_ids, const void *gt, int gt_kind, double *loss_sum, float *wpix,
+                             const int32_t *status, void *stream) {
+    if (cfg == nullptr || cfg->tile_size != EG_TILE) {
+        eg_set_error("eg_raster_fwd: tile_size must be %d", EG_TILE);
+        return 1;
+    }
+    if (last_ids == nullptr || flatten_ids == nullptr) {
+        eg_set_error("eg_raster_fwd: last_ids and flatten_ids are required");
+        return 1;
+    }
+    if (gt == nullptr) gt_kind = EG_GT_NONE;
+    int tw, th;
+    eg_tile_grid(cfg->width, cfg->height, cfg->tile_size, &tw, &th);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int grid = tw * th;
+#define EG_LAUNCH(KIND)                                                                                          \
+    raster_fwd_kernel<KIND><<<grid, RF_THREADS, 0, s>>>(*cfg, tw, (const float4 *)rec, tile_offsets, (u64 *)keys, \
+                                                        flatten_ids, (long long *)isect_ids, render0, alpha,      \
+                                                        last_ids, gt, loss_sum, wpix, status)
+    switch (gt_kind) {
+        case EG_GT_NONE: EG_LAUNCH(EG_GT_NONE); break;
+        case EG_GT_F32: EG_LAUNCH(EG_GT_F32); break;
+        case EG_GT_U8: EG_LAUNCH(EG_GT_U8); break;
+        default: eg_set_error("eg_raster_fwd: bad gt_kind %d", gt_kind); return 1;
+    }
+#undef EG_LAUNCH
+    return eg_check_launch("eg_raster_fwd");
+}

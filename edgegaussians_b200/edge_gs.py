@@ -1,0 +1,330 @@
+"""Host-side mirror of the reference model's hot path (same names, argument meaning and behaviour).
+
+Mirrors /root/reference/edgegaussians/models/edge_gs.py::EdgeGaussianSplatting for SURVEY.md
+section 8a rows a2, a8..a13:
+  poplutate_params (sic)        edge_gs.py:67-103      parameter container (means, log-scales, quats wxyz,
+                                                       logit-opacities) -- state-dict keys gauss_params.*
+  get_outputs / forward         edge_gs.py:197-286, 617-623
+  compute_image_masks / compute_weight_masks / compute_projection_loss   edge_gs.py:154-193, 288-324
+  update_absgrads / reset_absgrads                                       edge_gs.py:603-613
+  update_nearest_neighbors / compute_direction_loss / compute_ratio_loss edge_gs.py:326-380
+plus ``raster_step`` -- the B200-native fused iteration (activations + projection + binning + sort +
+compositing + "whole" L1 loss + both backward kernels + abs-grad accumulation, no autograd graph,
+no host sync, CUDA-graph capturable) that produces the same loss and ``.grad`` values as
+``forward -> compute_projection_loss("whole") -> backward -> update_absgrads`` of the reference
+(train_gaussians.py:81-102).
+
+Densify / cull / optimizer surgery, data parsing, PLY export and post-processing are out of scope
+(SURVEY.md section 2.1).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Union
+
+import torch
+
+from . import _lib
+from .cameras import BaseCamera
+from .engine import TILE, SplatState, get_engine, tile_grid, _p, _stream
+from .losses import MaskedL1Loss, WeightedL1Loss
+from .rasterization import rasterization
+
+
+@dataclass
+class EdgeGaussianSplattingConfig:
+    """Hot-path subset of edge_gs.py:16-54 (unknown keys are ignored, as dacite does there)."""
+    init_scales_val: float = 0.005
+    init_opacity_val: float = 0.08
+    edge_detection_threshold: float = 0.5
+    rasterize_mode: str = "antialiased"   # not a dataclass field in the reference: always "antialiased"
+
+    @classmethod
+    def from_dict(cls, data: Optional[dict]):
+        data = data or {}
+        names = {"init_scales_val", "init_opacity_val", "edge_detection_threshold"}
+        return cls(**{k: v for k, v in data.items() if k in names})
+
+
+def random_quat_tensor(N, generator: Optional[torch.Generator] = None):
+    """utils/misc_utils.py:36-51."""
+    u, v, w = (torch.rand(N, generator=generator) for _ in range(3))
+    return torch.stack([torch.sqrt(1 - u) * torch.sin(2 * math.pi * v), torch.sqrt(1 - u) * torch.cos(2 * math.pi * v),
+                        torch.sqrt(u) * torch.sin(2 * math.pi * w), torch.sqrt(u) * torch.cos(2 * math.pi * w)], dim=-1)
+
+
+class RasterStepWorkspace:
+    """Persistent device buffers of the fused iteration for fixed (N, W, H, capacity)."""
+
+    def __init__(self, N: int, W: int, H: int, capacity: int, device):
+        tw, th = tile_grid(W, H)
+        T = tw * th
+        f32, i32 = torch.float32, torch.int32
+        self.N, self.W, self.H, self.T, self.capacity = N, W, H, T, int(capacity)
+        self.rec = torch.empty((N, 8), dtype=f32, device=device)
+        self.gint = torch.empty((N, 2), dtype=i32, device=device)
+        # tile_counts | status share one allocation so a single memset clears both
+        self.zero_block = torch.zeros(T + 1 + _lib.EG_ST_WORDS, dtype=i32, device=device)
+        self.tile_counts = self.zero_block[:T + 1]
+        self.status = self.zero_block[T + 1:]
+        self.tile_offsets = torch.empty(T + 1, dtype=i32, device=device)
+        self.tile_cursor = torch.empty(T, dtype=i32, device=device)
+        self.keys = torch.empty(self.capacity, dtype=torch.int64, device=device)
+        self.flatten_ids = torch.empty(self.capacity, dtype=i32, device=device)
+        self.last_ids = torch.empty((H, W), dtype=i32, device=device)
+        self.wpix = torch.empty((H, W), dtype=f32, device=device)
+        self.render0 = torch.empty((H, W), dtype=f32, device=device)
+        self.grad2d = torch.zeros((N, 8), dtype=f32, device=device)
+        self.loss_sum = torch.zeros(1, dtype=torch.float64, device=device)
+        self.grads = torch.zeros(11 * N, dtype=f32, device=device)  # means | scales | quats | opacities
+
+
+class EdgeGaussianSplatting(torch.nn.Module):
+
+    def __init__(self, device="cuda"):
+        super().__init__()
+        self.device = device
+        self.step = 0
+        self.crop_box = None
+        self._ws: Optional[RasterStepWorkspace] = None
+        self.config = EdgeGaussianSplattingConfig()
+        self.viewcams: List[BaseCamera] = []
+        self.edge_masks: List[torch.Tensor] = []
+        self.weight_masks: List[torch.Tensor] = []
+
+    # ------------------------------------------------------------------ parameters (a13)
+    def poplutate_params(self, seed_points=None, viewcams=None, config=None, generator=None):
+        assert seed_points is not None, "Seed points need to be provided"
+        assert viewcams is not None, "Viewcams need to be provided"
+        assert config is not None, "Config needs to be provided"
+        self.config = config if isinstance(config, EdgeGaussianSplattingConfig) else EdgeGaussianSplattingConfig.from_dict(config)
+        cfg = self.config
+        means = torch.nn.Parameter(seed_points.float().to(self.device))
+        n = means.shape[0]
+        scales = torch.nn.Parameter(torch.log(torch.tensor([cfg.init_scales_val]).float().repeat(n, 3)).to(self.device))
+        opacities = torch.nn.Parameter(torch.logit(cfg.init_opacity_val * torch.ones(n, 1)).to(self.device))
+        quats = torch.nn.Parameter(random_quat_tensor(n, generator).to(self.device))
+        self.viewcams = viewcams
+        self.edge_masks, self.weight_masks = [], []
+        self.absgrads = torch.zeros(n, device=self.device)
+        self.absgrads_normalize_factor = 1.0
+        self.gauss_params = torch.nn.ParameterDict({"means": means, "scales": scales, "quats": quats, "opacities": opacities})
+        self.step = 0
+
+    populate_params = poplutate_params
+
+    def set_params(self, means, scales, quats, opacities, viewcams=None):
+        """Install given raw parameters (log-scales, logit-opacities [N,1]); used by tests and bench."""
+        dev = self.device
+        mk = lambda t: torch.nn.Parameter(torch.as_tensor(t, dtype=torch.float32).to(dev).contiguous())
+        self.gauss_params = torch.nn.ParameterDict({"means": mk(means), "scales": mk(scales), "quats": mk(quats),
+                                                    "opacities": mk(torch.as_tensor(opacities).reshape(-1, 1))})
+        self.absgrads = torch.zeros(self.num_points, device=dev)
+        self.absgrads_normalize_factor = 1.0
+        if viewcams is not None:
+            self.viewcams = viewcams
+
+    @property
+    def num_points(self):
+        return self.means.shape[0]
+
+    @property
+    def means(self):
+        return self.gauss_params["means"]
+
+    @property
+    def scales(self):
+        return self.gauss_params["scales"]
+
+    @property
+    def quats(self):
+        return self.gauss_params["quats"]
+
+    @property
+    def opacities(self):
+        return self.gauss_params["opacities"]
+
+    def get_gaussian_param_groups(self) -> Dict[str, List[torch.nn.Parameter]]:
+        return {name: [self.gauss_params[name]] for name in ["means", "scales", "quats", "opacities"]}
+
+    def load_state_dict(self, state_dict):  # edge_gs.py:625-633
+        self.gauss_params = torch.nn.ParameterDict({
+            k: torch.nn.Parameter(state_dict[f"gauss_params.{k}"].to(self.device)) for k in ["means", "scales", "quats", "opacities"]})
+
+    # ------------------------------------------------------------------ forward through the gsplat-shaped op (a2)
+    def get_outputs(self, camera: BaseCamera) -> Dict[str, Union[torch.Tensor, List]]:
+        if self.config.rasterize_mode not in ["antialiased", "classic"]:
+            raise ValueError("Unknown rasterize_mode: %s", self.config.rasterize_mode)
+        viewmat, K = camera.get_viewmat(), camera.get_K()
+        W, H = camera.width, camera.height
+        self.last_size = (H, W)
+        render, alpha, info = rasterization(
+            means=self.means, quats=self.quats, scales=torch.exp(self.scales),
+            opacities=torch.sigmoid(self.opacities).squeeze(-1), colors=None,  # colors == 1 (edge_gs.py:247)
+            viewmats=viewmat, Ks=K, width=W, height=H, tile_size=TILE, packed=False, near_plane=0.01,
+            far_plane=1e10, render_mode="RGB", sparse_grad=False, absgrad=True,
+            rasterize_mode=self.config.rasterize_mode)
+        if self.training and info["means2d"].requires_grad:
+            info["means2d"].retain_grad()
+        self.xys = info["means2d"]
+        self.radii = info["radii"][0]
+        self.info = info
+        rgb = torch.clamp(render[:, ..., :3], 0.0, 1.0)
+        return {"rgb": rgb.squeeze(0), "depth": None, "accumulation": alpha.squeeze(0)}
+
+    def forward(self, idx):
+        camera = self.viewcams[int(idx)]
+        outputs = self.get_outputs(camera)
+        self.step += 1
+        return outputs
+
+    # ------------------------------------------------------------------ losses (a8)
+    def compute_image_masks(self, gt_images):
+        for image in gt_images:
+            self.edge_masks.append((image >= self.config.edge_detection_threshold).to(self.device))
+
+    def compute_weight_masks(self):
+        assert self.edge_masks, "Edge masks need to be computed first"
+        self.weight_masks = []
+        for edge_mask in self.edge_masks:
+            n_edge, n_bg = edge_mask.sum(), (~edge_mask).sum()
+            w = torch.zeros_like(edge_mask, dtype=torch.float)
+            w[edge_mask] = (n_bg / (n_edge + n_bg)).float()
+            w[~edge_mask] = (n_edge / (n_edge + n_bg)).float()
+            self.weight_masks.append(w)
+
+    def compute_projection_loss(self, output_image, gt_image, image_index=None, strategy="bg_edge_ratio",
+                                bg_edge_pixel_ratio=1.0, loss_type: str = "l1", generator=None):
+        if strategy == "whole":
+            crit = torch.nn.functional.l1_loss if loss_type == "l1" else torch.nn.functional.mse_loss
+            return crit(output_image, gt_image)
+        if strategy == "bg_edge_ratio":
+            masked = MaskedL1Loss()
+            mask = self.edge_masks[int(image_index)]
+            edge_loss = masked(output_image, gt_image, mask)
+            num_bg = int(bg_edge_pixel_ratio * mask.sum())
+            n_bg = int((~mask).sum())
+            # reference quirk (edge_gs.py:303-310): a permutation of range(n_bg) unravelled as FLAT pixel ids
+            sel = torch.randperm(n_bg, generator=generator)[:num_bg].to(mask.device) % mask.numel()
+            bg_final = torch.zeros(mask.numel(), dtype=torch.bool, device=mask.device)
+            bg_final[sel] = True
+            return edge_loss + masked(output_image, gt_image, bg_final.view_as(mask))
+        if strategy == "weighted":
+            return WeightedL1Loss()(output_image, gt_image, self.weight_masks[int(image_index)])
+        raise ValueError(f"Unknown projection loss strategy: {strategy}")
+
+    # ------------------------------------------------------------------ abs-grad statistics (a9)
+    def reset_absgrads(self):
+        self.absgrads = torch.zeros(self.means.shape[0], device=self.device)
+        self.absgrads_normalize_factor = 1
+
+    def update_absgrads(self):
+        if self.absgrads.shape[0] != self.means.shape[0]:
+            self.reset_absgrads()
+        self.absgrads += self.xys.absgrad[0].norm(dim=-1)
+        self.absgrads_normalize_factor += 1
+
+    # ------------------------------------------------------------------ regularisers (a10-a12)
+    def update_nearest_neighbors(self):
+        from .knn import knn_indices
+        k = self.dir_loss_num_nn
+        points = self.means.data
+        points[torch.isnan(points)] = 0
+        kk = 2 * k if self.dir_loss_enforce_method == "enforce_half" else k
+        self.nn_indices = knn_indices(points, kk)  # [N,kk] int32 on device (the reference keeps float32 on CPU)
+
+    def compute_direction_loss(self):
+        from .regularisers import direction_loss
+        return direction_loss(self.means, self.quats, self.scales, self.nn_indices, self.dir_loss_num_nn,
+                              self.dir_loss_enforce_method == "enforce_half")
+
+    def compute_ratio_loss(self):
+        from .regularisers import ratio_loss
+        return ratio_loss(self.scales)
+
+    # ------------------------------------------------------------------ fused B200 iteration
+    def _workspace(self, W, H, capacity=None) -> RasterStepWorkspace:
+        N = self.num_points
+        ws = self._ws
+        eng = get_engine(self.means.device)
+        want = int(capacity) if capacity is not None else max(eng._ensure_capacity(N), ws.capacity if ws else 0)
+        if ws is None or (ws.N, ws.W, ws.H) != (N, W, H) or ws.capacity < want:
+            ws = RasterStepWorkspace(N, W, H, want, self.means.device)
+            self._ws = ws
+        return ws
+
+    def enqueue_raster_step(self, viewmat, K, W, H, gt, *, loss_weight=1.0, accumulate_absgrad=True, capacity=None,
+                            want_render=False) -> RasterStepWorkspace:
+        """Enqueue one fused forward+backward iteration on the current stream. No host sync, no
+        allocation after the first call for a given (N, W, H): CUDA-graph capturable.
+
+        Results (device): ws.loss_sum[0] / (W*H) = "whole" L1 loss; ws.grads = gradients of
+        loss_weight * loss w.r.t. (means | log-scales | quats | logit-opacities), also installed as
+        ``.grad`` views on the parameters; self.absgrads += ||means2d.absgrad|| when
+        ``accumulate_absgrad``; ws.status = (n_isects, overflow, ...)."""
+        lib = get_engine(self.means.device).lib
+        ws = self._workspace(W, H, capacity)
+        N = ws.N
+        cfg = _lib.EgConfig(n=N, width=W, height=H, tile_size=TILE, eps2d=0.3, near_plane=0.01, far_plane=1e10,
+                            radius_clip=0.0, antialiased=1 if self.config.rasterize_mode == "antialiased" else 0,
+                            raw_params=1, isect_capacity=ws.capacity)
+        c = ctypes.byref(cfg)
+        s = _stream()
+        gt_kind = _lib.EG_GT_U8 if gt.dtype == torch.uint8 else _lib.EG_GT_F32
+        means, quats, scales, opac = self.means.data, self.quats.data, self.scales.data, self.opacities.data
+        ws.zero_block.zero_()
+        ws.grad2d.zero_()
+        ws.loss_sum.zero_()
+        chk = _lib.check
+        chk(lib.eg_project_fwd(c, _p(means), _p(quats), _p(scales), _p(opac), None, _p(viewmat), _p(K), _p(ws.rec),
+                               _p(ws.gint), _p(ws.tile_counts), _p(ws.status), s), "eg_project_fwd")
+        chk(lib.eg_bin(c, _p(ws.rec), _p(ws.gint), _p(ws.tile_counts), _p(ws.tile_offsets), _p(ws.tile_cursor),
+                       _p(ws.keys), _p(ws.status), s), "eg_bin")
+        chk(lib.eg_raster_fwd(c, _p(ws.rec), _p(ws.tile_offsets), _p(ws.keys), _p(ws.flatten_ids), None,
+                              _p(ws.render0) if want_render else None, None, _p(ws.last_ids), _p(gt), gt_kind,
+                              _p(ws.loss_sum), _p(ws.wpix), _p(ws.status), s), "eg_raster_fwd")
+        chk(lib.eg_raster_bwd(c, _p(ws.rec), _p(ws.tile_offsets), _p(ws.flatten_ids), _p(ws.last_ids), None, None, 0,
+                              None, _p(ws.wpix), float(loss_weight) / float(W * H), _p(ws.grad2d), _p(ws.status), s),
+            "eg_raster_bwd")
+        g = ws.grads
+        chk(lib.eg_project_bwd(c, _p(means), _p(quats), _p(scales), _p(opac), _p(viewmat), _p(K), _p(ws.rec),
+                               _p(ws.gint), _p(ws.grad2d), None, _p(g[0:3 * N]), _p(g[6 * N:10 * N]),
+                               _p(g[3 * N:6 * N]), _p(g[10 * N:11 * N]),
+                               _p(self.absgrads) if accumulate_absgrad else None, s), "eg_project_bwd")
+        return ws
+
+    def install_grads(self, ws: RasterStepWorkspace):
+        N, g = ws.N, ws.grads
+        self.means.grad = g[0:3 * N].view(N, 3)
+        self.scales.grad = g[3 * N:6 * N].view(N, 3)
+        self.quats.grad = g[6 * N:10 * N].view(N, 4)
+        self.opacities.grad = g[10 * N:11 * N].view(N, 1)
+
+    def raster_step(self, idx_or_camera, gt, *, loss_weight=1.0, sync=True):
+        """Fused equivalent of train_gaussians.py:81-102 for the "whole" L1 strategy:
+        model(idx) -> compute_projection_loss -> (lambda * loss).backward() -> update_absgrads().
+        ``gt`` is the [H,W] edge map on the device: float32 in [0,1] or the raw uint8 image (the /255 of
+        train_gaussians.py:87 is then fused).  Returns the loss as a 0-dim device tensor.
+
+        ``sync=True`` validates the intersection capacity on the host (waits only for the status
+        words) and transparently re-runs with larger buffers when needed."""
+        cam = self.viewcams[int(idx_or_camera)] if not isinstance(idx_or_camera, BaseCamera) else idx_or_camera
+        viewmat, K = cam.viewmat.reshape(4, 4), cam.K.reshape(3, 3)
+        W, H = cam.width, cam.height
+        while True:
+            ws = self.enqueue_raster_step(viewmat, K, W, H, gt, loss_weight=loss_weight)
+            if not sync:
+                break
+            hs = ws.status.cpu()
+            if not int(hs[_lib.EG_ST_OVERFLOW]):
+                break
+            # roll back the abs-grad accumulation is unnecessary: overflowed runs are no-ops in raster kernels
+            eng = get_engine(self.means.device)
+            eng.capacity = max(eng.capacity, int(int(hs[_lib.EG_ST_NISECT]) * 1.25) + 1024)
+        self.install_grads(ws)
+        self.absgrads_normalize_factor += 1
+        self.step += 1
+        self.last_size = (H, W)
+        return (ws.loss_sum[0] / float(W * H)).float()

@@ -1,0 +1,232 @@
+"""Host-side driver of the splat kernels: owns the device buffers (torch tensors) and issues the
+C-ABI calls of include/edgegs.h on the current CUDA stream.  No arithmetic happens here.
+
+Stages and the reference code they replace:
+  project_bin  a3 + a4   gsplat projection + tile binning behind edge_gs.py:250-268
+  raster_fwd   a4 + a5   per-tile sort + compositing (+ a8 "whole" L1 loss, edge_gs.py:290-296)
+  raster_bwd   a6        compositing backward with abs-grad
+  project_bwd  a7 + a9   projection backward + activation VJPs + update_absgrads (edge_gs.py:603-613)
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import EG_GT_F32, EG_GT_NONE, EG_GT_U8, EG_ST_BADCOLOR, EG_ST_NISECT, EG_ST_OVERFLOW, EG_ST_WORDS, EgConfig
+
+TILE = 16
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def tile_grid(width: int, height: int):
+    return (width + TILE - 1) // TILE, (height + TILE - 1) // TILE
+
+
+@dataclass
+class SplatState:
+    """Everything one forward call produced that the backward (or gsplat's ``meta``) needs."""
+    cfg: EgConfig
+    N: int
+    width: int
+    height: int
+    tile_w: int
+    tile_h: int
+    rec: torch.Tensor            # [N,8] f32
+    gint: torch.Tensor           # [N,2] i32
+    tile_offsets: torch.Tensor   # [T+1] i32
+    keys: torch.Tensor           # [cap] i64 storage of the u64 keys
+    flatten_ids: torch.Tensor    # [cap] i32
+    status: torch.Tensor         # [8] i32
+    last_ids: Optional[torch.Tensor] = None   # [H,W] i32
+    alpha: Optional[torch.Tensor] = None      # [H,W] f32
+    render0: Optional[torch.Tensor] = None    # [H,W] f32
+    wpix: Optional[torch.Tensor] = None       # [H,W] f32
+    loss_sum: Optional[torch.Tensor] = None   # [1] f64
+    isect_ids: Optional[torch.Tensor] = None  # [cap] i64
+    grad2d: Optional[torch.Tensor] = None     # [N,8] f32, written by raster_bwd
+    n_isects: Optional[int] = None            # known on the host only after a status read
+
+
+class Engine:
+    """Per-device driver. Keeps an intersection-capacity estimate so steady-state calls never
+    reallocate; buffers handed to the caller are fresh allocations from torch's caching allocator."""
+
+    def __init__(self, device: torch.device):
+        if device.type != "cuda":
+            raise RuntimeError("edgegaussians_b200 runs on CUDA devices only (no CPU fallback)")
+        self.device = device
+        self.lib = _lib.load()
+        self.capacity = 0
+        self._host_status = torch.zeros(EG_ST_WORDS, dtype=torch.int32).pin_memory()
+        self._event = torch.cuda.Event()
+
+    # ------------------------------------------------------------------ helpers
+    def make_cfg(self, n, width, height, *, eps2d=0.3, near_plane=0.01, far_plane=1e10, radius_clip=0.0,
+                 antialiased=True, raw_params=False, capacity=0) -> EgConfig:
+        return EgConfig(n=n, width=width, height=height, tile_size=TILE, eps2d=eps2d, near_plane=near_plane,
+                        far_plane=far_plane, radius_clip=radius_clip, antialiased=1 if antialiased else 0,
+                        raw_params=1 if raw_params else 0, isect_capacity=capacity)
+
+    def _ensure_capacity(self, n: int) -> int:
+        if self.capacity <= 0:
+            self.capacity = max(1 << 16, 4 * n)
+        return self.capacity
+
+    # ------------------------------------------------------------------ forward
+    def project_bin(self, means, quats, scales, opacities, viewmat, K, width, height, *, colors=None,
+                    raw_params=False, antialiased=True, eps2d=0.3, near_plane=0.01, far_plane=1e10,
+                    radius_clip=0.0, sync=True, capacity: Optional[int] = None) -> SplatState:
+        """K1 + K2.  ``sync=True`` waits (on an event recorded right after the binning kernels, while
+        later work may already be queued) for the device-side intersection count and grows the key
+        buffers if they were too small; ``sync=False`` never touches the host (CUDA-graph safe) and
+        relies on ``capacity``; overflow is then reported by :meth:`read_status`."""
+        for name, t in (("means", means), ("quats", quats), ("scales", scales), ("opacities", opacities),
+                        ("viewmat", viewmat), ("K", K)):
+            _lib.require_cuda(t, name)
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError(f"{name} must be contiguous float32")
+        N = means.shape[0]
+        dev = means.device
+        tw, th = tile_grid(width, height)
+        T = tw * th
+        cap = int(capacity) if capacity is not None else self._ensure_capacity(N)
+        rec = torch.empty((N, 8), dtype=torch.float32, device=dev)
+        gint = torch.empty((N, 2), dtype=torch.int32, device=dev)
+        tile_counts = torch.zeros(T + 1, dtype=torch.int32, device=dev)
+        tile_offsets = torch.empty(T + 1, dtype=torch.int32, device=dev)
+        tile_cursor = torch.empty(T, dtype=torch.int32, device=dev)
+        status = torch.zeros(EG_ST_WORDS, dtype=torch.int32, device=dev)
+        while True:
+            cfg = self.make_cfg(N, width, height, eps2d=eps2d, near_plane=near_plane, far_plane=far_plane,
+                                radius_clip=radius_clip, antialiased=antialiased, raw_params=raw_params,
+                                capacity=cap)
+            keys = torch.empty(cap, dtype=torch.int64, device=dev)
+            flatten_ids = torch.empty(cap, dtype=torch.int32, device=dev)
+            _lib.check(self.lib.eg_project_fwd(ctypes.byref(cfg), _p(means), _p(quats), _p(scales), _p(opacities),
+                                               _p(colors), _p(viewmat), _p(K), _p(rec), _p(gint),
+                                               _p(tile_counts), _p(status), _stream()), "eg_project_fwd")
+            _lib.check(self.lib.eg_bin(ctypes.byref(cfg), _p(rec), _p(gint), _p(tile_counts), _p(tile_offsets),
+                                       _p(tile_cursor), _p(keys), _p(status), _stream()), "eg_bin")
+            st = SplatState(cfg=cfg, N=N, width=width, height=height, tile_w=tw, tile_h=th, rec=rec, gint=gint,
+                            tile_offsets=tile_offsets, keys=keys, flatten_ids=flatten_ids, status=status)
+            if not sync:
+                return st
+            self._host_status.copy_(status, non_blocking=True)
+            self._event.record()
+            self._event.synchronize()
+            hs = self._host_status
+            if int(hs[EG_ST_BADCOLOR]):
+                raise NotImplementedError(
+                    "edgegaussians_b200.rasterization supports colors == 1 only (the reference always passes "
+                    "torch.ones(N,3), edge_gs.py:247)")
+            n_isects = int(hs[EG_ST_NISECT])
+            st.n_isects = n_isects
+            if not int(hs[EG_ST_OVERFLOW]):
+                return st
+            # too small: grow geometrically and redo the binning (projection outputs are still valid)
+            cap = int(n_isects * 1.25) + 1024
+            self.capacity = max(self.capacity, cap)
+            status.zero_()
+            tile_counts.zero_()
+
+    def raster_fwd(self, st: SplatState, *, gt: Optional[torch.Tensor] = None, want_alpha=True, want_render=True,
+                   want_isect_ids=False, want_wpix=False) -> SplatState:
+        dev = st.rec.device
+        H, W = st.height, st.width
+        st.last_ids = torch.empty((H, W), dtype=torch.int32, device=dev)
+        st.alpha = torch.empty((H, W), dtype=torch.float32, device=dev) if want_alpha else None
+        st.render0 = torch.empty((H, W), dtype=torch.float32, device=dev) if want_render else None
+        if want_isect_ids:
+            st.isect_ids = torch.empty(st.keys.shape[0], dtype=torch.int64, device=dev)
+        gt_kind = EG_GT_NONE
+        if gt is not None:
+            _lib.require_cuda(gt, "gt")
+            if tuple(gt.shape[-2:]) != (H, W) or not gt.is_contiguous():
+                raise ValueError("gt must be a contiguous [H,W] tensor")
+            if gt.dtype == torch.float32:
+                gt_kind = EG_GT_F32
+            elif gt.dtype == torch.uint8:
+                gt_kind = EG_GT_U8
+            else:
+                raise ValueError("gt must be float32 in [0,1] or uint8")
+            st.loss_sum = torch.zeros(1, dtype=torch.float64, device=dev)
+            st.wpix = torch.empty((H, W), dtype=torch.float32, device=dev) if want_wpix else None
+        _lib.check(self.lib.eg_raster_fwd(ctypes.byref(st.cfg), _p(st.rec), _p(st.tile_offsets), _p(st.keys),
+                                          _p(st.flatten_ids), _p(st.isect_ids), _p(st.render0), _p(st.alpha),
+                                          _p(st.last_ids), _p(gt), gt_kind, _p(st.loss_sum), _p(st.wpix),
+                                          _p(st.status), _stream()), "eg_raster_fwd")
+        return st
+
+    # ------------------------------------------------------------------ backward
+    def raster_bwd(self, st: SplatState, *, v_render: Optional[torch.Tensor] = None,
+                   v_alpha: Optional[torch.Tensor] = None, seed_scale: float = 1.0,
+                   grad2d: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """K6. Either (v_render [H,W,C] and/or v_alpha [H,W]) or the fused-loss seed st.wpix."""
+        dev = st.rec.device
+        if grad2d is None:
+            grad2d = torch.zeros((st.N, 8), dtype=torch.float32, device=dev)
+        ch = 0
+        wpix = None
+        if v_render is None and v_alpha is None:
+            if st.wpix is None:
+                raise RuntimeError("raster_bwd needs v_render / v_alpha or a fused-loss forward (wpix)")
+            wpix = st.wpix
+        else:
+            if st.alpha is None:
+                raise RuntimeError("raster_bwd with v_render / v_alpha needs the forward alpha image")
+            if v_render is not None:
+                v_render = v_render.contiguous()
+                ch = v_render.shape[-1] if v_render.dim() == 3 else 1
+            if v_alpha is not None:
+                v_alpha = v_alpha.contiguous()
+        _lib.check(self.lib.eg_raster_bwd(ctypes.byref(st.cfg), _p(st.rec), _p(st.tile_offsets), _p(st.flatten_ids),
+                                          _p(st.last_ids), _p(st.alpha), _p(v_render), ch, _p(v_alpha), _p(wpix),
+                                          float(seed_scale), _p(grad2d), _p(st.status), _stream()), "eg_raster_bwd")
+        return grad2d
+
+    def project_bwd(self, st: SplatState, means, quats, scales, opacities, viewmat, K, grad2d, *, v_depths=None,
+                    out: Optional[torch.Tensor] = None, absgrad_accum: Optional[torch.Tensor] = None):
+        """K7. Returns (v_means [N,3], v_quats [N,4], v_scales [N,3], v_opacities [N]) as views of one
+        flat fp32 buffer laid out means|scales|quats|opacities (11*N floats) -- the buffer that is
+        all-reduced in the view-sharded multi-GPU step."""
+        N = st.N
+        if out is None:
+            out = torch.empty(11 * N, dtype=torch.float32, device=st.rec.device)
+        v_means = out[0:3 * N].view(N, 3)
+        v_scales = out[3 * N:6 * N].view(N, 3)
+        v_quats = out[6 * N:10 * N].view(N, 4)
+        v_opac = out[10 * N:11 * N]
+        _lib.check(self.lib.eg_project_bwd(ctypes.byref(st.cfg), _p(means), _p(quats), _p(scales), _p(opacities),
+                                           _p(viewmat), _p(K), _p(st.rec), _p(st.gint), _p(grad2d), _p(v_depths),
+                                           _p(v_means), _p(v_quats), _p(v_scales), _p(v_opac), _p(absgrad_accum),
+                                           _stream()), "eg_project_bwd")
+        return v_means, v_quats, v_scales, v_opac
+
+    # ------------------------------------------------------------------ status
+    def read_status(self, st: SplatState):
+        """Blocking read of the device status words -> dict (n_isects, overflow, bad_color)."""
+        hs = st.status.cpu()
+        return dict(n_isects=int(hs[EG_ST_NISECT]), overflow=bool(hs[EG_ST_OVERFLOW]), bad_color=bool(hs[EG_ST_BADCOLOR]))
+
+
+_engines = {}
+
+
+def get_engine(device) -> Engine:
+    device = torch.device(device)
+    if device.type == "cuda" and device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    if device not in _engines:
+        _engines[device] = Engine(device)
+    return _engines[device]

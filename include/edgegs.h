@@ -1,0 +1,136 @@
+/*
+ * edgegs.h -- C ABI of the B200-native edge-Gaussian splat path (libedgegs.so).
+ *
+ * This is the drop-in boundary for the ONE third-party call on the reference's hot path:
+ *     render, alpha, info = gsplat.rasterization(...)      /root/reference/edgegaussians/models/edge_gs.py:250-268
+ * plus the reference-owned arithmetic that surrounds it (activations edge_gs.py:253-254, clamp and
+ * channel select edge_gs.py:279 / train_gaussians.py:84, "whole" L1 loss edge_gs.py:290-296,
+ * update_absgrads edge_gs.py:603-613, direction / ratio regularisers edge_gs.py:346-380).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless marked "host";
+ *   - the caller owns every buffer, the library allocates nothing and keeps no state besides the
+ *     thread-local error string; all launches are asynchronous on `stream` (a cudaStream_t);
+ *   - return 0 = ok, non-zero = error, text via eg_last_error();
+ *   - no host synchronisation anywhere: the number of tile intersections stays on the device
+ *     (status[EG_ST_NISECT]); if it exceeds `isect_capacity` the flag status[EG_ST_OVERFLOW] is
+ *     raised, the raster kernels become no-ops and the caller re-runs with a larger capacity.
+ *
+ * Layouts (fp32 unless stated), N Gaussians, T = tile_w*tile_h tiles, P = W*H pixels, cap = isect_capacity:
+ *   means [N,3]  quats [N,4] (w,x,y,z; any norm)  scales [N,3]  opacities [N]
+ *       raw_params = 1: scales are LOG-scales and opacities are LOGITS as the reference stores
+ *       them (edge_gs.py:78-103), exp / sigmoid are fused; raw_params = 0: activated values
+ *       (the gsplat signature).
+ *   viewmat [16] row-major world->camera, K [9] row-major (cameras.py:84-96,129-135), on the device.
+ *   rec   [N,8]  = (mean2d.x, mean2d.y, opacity*comp, depth | conic.a, conic.b, conic.c, comp)
+ *                  gsplat's meta means2d/opacities/depths/conics are strided views of this record.
+ *   gint  [N,2] i32 = (radius, tiles_per_gauss); radius 0 = culled.
+ *   tile_counts [T+1] i32 (zeroed by caller before eg_project_fwd), tile_offsets [T+1] i32 (exclusive
+ *                  scan; [T] = n_isects), tile_cursor [T] i32 scratch.
+ *   keys  [cap] u64 = depth_bits<<32 | gaussian_id, unsorted per tile after eg_bin, sorted (per tile)
+ *                  after eg_raster_fwd.
+ *   flatten_ids [cap] i32 : gsplat's flatten_ids (sorted by tile, depth bits, id).
+ *   isect_ids   [cap] i64 : gsplat's isect_ids (tile<<32 | depth bits), optional (may be NULL).
+ *   alpha [P], render0 [P] (channel 0 of render; all three channels are equal because the reference
+ *                  passes colors == 1, edge_gs.py:247), last_ids [P] i32.
+ *   grad2d [N,8] = (v_mean2d.x, .y, absgrad.x, absgrad.y | v_conic.a, .b, .c, v_opacity_eff),
+ *                  accumulated with atomics: zero it before eg_raster_bwd.
+ *   status [EG_ST_WORDS] i32, zeroed by the caller before eg_project_fwd.
+ */
+#ifndef EDGEGS_H
+#define EDGEGS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EG_ABI_VERSION 1
+
+enum { EG_ST_NISECT = 0, EG_ST_OVERFLOW = 1, EG_ST_BADCOLOR = 2, EG_ST_NVISIBLE = 3, EG_ST_WORDS = 8 };
+
+enum { EG_GT_NONE = 0, EG_GT_F32 = 1, EG_GT_U8 = 2 };
+
+typedef struct eg_config {
+    int32_t n;            /* number of Gaussians                                   */
+    int32_t width;        /* image width  (camera.width,  edge_gs.py:239)          */
+    int32_t height;       /* image height (camera.height)                          */
+    int32_t tile_size;    /* must be 16 (BLOCK_WIDTH, edge_gs.py:233)              */
+    float eps2d;          /* 0.3                                                   */
+    float near_plane;     /* 0.01  (edge_gs.py:261)                                */
+    float far_plane;      /* 1e10  (edge_gs.py:262)                                */
+    float radius_clip;    /* 0.0                                                   */
+    int32_t antialiased;  /* 1 = rasterize_mode "antialiased" (edge_gs.py:50)      */
+    int32_t raw_params;   /* 1 = log-scales / logit-opacities, activations fused   */
+    int64_t isect_capacity; /* elements available in keys / flatten_ids / isect_ids */
+} eg_config;
+
+const char *eg_last_error(void);
+int eg_abi_version(void);
+/* tile grid for an image: replaces gsplat's tile_width / tile_height arithmetic (rendering.py) */
+int eg_tile_grid(int width, int height, int tile_size, int *tile_w, int *tile_h);
+
+/* K1 (+ K2 pass 1): projection forward + per-tile intersection counts.
+ * Replaces gsplat fully_fused_projection fwd + isect_tiles pass 1 behind edge_gs.py:250-268.
+ * colors: [N,3] or NULL; when given it is only VERIFIED to be all-ones (status[EG_ST_BADCOLOR]). */
+int eg_project_fwd(const eg_config *cfg, const float *means, const float *quats, const float *scales,
+                   const float *opacities, const float *colors, const float *viewmat, const float *K,
+                   float *rec, int32_t *gint, int32_t *tile_counts, int32_t *status, void *stream);
+
+/* K2 pass 2: exclusive scan of the tile counts + emission of (depth,id) keys into per-tile segments.
+ * Replaces gsplat cumsum + isect_tiles pass 2 + isect_offset_encode (the sort itself is per tile
+ * inside eg_raster_fwd). */
+int eg_bin(const eg_config *cfg, const float *rec, const int32_t *gint, const int32_t *tile_counts,
+           int32_t *tile_offsets, int32_t *tile_cursor, uint64_t *keys, int32_t *status, void *stream);
+
+/* K3 + K5 (+ a8 "whole" L1): per-tile sort, front-to-back compositing, optional fused edge-map loss.
+ * Replaces cub radix sort + gsplat rasterize_to_pixels fwd; with gt != NULL also
+ * clamp/select/L1 (edge_gs.py:279,290-296; train_gaussians.py:84-94):
+ *   loss_sum[0] += sum_p |clamp(render0) - gt|      (one fp64 word; caller divides by P)
+ *   wpix[p]      = sign(clamp(render0) - gt) * T_final   (the backward seed of pixel p, unscaled)
+ * gt_kind: EG_GT_F32 (values in [0,1]) or EG_GT_U8 (value/255, train_gaussians.py:87).
+ * Any of render0 / alpha / isect_ids / gt / loss_sum / wpix may be NULL. */
+int eg_raster_fwd(const eg_config *cfg, const float *rec, const int32_t *tile_offsets, uint64_t *keys,
+                  int32_t *flatten_ids, int64_t *isect_ids, float *render0, float *alpha,
+                  int32_t *last_ids, const void *gt, int gt_kind, double *loss_sum, float *wpix,
+                  const int32_t *status, void *stream);
+
+/* K6: compositing backward with abs-grad.  Replaces gsplat rasterize_to_pixels bwd.
+ * The seed of pixel p is  w_p = (sum_ch v_render[p,ch] + v_alpha[p]) * (1 - alpha[p])  when
+ * v_render/v_alpha/alpha are given (generic autograd path; v_render has `v_render_channels`
+ * interleaved channels), or  w_p = seed_scale * wpix[p]  (fused-loss path). */
+int eg_raster_bwd(const eg_config *cfg, const float *rec, const int32_t *tile_offsets,
+                  const int32_t *flatten_ids, const int32_t *last_ids, const float *alpha,
+                  const float *v_render, int v_render_channels, const float *v_alpha,
+                  const float *wpix, float seed_scale, float *grad2d, const int32_t *status,
+                  void *stream);
+
+/* K7 (+ activation VJPs + a9): projection backward.  Replaces gsplat fully_fused_projection bwd,
+ * the opacity*compensation VJP, Exp/Sigmoid backward and update_absgrads (edge_gs.py:603-613).
+ * grads are WRITTEN (not accumulated): v_means [N,3], v_quats [N,4], v_scales [N,3],
+ * v_opacities [N] w.r.t. the inputs as given (raw or activated per cfg->raw_params).
+ * v_depths may be NULL.  absgrad_accum [N] (may be NULL) += ||absgrad||_2 . */
+int eg_project_bwd(const eg_config *cfg, const float *means, const float *quats, const float *scales,
+                   const float *opacities, const float *viewmat, const float *K, const float *rec,
+                   const int32_t *gint, const float *grad2d, const float *v_depths, float *v_means,
+                   float *v_quats, float *v_scales, float *v_opacities, float *absgrad_accum,
+                   void *stream);
+
+/* a10 + a11: edge-direction and anisotropy regularisers, forward + backward in one pass.
+ * Replaces compute_direction_loss / compute_ratio_loss + autograd (edge_gs.py:346-380).
+ * nn_indices [N,nn_cols] i32 (nn_cols = k, or 2k for enforce_half); losses (2 fp64 words, accumulated):
+ * losses[0] += sum_i mean_n |m.d|
+ * (direction loss = 1 - losses[0]/N), losses[1] = sum_i ratio_i (ratio loss = losses[1]/N).
+ * Gradients are ACCUMULATED (atomics): dir_weight * dL_dir and ratio_weight * dL_ratio into
+ * v_means [N,3], v_quats [N,4], v_log_scales [N,3]. */
+int eg_reg_fwd_bwd(int n, const float *means, const float *quats, const float *log_scales,
+                   const int32_t *nn_indices, int nn_cols, int k, int enforce_half, float dir_weight,
+                   float ratio_weight, double *losses, float *v_means, float *v_quats,
+                   float *v_log_scales, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EDGEGS_H */
