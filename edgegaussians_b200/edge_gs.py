@@ -256,7 +256,7 @@ class EdgeGaussianSplatting(torch.nn.Module):
         return ws
 
     def enqueue_raster_step(self, viewmat, K, W, H, gt, *, loss_weight=1.0, accumulate_absgrad=True, capacity=None,
-                            want_render=False) -> RasterStepWorkspace:
+                            want_render=False, stage_cb=None) -> RasterStepWorkspace:
         """Enqueue one fused forward+backward iteration on the current stream. No host sync, no
         allocation after the first call for a given (N, W, H): CUDA-graph capturable.
 
@@ -274,25 +274,33 @@ class EdgeGaussianSplatting(torch.nn.Module):
         s = _stream()
         gt_kind = _lib.EG_GT_U8 if gt.dtype == torch.uint8 else _lib.EG_GT_F32
         means, quats, scales, opac = self.means.data, self.quats.data, self.scales.data, self.opacities.data
+        cb = stage_cb if stage_cb is not None else (lambda name: None)
+        cb("begin")
         ws.zero_block.zero_()
         ws.grad2d.zero_()
         ws.loss_sum.zero_()
+        cb("memset")
         chk = _lib.check
         chk(lib.eg_project_fwd(c, _p(means), _p(quats), _p(scales), _p(opac), None, _p(viewmat), _p(K), _p(ws.rec),
                                _p(ws.gint), _p(ws.tile_counts), _p(ws.status), s), "eg_project_fwd")
+        cb("project_fwd")
         chk(lib.eg_bin(c, _p(ws.rec), _p(ws.gint), _p(ws.tile_counts), _p(ws.tile_offsets), _p(ws.tile_cursor),
                        _p(ws.keys), _p(ws.status), s), "eg_bin")
+        cb("bin")
         chk(lib.eg_raster_fwd(c, _p(ws.rec), _p(ws.tile_offsets), _p(ws.keys), _p(ws.flatten_ids), None,
                               _p(ws.render0) if want_render else None, None, _p(ws.last_ids), _p(gt), gt_kind,
                               _p(ws.loss_sum), _p(ws.wpix), _p(ws.status), s), "eg_raster_fwd")
+        cb("raster_fwd")
         chk(lib.eg_raster_bwd(c, _p(ws.rec), _p(ws.tile_offsets), _p(ws.flatten_ids), _p(ws.last_ids), None, None, 0,
                               None, _p(ws.wpix), float(loss_weight) / float(W * H), _p(ws.grad2d), _p(ws.status), s),
             "eg_raster_bwd")
+        cb("raster_bwd")
         g = ws.grads
         chk(lib.eg_project_bwd(c, _p(means), _p(quats), _p(scales), _p(opac), _p(viewmat), _p(K), _p(ws.rec),
                                _p(ws.gint), _p(ws.grad2d), None, _p(g[0:3 * N]), _p(g[6 * N:10 * N]),
                                _p(g[3 * N:6 * N]), _p(g[10 * N:11 * N]),
                                _p(self.absgrads) if accumulate_absgrad else None, s), "eg_project_bwd")
+        cb("project_bwd")
         return ws
 
     def install_grads(self, ws: RasterStepWorkspace):

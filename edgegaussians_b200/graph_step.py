@@ -1,0 +1,81 @@
+"""CUDA-graph execution of the fused raster iteration (one graph per view slot).
+
+The whole iteration (3 memsets + 6 kernels, see edge_gs.enqueue_raster_step) is launch-latency
+sensitive at the reference's sizes (tens of microseconds of device work per kernel), so steady-state
+training replays a captured graph instead of re-issuing launches from Python.  Everything the graph
+reads that changes from step to step -- camera matrices and the edge map of the view -- lives in
+static per-slot device buffers that are refreshed by (async) copies before the replay.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from .edge_gs import EdgeGaussianSplatting, RasterStepWorkspace
+
+
+class GraphedRasterStep:
+    def __init__(self, model: EdgeGaussianSplatting, width: int, height: int, n_slots: int, gt_dtype=torch.uint8,
+                 loss_weight: float = 1.0, accumulate_absgrad: bool = True):
+        dev = model.means.device
+        self.model, self.W, self.H, self.n_slots = model, width, height, n_slots
+        self.loss_weight, self.accumulate_absgrad = loss_weight, accumulate_absgrad
+        self.viewmats = torch.zeros((n_slots, 4, 4), dtype=torch.float32, device=dev)
+        self.Ks = torch.zeros((n_slots, 3, 3), dtype=torch.float32, device=dev)
+        self.gts = torch.zeros((n_slots, height, width), dtype=gt_dtype, device=dev)
+        self.graphs: Dict[int, torch.cuda.CUDAGraph] = {}
+        self.ws: Optional[RasterStepWorkspace] = None
+        self._capacity = None
+
+    def set_view(self, slot: int, viewmat: torch.Tensor, K: torch.Tensor, gt: torch.Tensor, non_blocking=True):
+        """Refresh a slot from host (pinned) or device tensors."""
+        self.viewmats[slot].copy_(viewmat.reshape(4, 4), non_blocking=non_blocking)
+        self.Ks[slot].copy_(K.reshape(3, 3), non_blocking=non_blocking)
+        self.gts[slot].copy_(gt, non_blocking=non_blocking)
+
+    def _enqueue(self, slot: int, stage_cb=None):
+        return self.model.enqueue_raster_step(self.viewmats[slot], self.Ks[slot], self.W, self.H, self.gts[slot],
+                                              loss_weight=self.loss_weight, accumulate_absgrad=self.accumulate_absgrad,
+                                              capacity=self._capacity, stage_cb=stage_cb)
+
+    def calibrate(self, slots=None, margin: float = 1.3) -> int:
+        """Eager runs (with a host read of the status words) that size the intersection capacity for
+        the given slots; must be called before :meth:`capture`."""
+        need = 0
+        for slot in (range(self.n_slots) if slots is None else slots):
+            while True:
+                ws = self._enqueue(slot)
+                hs = ws.status.cpu()
+                n_isects = int(hs[0])
+                need = max(need, n_isects)
+                if not int(hs[1]):
+                    break
+                self._capacity = int(n_isects * margin) + 1024
+        self._capacity = max(int(need * margin) + 1024, 1 << 16)
+        self.ws = self.model._workspace(self.W, self.H, self._capacity)
+        self.model.install_grads(self.ws)
+        self.graphs.clear()
+        return need
+
+    def capture(self, slot: int, stage_cb=None) -> torch.cuda.CUDAGraph:
+        if self.ws is None:
+            self.calibrate([slot])
+        g = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g):
+            ws = self._enqueue(slot, stage_cb=stage_cb)
+        assert ws is self.ws, "workspace changed during capture"
+        if stage_cb is None:
+            self.graphs[slot] = g
+        return g
+
+    def replay(self, slot: int):
+        g = self.graphs.get(slot)
+        if g is None:
+            g = self.capture(slot)
+        g.replay()
+        return self.ws
+
+    def loss(self) -> torch.Tensor:
+        return (self.ws.loss_sum[0] / float(self.W * self.H)).float()

@@ -95,8 +95,10 @@ def test_forward_parity(case):
     assert a.min() >= 0.0 and a.max() <= 1.0 - 1e-4 + 1e-6
 
 
-def _check_grad(name, key, got, ref):
-    scale = np.abs(ref).max()
+def _check_grad(name, key, got, ref, floor=0.0):
+    """``floor``: absolute noise floor for tensors whose true value is a cancellation to ~0 (the
+    quaternion gradient of an isotropic Gaussian): fp32 rounding of O(1) terms, not an error."""
+    scale = max(np.abs(ref).max(), floor)
     err = np.abs(got - ref)
     tol = 1e-3 * np.abs(ref) + 2e-5 * scale
     frac_bad = float((err > tol).mean())
@@ -120,8 +122,9 @@ def test_backward_parity(case):
     loss.backward()
     _check_grad(name, "v_means2d", meta["means2d"].grad[0].cpu().numpy(), gref["v_means2d"])
     _check_grad(name, "absgrad", meta["means2d"].absgrad[0].cpu().numpy(), gref["v_means2d_abs"])
+    floor = 1e-6 * np.abs(gref["v_means"]).max()
     for key, t in (("v_means", tm), ("v_quats", tq), ("v_scales", ts), ("v_opacities", to)):
-        _check_grad(name, key, t.grad.cpu().numpy().reshape(gref[key].shape), gref[key])
+        _check_grad(name, key, t.grad.cpu().numpy().reshape(gref[key].shape), gref[key], floor)
     ag = meta["means2d"].absgrad[0].cpu().numpy()
     g2 = meta["means2d"].grad[0].cpu().numpy()
     assert (ag >= np.abs(g2) - 1e-5 * np.abs(ag).max()).all()
@@ -144,7 +147,7 @@ def test_fused_raster_step_parity(case, gt_dtype):
         loss = model.raster_step(0, gt)
         assert abs(float(loss) - ref["loss"]) <= 2e-6 + 1e-5 * abs(ref["loss"]), (float(loss), ref["loss"])
         _check_grad(name, "v_means", model.means.grad.cpu().numpy(), ref["v_means"])
-        _check_grad(name, "v_quats", model.quats.grad.cpu().numpy(), ref["v_quats"])
+        _check_grad(name, "v_quats", model.quats.grad.cpu().numpy(), ref["v_quats"], 1e-6 * np.abs(ref["v_means"]).max())
         _check_grad(name, "v_log_scales", model.scales.grad.cpu().numpy(), ref["v_log_scales"])
         _check_grad(name, "v_logit_opacities", model.opacities.grad.cpu().numpy()[:, 0], ref["v_logit_opacities"])
         _check_grad(name, "absgrads", model.absgrads.cpu().numpy(), (it + 1) * ref["absgrad_norm"])
@@ -171,7 +174,7 @@ def test_autograd_path_matches_fused_path():
     assert abs(float(loss_a) - float(loss_b)) < 1e-6
     for pa, pb, key in ((a.means, b.means, "means"), (a.quats, b.quats, "quats"), (a.scales, b.scales, "scales"),
                         (a.opacities, b.opacities, "opacities")):
-        _check_grad("auto-vs-fused", key, pa.grad.cpu().numpy(), pb.grad.cpu().numpy())
+        _check_grad("auto-vs-fused", key, pa.grad.cpu().numpy(), pb.grad.cpu().numpy(), 1e-6 * float(b.means.grad.abs().max()))
     _check_grad("auto-vs-fused", "absgrads", a.absgrads.cpu().numpy(), b.absgrads.cpu().numpy())
     assert a.radii.shape == (N,) and a.radii.dtype == torch.int32
 
