@@ -17,9 +17,8 @@ namespace {
 
 constexpr int SCAN_THREADS = 1024;
 
-__global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const int32_t *__restrict__ counts,
-                                                           int32_t *__restrict__ offsets,
-                                                           int32_t *__restrict__ cursor, int T,
+__global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(int32_t *__restrict__ counts,
+                                                           int32_t *__restrict__ offsets, int T,
                                                            int32_t *__restrict__ status, long long capacity) {
     __shared__ int32_t warp_sums[SCAN_THREADS / 32];
     __shared__ int32_t carry_s;
@@ -28,7 +27,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const int32_t *__res
     __syncthreads();
     for (int base = 0; base < T; base += SCAN_THREADS) {
         const int i = base + tid;
-        const int32_t v = i < T ? counts[i] : 0;
+        const int32_t v = i < T ? counts[(size_t)i * EG_CNT_STRIDE] : 0;
         int32_t x = v;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -51,7 +50,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const int32_t *__res
         const int32_t incl = x + (wid > 0 ? warp_sums[wid - 1] : 0) + carry;
         if (i < T) {
             offsets[i] = incl - v;
-            cursor[i] = incl - v;
+            counts[(size_t)i * EG_CNT_STRIDE + 1] = incl - v;  // append cursor of the tile
         }
         __syncthreads();
         if (tid == SCAN_THREADS - 1) carry_s = incl;
@@ -66,7 +65,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const int32_t *__res
 }
 
 __global__ void __launch_bounds__(256) emit_kernel(int n, const float4 *__restrict__ rec,
-                                                   const int2 *__restrict__ gint, int32_t *__restrict__ cursor,
+                                                   const int2 *__restrict__ gint, int32_t *__restrict__ counts,
                                                    unsigned long long *__restrict__ keys, long long capacity,
                                                    int tw, int th) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -79,15 +78,15 @@ __global__ void __launch_bounds__(256) emit_kernel(int n, const float4 *__restri
     const unsigned long long key = ((unsigned long long)__float_as_uint(r0.w) << 32) | (unsigned int)g;
     for (uint32_t i = y0; i < y1; ++i)
         for (uint32_t j = x0; j < x1; ++j) {
-            const long long pos = atomicAdd(cursor + (i * tw + j), 1);
+            const long long pos = atomicAdd(counts + (size_t)(i * tw + j) * EG_CNT_STRIDE + 1, 1);
             if (pos < capacity) keys[pos] = key;
         }
 }
 
 }  // namespace
 
-extern "C" int eg_bin(const eg_config *cfg, const float *rec, const int32_t *gint, const int32_t *tile_counts,
-                      int32_t *tile_offsets, int32_t *tile_cursor, uint64_t *keys, int32_t *status, void *stream) {
+extern "C" int eg_bin(const eg_config *cfg, const float *rec, const int32_t *gint, int32_t *tile_counts,
+                      int32_t *tile_offsets, uint64_t *keys, int32_t *status, void *stream) {
     if (cfg == nullptr || cfg->tile_size != EG_TILE) {
         eg_set_error("eg_bin: tile_size must be %d", EG_TILE);
         return 1;
@@ -95,11 +94,11 @@ extern "C" int eg_bin(const eg_config *cfg, const float *rec, const int32_t *gin
     int tw, th;
     eg_tile_grid(cfg->width, cfg->height, cfg->tile_size, &tw, &th);
     cudaStream_t s = (cudaStream_t)stream;
-    scan_kernel<<<1, SCAN_THREADS, 0, s>>>(tile_counts, tile_offsets, tile_cursor, tw * th, status,
+    scan_kernel<<<1, SCAN_THREADS, 0, s>>>(tile_counts, tile_offsets, tw * th, status,
                                            (long long)cfg->isect_capacity);
     if (int e = eg_check_launch("eg_bin/scan")) return e;
     if (cfg->n > 0) {
-        emit_kernel<<<(cfg->n + 255) / 256, 256, 0, s>>>(cfg->n, (const float4 *)rec, (const int2 *)gint, tile_cursor,
+        emit_kernel<<<(cfg->n + 255) / 256, 256, 0, s>>>(cfg->n, (const float4 *)rec, (const int2 *)gint, tile_counts,
                                                          (unsigned long long *)keys, (long long)cfg->isect_capacity,
                                                          tw, th);
         if (int e = eg_check_launch("eg_bin/emit")) return e;

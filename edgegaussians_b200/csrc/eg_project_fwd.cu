@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(256) project_fwd_kernel(
     rec[2 * g + 1] = r1;
     gint[g] = make_int2(radius_i, ntiles);
     for (uint32_t i = y0; i < y1; ++i)
-        for (uint32_t j = x0; j < x1; ++j) atomicAdd(tile_counts + (i * tw + j), 1);
+        for (uint32_t j = x0; j < x1; ++j) atomicAdd(tile_counts + (size_t)(i * tw + j) * EG_CNT_STRIDE, 1);
 }
 
 }  // namespace

@@ -9,48 +9,33 @@
 //     render_ch(p) = sum_i alpha_i T_i = 1 - prod_i (1 - alpha_i) = alpha(p)
 // and therefore   d out(p) / d alpha_k = T_final(p) / (1 - alpha_k)   for every composited k:
 // gsplat's  (color*T_k - buffer_k*ra_k)  is this quantity computed with cancellation.  The backward
-// is thus a plain sum over (pixel, Gaussian) pairs with no ordering dependence, and is organised the
-// other way round: one THREAD per (tile, Gaussian), looping over the pixels of the tile that the
-// Gaussian's alpha >= 1/255 footprint can reach.  Per-Gaussian gradients accumulate in registers --
-// no warp reductions -- and leave as two 128-bit vector reductions (red.global.add.v4.f32) per
-// (tile, Gaussian).  Footprints larger than BIG_AREA pixels are deferred to a cooperative pass in
-// which a whole warp shares one Gaussian.  The per-pixel state (seed * T_final, last contributor)
-// lives in shared memory.
+// is thus a plain sum over (pixel, Gaussian) pairs with no ordering dependence, and is organised
+// Gaussian-major with a BALANCED pair distribution:
+//   1. batches of 256 Gaussians of the tile are staged in shared memory together with the pixel
+//      rectangle (inside the tile) their alpha >= 1/255 footprint can reach;
+//   2. a block-wide prefix sum over the rectangle areas linearises all (Gaussian, pixel) pairs of the
+//      batch; every thread takes an equal contiguous slice of that pair list and walks it,
+//      accumulating the 8 per-Gaussian gradient values in registers (no warp reductions);
+//   3. whenever the walk leaves a Gaussian its partial sums leave as two 128-bit vector reductions
+//      (red.global.add.v4.f32) -- about two flushes per thread.
+// The per-pixel state (seed * T_final, last contributor) lives in shared memory.
 #include "eg_common.cuh"
 
 namespace {
 
 constexpr int RB_THREADS = 256;
-constexpr int BIG_AREA = 48;    // footprints (pixels inside the tile) above this go to the warp pass
-constexpr int BIG_QUEUE = 1024; // per-CTA queue of deferred Gaussians (overflow handled inline)
 
 struct PairAcc {
     float gx, gy, ax, ay, ca, cb, cc, go;
 };
 
-// contribution of pixel (w = seed*T_final, valid) to Gaussian (mx,my,o | A,B,C)
-__device__ __forceinline__ void pair_grad(float w, float mx, float my, float o, float A, float B, float C,
-                                          float px, float py, PairAcc &acc) {
-    const float dx = mx - px, dy = my - py;
-    const float sigma = eg_sigma(A, B, C, dx, dy);
-    const float vis = eg_vis(sigma);
-    const float ov = __fmul_rn(o, vis);
-    const float al = fminf(EG_ALPHA_MAX, ov);
-    if (sigma < 0.0f || al < EG_ALPHA_MIN) return;
-    const float ra = __fdividef(1.0f, 1.0f - al);
-    const float v_alpha = w * ra;
-    if (ov <= EG_ALPHA_MAX) {
-        const float v_sigma = -ov * v_alpha;
-        const float gx = v_sigma * (A * dx + B * dy);
-        const float gy = v_sigma * (B * dx + C * dy);
-        acc.gx += gx;
-        acc.gy += gy;
-        acc.ax += fabsf(gx);
-        acc.ay += fabsf(gy);
-        acc.ca += 0.5f * v_sigma * dx * dx;
-        acc.cb += v_sigma * dx * dy;
-        acc.cc += 0.5f * v_sigma * dy * dy;
-        acc.go += vis * v_alpha;
+__device__ __forceinline__ void acc_zero(PairAcc &a) { a.gx = a.gy = a.ax = a.ay = a.ca = a.cb = a.cc = a.go = 0.0f; }
+
+__device__ __forceinline__ void acc_flush(const PairAcc &a, float *__restrict__ grad2d, int gid) {
+    if (a.go != 0.0f || a.ax != 0.0f || a.ay != 0.0f || a.ca != 0.0f || a.cc != 0.0f) {
+        float *dst = grad2d + 8ll * gid;
+        eg_red_add_v4(dst, a.gx, a.gy, a.ax, a.ay);
+        eg_red_add_v4(dst + 4, a.ca, a.cb, a.cc, a.go);
     }
 }
 
@@ -60,10 +45,11 @@ __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
     const float *__restrict__ v_render, int vr_ch, const float *__restrict__ v_alpha,
     const float *__restrict__ wpix, float seed_scale, float *__restrict__ grad2d,
     const int32_t *__restrict__ status) {
-    __shared__ float s_w[EG_TILE * EG_TILE];    // seed * T_final per pixel (0 outside the image)
-    __shared__ int s_last[EG_TILE * EG_TILE];   // last contributor, relative to the segment start
-    __shared__ int s_big[BIG_QUEUE];
-    __shared__ int s_nbig;
+    __shared__ float2 s_pix[EG_TILE * EG_TILE];        // (seed * T_final, last contributor rel. to segment start)
+    __shared__ __align__(16) float4 sA[RB_THREADS];    // mean2d.x, mean2d.y, opacity, packed pixel rectangle
+    __shared__ __align__(16) float4 sB[RB_THREADS];    // conic a, b, c, gaussian id
+    __shared__ int s_off[RB_THREADS + 1];              // exclusive prefix of the rectangle areas
+    __shared__ int s_wsum[RB_THREADS / 32];
 
     if (status[EG_ST_OVERFLOW]) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -92,90 +78,108 @@ __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
             }
             last = __ldg(last_ids + pix) - start;
         }
-        s_w[tid] = w;
-        s_last[tid] = last;
-        if (tid == 0) s_nbig = 0;
+        s_pix[tid] = make_float2(w, __int_as_float(last));
     }
-    __syncthreads();
-
     const int xmax = min(EG_TILE, cfg.width - X0) - 1, ymax = min(EG_TILE, cfg.height - Y0) - 1;
 
-    // ---- pass 1: one thread per (tile, Gaussian) ----
-    for (int k = tid; k < L; k += RB_THREADS) {
-        const int gid = __ldg(flatten_ids + start + k);
-        const float4 r0 = __ldg(rec + 2 * gid), r1 = __ldg(rec + 2 * gid + 1);
-        float hx, hy, tau;
-        if (!eg_extent(r0.z, r1.x, r1.y, r1.z, hx, hy, tau)) continue;
-        // pixel j (centre j + 0.5) is reachable iff  mx - hx <= j + 0.5 <= mx + hx
-        const float fx0 = r0.x - (float)X0, fy0 = r0.y - (float)Y0;
-        const int xlo = max(0, (int)ceilf(fminf(fx0 - hx - 0.5f, 64.0f)));
-        const int xhi = min(xmax, (int)floorf(fmaxf(fx0 + hx - 0.5f, -64.0f)));
-        const int ylo = max(0, (int)ceilf(fminf(fy0 - hy - 0.5f, 64.0f)));
-        const int yhi = min(ymax, (int)floorf(fmaxf(fy0 + hy - 0.5f, -64.0f)));
-        if (xlo > xhi || ylo > yhi) continue;
-        const int area = (xhi - xlo + 1) * (yhi - ylo + 1);
-        if (area > BIG_AREA) {
-            const int slot = atomicAdd(&s_nbig, 1);
-            if (slot < BIG_QUEUE) {
-                s_big[slot] = k;
-                continue;
+    for (int b0 = 0; b0 < L; b0 += RB_THREADS) {
+        __syncthreads();  // s_pix visible / previous batch fully consumed
+        // ---- 1. stage one Gaussian per thread, with its reachable pixel rectangle ----
+        const int k = b0 + tid;
+        int area = 0;
+        if (k < L) {
+            const int gid = __ldg(flatten_ids + start + k);
+            const float4 r0 = __ldg(rec + 2 * gid), r1 = __ldg(rec + 2 * gid + 1);
+            float hx, hy, tau;
+            int rect = 0;
+            if (eg_extent(r0.z, r1.x, r1.y, r1.z, hx, hy, tau)) {
+                // pixel j (centre j + 0.5) is reachable iff  mx - hx <= j + 0.5 <= mx + hx
+                const float fx0 = r0.x - (float)X0, fy0 = r0.y - (float)Y0;
+                const int xlo = max(0, (int)ceilf(fminf(fx0 - hx - 0.5f, 64.0f)));
+                const int xhi = min(xmax, (int)floorf(fmaxf(fx0 + hx - 0.5f, -64.0f)));
+                const int ylo = max(0, (int)ceilf(fminf(fy0 - hy - 0.5f, 64.0f)));
+                const int yhi = min(ymax, (int)floorf(fmaxf(fy0 + hy - 0.5f, -64.0f)));
+                if (xlo <= xhi && ylo <= yhi) {
+                    area = (xhi - xlo + 1) * (yhi - ylo + 1);
+                    rect = xlo | (xhi << 4) | (ylo << 8) | (yhi << 12);
+                }
             }
+            sA[tid] = make_float4(r0.x, r0.y, r0.z, __int_as_float(rect));
+            sB[tid] = make_float4(r1.x, r1.y, r1.z, __int_as_float(gid));
         }
-        PairAcc acc = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int y = ylo; y <= yhi; ++y) {
-            const float py = (float)(Y0 + y) + 0.5f;
-            for (int x = xlo; x <= xhi; ++x) {
-                const int p = y * EG_TILE + x;
-                const float w = s_w[p];
-                if (w == 0.0f || k > s_last[p]) continue;
-                pair_grad(w, r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, (float)(X0 + x) + 0.5f, py, acc);
-            }
-        }
-        if (acc.ax != 0.0f || acc.ay != 0.0f || acc.go != 0.0f || acc.ca != 0.0f || acc.cc != 0.0f) {
-            float *dst = grad2d + 8ll * gid;
-            eg_red_add_v4(dst, acc.gx, acc.gy, acc.ax, acc.ay);
-            eg_red_add_v4(dst + 4, acc.ca, acc.cb, acc.cc, acc.go);
-        }
-    }
-    __syncthreads();
-
-    // ---- pass 2: large footprints, one warp per Gaussian, lanes = pixels of the tile ----
-    const int nbig = min(s_nbig, BIG_QUEUE);
-    for (int q = warp; q < nbig; q += RB_THREADS / 32) {
-        const int k = s_big[q];
-        const int gid = __ldg(flatten_ids + start + k);
-        const float4 r0 = __ldg(rec + 2 * gid), r1 = __ldg(rec + 2 * gid + 1);
-        float hx, hy, tau;
-        eg_extent(r0.z, r1.x, r1.y, r1.z, hx, hy, tau);
-        const float fx0 = r0.x - (float)X0, fy0 = r0.y - (float)Y0;
-        const int xlo = max(0, (int)ceilf(fminf(fx0 - hx - 0.5f, 64.0f)));
-        const int xhi = min(xmax, (int)floorf(fmaxf(fx0 + hx - 0.5f, -64.0f)));
-        const int ylo = max(0, (int)ceilf(fminf(fy0 - hy - 0.5f, 64.0f)));
-        const int yhi = min(ymax, (int)floorf(fmaxf(fy0 + hy - 0.5f, -64.0f)));
-        const int wbox = xhi - xlo + 1, area = wbox * (yhi - ylo + 1);
-        PairAcc acc = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int i = lane; i < area; i += 32) {
-            const int y = ylo + i / wbox, x = xlo + i % wbox;
-            const int p = y * EG_TILE + x;
-            const float w = s_w[p];
-            if (w == 0.0f || k > s_last[p]) continue;
-            pair_grad(w, r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, (float)(X0 + x) + 0.5f, (float)(Y0 + y) + 0.5f, acc);
-        }
+        // ---- 2. block-wide exclusive prefix sum of the areas ----
+        int incl = area;
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            acc.gx += __shfl_xor_sync(0xffffffffu, acc.gx, d);
-            acc.gy += __shfl_xor_sync(0xffffffffu, acc.gy, d);
-            acc.ax += __shfl_xor_sync(0xffffffffu, acc.ax, d);
-            acc.ay += __shfl_xor_sync(0xffffffffu, acc.ay, d);
-            acc.ca += __shfl_xor_sync(0xffffffffu, acc.ca, d);
-            acc.cb += __shfl_xor_sync(0xffffffffu, acc.cb, d);
-            acc.cc += __shfl_xor_sync(0xffffffffu, acc.cc, d);
-            acc.go += __shfl_xor_sync(0xffffffffu, acc.go, d);
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += y;
         }
-        if (lane == 0 && (acc.ax != 0.0f || acc.ay != 0.0f || acc.go != 0.0f || acc.ca != 0.0f || acc.cc != 0.0f)) {
-            float *dst = grad2d + 8ll * gid;
-            eg_red_add_v4(dst, acc.gx, acc.gy, acc.ax, acc.ay);
-            eg_red_add_v4(dst + 4, acc.ca, acc.cb, acc.cc, acc.go);
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        int wbase = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < RB_THREADS / 32; ++w) {
+            const int v = s_wsum[w];
+            if (w < warp) wbase += v;
+            total += v;
+        }
+        s_off[tid] = wbase + incl - area;
+        if (tid == 0) s_off[RB_THREADS] = total;
+        __syncthreads();
+        if (total == 0) continue;
+
+        // ---- 3. every thread walks an equal slice of the pair list ----
+        const int chunk = (total + RB_THREADS - 1) / RB_THREADS;
+        int p = tid * chunk;
+        const int p_end = min(total, p + chunk);
+        if (p >= p_end) continue;
+        // binary search: largest g with s_off[g] <= p  (areas may be 0, so take the last such g)
+        int lo = 0, hi = RB_THREADS;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (s_off[mid] <= p) lo = mid; else hi = mid;
+        }
+        int g = lo;
+        while (p < p_end) {
+            // (re)load the Gaussian g; skip empty ones
+            while (s_off[g + 1] <= p) ++g;
+            const float4 a = sA[g], cn = sB[g];
+            const int rect = __float_as_int(a.w);
+            const int xlo = rect & 15, xhi = (rect >> 4) & 15, ylo = (rect >> 8) & 15;
+            const int wbox = xhi - xlo + 1;
+            const int local = p - s_off[g];
+            int y = ylo + local / wbox, x = xlo + local - (local / wbox) * wbox;
+            const int seg_end = min(p_end, s_off[g + 1]);
+            const int kk = b0 + g;  // position of the Gaussian in the tile's sorted list
+            PairAcc acc;
+            acc_zero(acc);
+            for (; p < seg_end; ++p) {
+                const float2 pw = s_pix[y * EG_TILE + x];
+                if (pw.x != 0.0f && kk <= __float_as_int(pw.y)) {
+                    const float dx = a.x - ((float)(X0 + x) + 0.5f), dy = a.y - ((float)(Y0 + y) + 0.5f);
+                    const float sigma = eg_sigma(cn.x, cn.y, cn.z, dx, dy);
+                    const float vis = eg_vis(sigma);
+                    const float ov = __fmul_rn(a.z, vis);
+                    const float al = fminf(EG_ALPHA_MAX, ov);
+                    if (sigma >= 0.0f && al >= EG_ALPHA_MIN && ov <= EG_ALPHA_MAX) {
+                        const float ra = __fdividef(1.0f, 1.0f - al);
+                        const float v_al = pw.x * ra;
+                        const float v_sigma = -ov * v_al;
+                        const float gx = v_sigma * (cn.x * dx + cn.y * dy);
+                        const float gy = v_sigma * (cn.y * dx + cn.z * dy);
+                        acc.gx += gx;
+                        acc.gy += gy;
+                        acc.ax += fabsf(gx);
+                        acc.ay += fabsf(gy);
+                        acc.ca += 0.5f * v_sigma * dx * dx;
+                        acc.cb += v_sigma * dx * dy;
+                        acc.cc += 0.5f * v_sigma * dy * dy;
+                        acc.go += vis * v_al;
+                    }
+                }
+                if (++x > xhi) { x = xlo; ++y; }
+            }
+            acc_flush(acc, grad2d, __float_as_int(cn.w));
         }
     }
 }

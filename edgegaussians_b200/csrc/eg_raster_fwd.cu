@@ -1,8 +1,11 @@
 // eg_raster_fwd.cu -- K3 + K5 (+ fused "whole" L1 edge-map loss): one CTA per 16x16 tile.
 //
-//   phase A  sort the tile's (depth_bits<<32 | id) keys (shared-memory bitonic network; segments
-//            longer than SORT_CAP use a chunked shared/global hybrid of the same network) and write
-//            gsplat's flatten_ids / isect_ids for the segment;
+//   phase A  sort the tile's (depth_bits<<32 | id) keys.  Up to 2048 keys live in REGISTERS (1..8 per
+//            thread): bitonic exchanges at distance < 32 are warp shuffles, distances 32..128 go
+//            through a double-buffered shared-memory exchange (one barrier each), distances >= 256
+//            are register-to-register inside the thread.  Longer segments (rare) fall back to a
+//            chunked shared/global bitonic network.  gsplat's flatten_ids / isect_ids are written
+//            from the sorted keys;
 //   phase B  front-to-back alpha compositing, SURVEY.md Appendix A.3 (gsplat==1.0.0
 //            rasterize_to_pixels fwd behind /root/reference/edgegaussians/models/edge_gs.py:250-268):
 //            batches of 256 Gaussian records are staged in shared memory; each warp owns an 8x4
@@ -19,27 +22,109 @@
 namespace {
 
 constexpr int RF_THREADS = 256;
-constexpr int SORT_CAP = 2048;  // keys sorted entirely in shared memory (16 KB)
+constexpr int SORT_CAP = 2048;  // keys sorted on chip (registers + 2 x 16 KB exchange buffers)
 typedef unsigned long long u64;
 
+__device__ __forceinline__ u64 u64min(u64 a, u64 b) { return a < b ? a : b; }
+__device__ __forceinline__ u64 u64max(u64 a, u64 b) { return a > b ? a : b; }
+
+// ---------------------------------------------------------------------------------------------
+// Register-resident bitonic sort of n_pad = 256*E keys (E == 1: n_pad may be 32..256).
+// Element index of key[r] in thread tid is e = r*256 + tid.  Standard network: step (k, j) pairs e
+// with e^j, ascending where (e & k) == 0.
+// ---------------------------------------------------------------------------------------------
+template <int E>
+__device__ __forceinline__ void sort_regs(u64 (&key)[E], const int n_pad, u64 *sbuf, const int tid) {
+    int buf = 0;
+    for (int k = 2; k <= n_pad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 256) {  // partner is another register of this thread (only when E > 1)
+                const int jr = j >> 8;
+#pragma unroll
+                for (int jc = 1; jc < E; jc <<= 1) {
+                    if (jr == jc) {
+#pragma unroll
+                        for (int r = 0; r < E; ++r) {
+                            if ((r & jc) == 0) {
+                                const bool up = (((r << 8) | tid) & k) == 0;
+                                const u64 lo = u64min(key[r], key[r | jc]), hi = u64max(key[r], key[r | jc]);
+                                key[r] = up ? lo : hi;
+                                key[r | jc] = up ? hi : lo;
+                            }
+                        }
+                    }
+                }
+            } else if (j >= 32) {  // partner lives in another warp: shared-memory exchange
+                u64 *sb = sbuf + buf * SORT_CAP;
+#pragma unroll
+                for (int r = 0; r < E; ++r) sb[(r << 8) | tid] = key[r];
+                __syncthreads();
+#pragma unroll
+                for (int r = 0; r < E; ++r) {
+                    const int e = (r << 8) | tid;
+                    const u64 p = sb[e ^ j];
+                    const bool keep_min = ((e & k) == 0) == ((e & j) == 0);
+                    key[r] = keep_min ? u64min(key[r], p) : u64max(key[r], p);
+                }
+                buf ^= 1;
+            } else {  // partner is a lane of the same warp
+#pragma unroll
+                for (int r = 0; r < E; ++r) {
+                    const int e = (r << 8) | tid;
+                    const u64 p = __shfl_xor_sync(0xffffffffu, key[r], j);
+                    const bool keep_min = ((e & k) == 0) == ((e & j) == 0);
+                    key[r] = keep_min ? u64min(key[r], p) : u64max(key[r], p);
+                }
+            }
+        }
+    }
+}
+
+template <int E>
+__device__ __forceinline__ void sort_segment_regs(const u64 *__restrict__ gkeys, const int L, const int n_pad,
+                                                  u64 *sbuf, uint32_t *sids, int32_t *__restrict__ flat,
+                                                  long long *__restrict__ isect, const long long tile_hi,
+                                                  const int tid) {
+    u64 key[E];
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+        const int e = (r << 8) | tid;
+        key[r] = e < L ? gkeys[e] : ~0ull;
+    }
+    sort_regs<E>(key, n_pad, sbuf, tid);
+    __syncthreads();  // exchange buffers are dead: reuse them for the sorted ids
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+        const int e = (r << 8) | tid;
+        if (e < L) {
+            sids[e] = (uint32_t)key[r];
+            flat[e] = (int32_t)(uint32_t)key[r];
+            if (isect) isect[e] = tile_hi | (long long)(key[r] >> 32);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fallback for segments longer than SORT_CAP: ascending-only bitonic network, chunks of SORT_CAP in
+// shared memory, the large-distance stages directly in global memory (virtual +inf padding: a
+// comparator whose upper index is >= L is a no-op and is skipped).
+// ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void cmpx(u64 &a, u64 &b) {
     if (a > b) { const u64 t = a; a = b; b = t; }
 }
 
-// ascending-only bitonic network on s[0..n_pad), n_pad a power of two; all 256 threads call it.
-// first_k lets the hybrid path resume at a later merge stage; k_end is the last merge size (incl.).
-__device__ void bitonic_smem(u64 *s, int n_pad, int tid) {
-    for (int k = 2; k <= n_pad; k <<= 1) {
-        const int hk = k >> 1;
-        for (int idx = tid; idx < (n_pad >> 1); idx += RF_THREADS) {
-            const int blk = idx / hk, off = idx - blk * hk;
-            const int i = blk * k + off, j = blk * k + k - 1 - off;
-            cmpx(s[i], s[j]);
+__device__ void bitonic_smem_full(u64 *s, int tid) {  // sorts SORT_CAP keys
+    for (int lk = 1; (1 << lk) <= SORT_CAP; ++lk) {
+        const int k = 1 << lk, hk = k >> 1;
+        for (int idx = tid; idx < (SORT_CAP >> 1); idx += RF_THREADS) {
+            const int blk = idx >> (lk - 1), off = idx & (hk - 1);
+            cmpx(s[blk * k + off], s[blk * k + k - 1 - off]);
         }
         __syncthreads();
-        for (int j = k >> 2; j > 0; j >>= 1) {
-            for (int idx = tid; idx < (n_pad >> 1); idx += RF_THREADS) {
-                const int i = 2 * j * (idx / j) + (idx % j);
+        for (int lj = lk - 2; lj >= 0; --lj) {
+            const int j = 1 << lj;
+            for (int idx = tid; idx < (SORT_CAP >> 1); idx += RF_THREADS) {
+                const int i = ((idx >> lj) << (lj + 1)) | (idx & (j - 1));
                 cmpx(s[i], s[i + j]);
             }
             __syncthreads();
@@ -47,21 +132,19 @@ __device__ void bitonic_smem(u64 *s, int n_pad, int tid) {
     }
 }
 
-// the tail of one merge stage inside a chunk: plain half-cleaners j = SORT_CAP/2 ... 1
-__device__ void bitonic_tail_smem(u64 *s, int tid) {
-    for (int j = SORT_CAP >> 1; j > 0; j >>= 1) {
+__device__ void bitonic_tail_smem(u64 *s, int tid) {  // half-cleaners j = SORT_CAP/2 ... 1
+    for (int lj = 10; lj >= 0; --lj) {
+        const int j = 1 << lj;
         for (int idx = tid; idx < (SORT_CAP >> 1); idx += RF_THREADS) {
-            const int i = 2 * j * (idx / j) + (idx % j);
+            const int i = ((idx >> lj) << (lj + 1)) | (idx & (j - 1));
             cmpx(s[i], s[i + j]);
         }
         __syncthreads();
     }
 }
 
-// Sort a segment longer than SORT_CAP in place in global memory (rare: > 2048 Gaussians on a tile).
-// Virtual padding with +inf: a comparator whose upper index is >= L is a no-op in an ascending-only
-// network, so it is skipped.
 __device__ void sort_large(u64 *__restrict__ gk, int L, u64 *s, int tid) {
+    static_assert(SORT_CAP == 2048, "bitonic_tail_smem assumes SORT_CAP == 2048");
     int n_pad = SORT_CAP;
     while (n_pad < L) n_pad <<= 1;
     const int n_chunks = (L + SORT_CAP - 1) / SORT_CAP;
@@ -69,7 +152,7 @@ __device__ void sort_large(u64 *__restrict__ gk, int L, u64 *s, int tid) {
         const int base = c * SORT_CAP;
         for (int i = tid; i < SORT_CAP; i += RF_THREADS) s[i] = (base + i < L) ? gk[base + i] : ~0ull;
         __syncthreads();
-        bitonic_smem(s, SORT_CAP, tid);
+        bitonic_smem_full(s, tid);
         for (int i = tid; i < SORT_CAP; i += RF_THREADS)
             if (base + i < L) gk[base + i] = s[i];
         __syncthreads();
@@ -114,10 +197,11 @@ __global__ void __launch_bounds__(RF_THREADS) raster_fwd_kernel(
     float *__restrict__ render0, float *__restrict__ alpha_out, int32_t *__restrict__ last_ids,
     const void *__restrict__ gt, double *__restrict__ loss_sum, float *__restrict__ wpix,
     const int32_t *__restrict__ status) {
-    __shared__ __align__(16) u64 skeys[SORT_CAP];
-    __shared__ __align__(16) float4 sA[RF_THREADS];  // mean2d.x, mean2d.y, opacity, sub-tile mask bits
-    __shared__ __align__(16) float4 sB[RF_THREADS];  // conic a, b, c, -
+    __shared__ __align__(16) u64 sbuf[2 * SORT_CAP];  // sort exchange buffers, then the sorted ids
+    __shared__ __align__(16) float4 sA[RF_THREADS];   // mean2d.x, mean2d.y, opacity, sub-tile mask bits
+    __shared__ __align__(16) float4 sB[RF_THREADS];   // conic a, b, c, -
     __shared__ float s_red[RF_THREADS / 32];
+    uint32_t *sids = reinterpret_cast<uint32_t *>(sbuf);
 
     if (status[EG_ST_OVERFLOW]) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -127,28 +211,27 @@ __global__ void __launch_bounds__(RF_THREADS) raster_fwd_kernel(
     const int L = tile_offsets[tile + 1] - start;
 
     // ---------------- phase A: sort the segment ----------------
-    const bool in_smem = L <= SORT_CAP;
+    const bool on_chip = L <= SORT_CAP;
     if (L > 0) {
-        if (in_smem) {
+        const long long tile_hi = (long long)tile << 32;
+        long long *isect = isect_ids ? isect_ids + start : nullptr;
+        if (L <= 256) {
             int n_pad = 32;
             while (n_pad < L) n_pad <<= 1;
-            for (int i = tid; i < n_pad; i += RF_THREADS) skeys[i] = i < L ? keys[start + i] : ~0ull;
-            __syncthreads();
-            bitonic_smem(skeys, n_pad, tid);
-            for (int i = tid; i < L; i += RF_THREADS) {
-                const u64 k = skeys[i];
-                flatten_ids[start + i] = (int32_t)(uint32_t)k;
-                keys[start + i] = k;
-                if (isect_ids) isect_ids[start + i] = ((long long)tile << 32) | (long long)(k >> 32);
-            }
+            sort_segment_regs<1>(keys + start, L, n_pad, sbuf, sids, flatten_ids + start, isect, tile_hi, tid);
+        } else if (L <= 512) {
+            sort_segment_regs<2>(keys + start, L, 512, sbuf, sids, flatten_ids + start, isect, tile_hi, tid);
+        } else if (L <= 1024) {
+            sort_segment_regs<4>(keys + start, L, 1024, sbuf, sids, flatten_ids + start, isect, tile_hi, tid);
+        } else if (L <= 2048) {
+            sort_segment_regs<8>(keys + start, L, 2048, sbuf, sids, flatten_ids + start, isect, tile_hi, tid);
         } else {
-            sort_large(keys + start, L, skeys, tid);
+            sort_large(keys + start, L, sbuf, tid);
             for (int i = tid; i < L; i += RF_THREADS) {
                 const u64 k = keys[start + i];
                 flatten_ids[start + i] = (int32_t)(uint32_t)k;
-                if (isect_ids) isect_ids[start + i] = ((long long)tile << 32) | (long long)(k >> 32);
+                if (isect) isect[i] = tile_hi | (long long)(k >> 32);
             }
-            __syncthreads();
         }
     }
 
@@ -164,11 +247,11 @@ __global__ void __launch_bounds__(RF_THREADS) raster_fwd_kernel(
     bool done = !inside;
 
     for (int b0 = 0; b0 < L; b0 += RF_THREADS) {
-        // barrier doubles as "previous batch fully consumed" and the all-pixels-done early exit
+        // barrier doubles as "sorted ids / previous batch visible" and the all-pixels-done early exit
         if (__syncthreads_and(done)) break;
         const int k = b0 + tid;
         if (k < L) {
-            const int gid = in_smem ? (int)(uint32_t)skeys[k] : flatten_ids[start + k];
+            const int gid = on_chip ? (int)sids[k] : flatten_ids[start + k];
             const float4 r0 = __ldg(rec + 2 * gid), r1 = __ldg(rec + 2 * gid + 1);
             int mask = 0;
             float hx, hy, tau;

@@ -66,11 +66,10 @@ class RasterStepWorkspace:
         self.rec = torch.empty((N, 8), dtype=f32, device=device)
         self.gint = torch.empty((N, 2), dtype=i32, device=device)
         # tile_counts | status share one allocation so a single memset clears both
-        self.zero_block = torch.zeros(T + 1 + _lib.EG_ST_WORDS, dtype=i32, device=device)
-        self.tile_counts = self.zero_block[:T + 1]
-        self.status = self.zero_block[T + 1:]
+        self.zero_block = torch.zeros(T * _lib.EG_CNT_STRIDE + _lib.EG_ST_WORDS, dtype=i32, device=device)
+        self.tile_counts = self.zero_block[:T * _lib.EG_CNT_STRIDE]
+        self.status = self.zero_block[T * _lib.EG_CNT_STRIDE:]
         self.tile_offsets = torch.empty(T + 1, dtype=i32, device=device)
-        self.tile_cursor = torch.empty(T, dtype=i32, device=device)
         self.keys = torch.empty(self.capacity, dtype=torch.int64, device=device)
         self.flatten_ids = torch.empty(self.capacity, dtype=i32, device=device)
         self.last_ids = torch.empty((H, W), dtype=i32, device=device)
@@ -284,8 +283,8 @@ class EdgeGaussianSplatting(torch.nn.Module):
         chk(lib.eg_project_fwd(c, _p(means), _p(quats), _p(scales), _p(opac), None, _p(viewmat), _p(K), _p(ws.rec),
                                _p(ws.gint), _p(ws.tile_counts), _p(ws.status), s), "eg_project_fwd")
         cb("project_fwd")
-        chk(lib.eg_bin(c, _p(ws.rec), _p(ws.gint), _p(ws.tile_counts), _p(ws.tile_offsets), _p(ws.tile_cursor),
-                       _p(ws.keys), _p(ws.status), s), "eg_bin")
+        chk(lib.eg_bin(c, _p(ws.rec), _p(ws.gint), _p(ws.tile_counts), _p(ws.tile_offsets), _p(ws.keys),
+                       _p(ws.status), s), "eg_bin")
         cb("bin")
         chk(lib.eg_raster_fwd(c, _p(ws.rec), _p(ws.tile_offsets), _p(ws.keys), _p(ws.flatten_ids), None,
                               _p(ws.render0) if want_render else None, None, _p(ws.last_ids), _p(gt), gt_kind,

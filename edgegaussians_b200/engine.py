@@ -103,9 +103,8 @@ class Engine:
         cap = int(capacity) if capacity is not None else self._ensure_capacity(N)
         rec = torch.empty((N, 8), dtype=torch.float32, device=dev)
         gint = torch.empty((N, 2), dtype=torch.int32, device=dev)
-        tile_counts = torch.zeros(T + 1, dtype=torch.int32, device=dev)
+        tile_counts = torch.zeros(T * _lib.EG_CNT_STRIDE, dtype=torch.int32, device=dev)
         tile_offsets = torch.empty(T + 1, dtype=torch.int32, device=dev)
-        tile_cursor = torch.empty(T, dtype=torch.int32, device=dev)
         status = torch.zeros(EG_ST_WORDS, dtype=torch.int32, device=dev)
         while True:
             cfg = self.make_cfg(N, width, height, eps2d=eps2d, near_plane=near_plane, far_plane=far_plane,
@@ -117,7 +116,7 @@ class Engine:
                                                _p(colors), _p(viewmat), _p(K), _p(rec), _p(gint),
                                                _p(tile_counts), _p(status), _stream()), "eg_project_fwd")
             _lib.check(self.lib.eg_bin(ctypes.byref(cfg), _p(rec), _p(gint), _p(tile_counts), _p(tile_offsets),
-                                       _p(tile_cursor), _p(keys), _p(status), _stream()), "eg_bin")
+                                       _p(keys), _p(status), _stream()), "eg_bin")
             st = SplatState(cfg=cfg, N=N, width=width, height=height, tile_w=tw, tile_h=th, rec=rec, gint=gint,
                             tile_offsets=tile_offsets, keys=keys, flatten_ids=flatten_ids, status=status)
             if not sync:

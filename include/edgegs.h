@@ -25,8 +25,10 @@
  *   rec   [N,8]  = (mean2d.x, mean2d.y, opacity*comp, depth | conic.a, conic.b, conic.c, comp)
  *                  gsplat's meta means2d/opacities/depths/conics are strided views of this record.
  *   gint  [N,2] i32 = (radius, tiles_per_gauss); radius 0 = culled.
- *   tile_counts [T+1] i32 (zeroed by caller before eg_project_fwd), tile_offsets [T+1] i32 (exclusive
- *                  scan; [T] = n_isects), tile_cursor [T] i32 scratch.
+ *   tile_counts [T, EG_CNT_STRIDE] i32 (zeroed by caller before eg_project_fwd): column 0 = number of
+ *                  intersections of the tile, column 1 = append cursor (scratch of eg_bin); one 128-byte
+ *                  line per tile so that the L2 atomic units do not serialise neighbouring tiles.
+ *   tile_offsets [T+1] i32 (exclusive scan; [T] = n_isects).
  *   keys  [cap] u64 = depth_bits<<32 | gaussian_id, unsorted per tile after eg_bin, sorted (per tile)
  *                  after eg_raster_fwd.
  *   flatten_ids [cap] i32 : gsplat's flatten_ids (sorted by tile, depth bits, id).
@@ -47,7 +49,8 @@
 extern "C" {
 #endif
 
-#define EG_ABI_VERSION 1
+#define EG_ABI_VERSION 2
+#define EG_CNT_STRIDE 32
 
 enum { EG_ST_NISECT = 0, EG_ST_OVERFLOW = 1, EG_ST_BADCOLOR = 2, EG_ST_NVISIBLE = 3, EG_ST_WORDS = 8 };
 
@@ -82,8 +85,8 @@ int eg_project_fwd(const eg_config *cfg, const float *means, const float *quats,
 /* K2 pass 2: exclusive scan of the tile counts + emission of (depth,id) keys into per-tile segments.
  * Replaces gsplat cumsum + isect_tiles pass 2 + isect_offset_encode (the sort itself is per tile
  * inside eg_raster_fwd). */
-int eg_bin(const eg_config *cfg, const float *rec, const int32_t *gint, const int32_t *tile_counts,
-           int32_t *tile_offsets, int32_t *tile_cursor, uint64_t *keys, int32_t *status, void *stream);
+int eg_bin(const eg_config *cfg, const float *rec, const int32_t *gint, int32_t *tile_counts,
+           int32_t *tile_offsets, uint64_t *keys, int32_t *status, void *stream);
 
 /* K3 + K5 (+ a8 "whole" L1): per-tile sort, front-to-back compositing, optional fused edge-map loss.
  * Replaces cub radix sort + gsplat rasterize_to_pixels fwd; with gt != NULL also
