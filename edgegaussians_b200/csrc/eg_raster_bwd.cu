@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
     __shared__ float2 s_pix[EG_TILE * EG_TILE];        // (seed * T_final, last contributor rel. to segment start)
     __shared__ __align__(16) float4 sA[RB_THREADS];    // mean2d.x, mean2d.y, opacity, packed pixel rectangle
     __shared__ __align__(16) float4 sB[RB_THREADS];    // conic a, b, c, gaussian id
+    __shared__ __align__(16) float4 sC[RB_THREADS];    // 2*A*tau, det(conic), 1/A (0 = no row span), -
     __shared__ int s_off[RB_THREADS + 1];              // exclusive prefix of the rectangle areas
     __shared__ int s_wsum[RB_THREADS / 32];
 
@@ -82,6 +83,8 @@ __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
     }
     const int xmax = min(EG_TILE, cfg.width - X0) - 1, ymax = min(EG_TILE, cfg.height - Y0) - 1;
 
+    const float X0f = (float)X0 + 0.5f, Y0f = (float)Y0 + 0.5f;  // centre of pixel (0,0) of the tile
+
     for (int b0 = 0; b0 < L; b0 += RB_THREADS) {
         __syncthreads();  // s_pix visible / previous batch fully consumed
         // ---- 1. stage one Gaussian per thread, with its reachable pixel rectangle ----
@@ -92,6 +95,7 @@ __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
             const float4 r0 = __ldg(rec + 2 * gid), r1 = __ldg(rec + 2 * gid + 1);
             float hx, hy, tau;
             int rect = 0;
+            float two_tau_a = 0.0f, det = 0.0f, inv_a = 0.0f;  // inv_a == 0: no per-row span (degenerate conic)
             if (eg_extent(r0.z, r1.x, r1.y, r1.z, hx, hy, tau)) {
                 // pixel j (centre j + 0.5) is reachable iff  mx - hx <= j + 0.5 <= mx + hx
                 const float fx0 = r0.x - (float)X0, fy0 = r0.y - (float)Y0;
@@ -103,9 +107,15 @@ __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
                     area = (xhi - xlo + 1) * (yhi - ylo + 1);
                     rect = xlo | (xhi << 4) | (ylo << 8) | (yhi << 12);
                 }
+                if (hx < 1e29f) {
+                    det = r1.x * r1.z - r1.y * r1.y;
+                    two_tau_a = 2.0f * tau * r1.x;
+                    inv_a = 1.0f / r1.x;
+                }
             }
             sA[tid] = make_float4(r0.x, r0.y, r0.z, __int_as_float(rect));
             sB[tid] = make_float4(r1.x, r1.y, r1.z, __int_as_float(gid));
+            sC[tid] = make_float4(two_tau_a, det, inv_a, 0.0f);
         }
         // ---- 2. block-wide exclusive prefix sum of the areas ----
         int incl = area;
@@ -128,12 +138,12 @@ __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
         __syncthreads();
         if (total == 0) continue;
 
-        // ---- 3. every thread walks an equal slice of the pair list ----
+        // ---- 3. every thread walks an equal slice of the (Gaussian, rectangle pixel) pair list ----
         const int chunk = (total + RB_THREADS - 1) / RB_THREADS;
         int p = tid * chunk;
         const int p_end = min(total, p + chunk);
         if (p >= p_end) continue;
-        // binary search: largest g with s_off[g] <= p  (areas may be 0, so take the last such g)
+        // binary search: largest g with s_off[g] <= p
         int lo = 0, hi = RB_THREADS;
         while (hi - lo > 1) {
             const int mid = (lo + hi) >> 1;
@@ -141,43 +151,65 @@ __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
         }
         int g = lo;
         while (p < p_end) {
-            // (re)load the Gaussian g; skip empty ones
-            while (s_off[g + 1] <= p) ++g;
-            const float4 a = sA[g], cn = sB[g];
+            while (s_off[g + 1] <= p) ++g;  // skip Gaussians with an empty rectangle
+            const float4 a = sA[g], cn = sB[g], sp = sC[g];
             const int rect = __float_as_int(a.w);
             const int xlo = rect & 15, xhi = (rect >> 4) & 15, ylo = (rect >> 8) & 15;
             const int wbox = xhi - xlo + 1;
             const int local = p - s_off[g];
-            int y = ylo + local / wbox, x = xlo + local - (local / wbox) * wbox;
+            const int row0 = local / wbox;
+            int y = ylo + row0, x = xlo + local - row0 * wbox;
             const int seg_end = min(p_end, s_off[g + 1]);
             const int kk = b0 + g;  // position of the Gaussian in the tile's sorted list
             PairAcc acc;
             acc_zero(acc);
-            for (; p < seg_end; ++p) {
-                const float2 pw = s_pix[y * EG_TILE + x];
-                if (pw.x != 0.0f && kk <= __float_as_int(pw.y)) {
-                    const float dx = a.x - ((float)(X0 + x) + 0.5f), dy = a.y - ((float)(Y0 + y) + 0.5f);
-                    const float sigma = eg_sigma(cn.x, cn.y, cn.z, dx, dy);
-                    const float vis = eg_vis(sigma);
-                    const float ov = __fmul_rn(a.z, vis);
-                    const float al = fminf(EG_ALPHA_MAX, ov);
-                    if (sigma >= 0.0f && al >= EG_ALPHA_MIN && ov <= EG_ALPHA_MAX) {
-                        const float ra = __fdividef(1.0f, 1.0f - al);
-                        const float v_al = pw.x * ra;
-                        const float v_sigma = -ov * v_al;
-                        const float gx = v_sigma * (cn.x * dx + cn.y * dy);
-                        const float gy = v_sigma * (cn.y * dx + cn.z * dy);
-                        acc.gx += gx;
-                        acc.gy += gy;
-                        acc.ax += fabsf(gx);
-                        acc.ay += fabsf(gy);
-                        acc.ca += 0.5f * v_sigma * dx * dx;
-                        acc.cb += v_sigma * dx * dy;
-                        acc.cc += 0.5f * v_sigma * dy * dy;
-                        acc.go += vis * v_al;
+            while (p < seg_end) {
+                // the part of row y that belongs to this slice: pixels x .. x + n_row - 1
+                const int n_row = min(xhi - x + 1, seg_end - p);
+                const float dy = a.y - (Y0f + (float)y);
+                int xs = x, xe = x + n_row - 1;
+                if (sp.z != 0.0f) {
+                    // sigma(dx, dy) <= tau  <=>  |dx - c| <= hw,  c = -B dy / A,  hw = sqrt(2 A tau - det dy^2) / A
+                    const float D = fmaf(-sp.y * dy, dy, sp.x);
+                    if (D < 0.0f) {
+                        xe = xs - 1;
+                    } else {
+                        const float hw = sqrtf(D) * sp.z * 1.0001f + 2e-3f;
+                        const float cpx = a.x + cn.y * dy * sp.z - X0f;  // pixel coordinate (in-tile) of the span centre
+                        xs = max(xs, (int)ceilf(fminf(cpx - hw, 64.0f)));
+                        xe = min(xe, (int)floorf(fmaxf(cpx + hw, -64.0f)));
                     }
                 }
-                if (++x > xhi) { x = xlo; ++y; }
+                int idx = y * EG_TILE + xs;
+                float pxf = X0f + (float)xs;
+                for (int xx = xs; xx <= xe; ++xx, ++idx, pxf += 1.0f) {
+                    const float2 pw = s_pix[idx];
+                    if (pw.x != 0.0f && kk <= __float_as_int(pw.y)) {
+                        const float dx = a.x - pxf;
+                        const float sigma = eg_sigma(cn.x, cn.y, cn.z, dx, dy);
+                        const float vis = eg_vis(sigma);
+                        const float ov = __fmul_rn(a.z, vis);
+                        if (sigma >= 0.0f && ov >= EG_ALPHA_MIN && ov <= EG_ALPHA_MAX) {
+                            const float ra = __fdividef(1.0f, 1.0f - ov);
+                            const float v_al = pw.x * ra;
+                            const float v_sigma = -ov * v_al;
+                            const float gx = v_sigma * fmaf(cn.x, dx, cn.y * dy);
+                            const float gy = v_sigma * fmaf(cn.y, dx, cn.z * dy);
+                            const float hs = 0.5f * v_sigma;
+                            acc.gx += gx;
+                            acc.gy += gy;
+                            acc.ax += fabsf(gx);
+                            acc.ay += fabsf(gy);
+                            acc.ca = fmaf(hs * dx, dx, acc.ca);
+                            acc.cb = fmaf(v_sigma * dx, dy, acc.cb);
+                            acc.cc = fmaf(hs * dy, dy, acc.cc);
+                            acc.go = fmaf(vis, v_al, acc.go);
+                        }
+                    }
+                }
+                p += n_row;
+                x = xlo;
+                ++y;
             }
             acc_flush(acc, grad2d, __float_as_int(cn.w));
         }

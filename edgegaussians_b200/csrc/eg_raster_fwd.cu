@@ -64,7 +64,7 @@ __device__ __forceinline__ void sort_regs(u64 (&key)[E], const int n_pad, u64 *s
                     const int e = (r << 8) | tid;
                     const u64 p = sb[e ^ j];
                     const bool keep_min = ((e & k) == 0) == ((e & j) == 0);
-                    key[r] = keep_min ? u64min(key[r], p) : u64max(key[r], p);
+                    key[r] = ((key[r] < p) == keep_min) ? key[r] : p;  // keys are unique (or both +inf)
                 }
                 buf ^= 1;
             } else {  // partner is a lane of the same warp
@@ -73,7 +73,7 @@ __device__ __forceinline__ void sort_regs(u64 (&key)[E], const int n_pad, u64 *s
                     const int e = (r << 8) | tid;
                     const u64 p = __shfl_xor_sync(0xffffffffu, key[r], j);
                     const bool keep_min = ((e & k) == 0) == ((e & j) == 0);
-                    key[r] = keep_min ? u64min(key[r], p) : u64max(key[r], p);
+                    key[r] = ((key[r] < p) == keep_min) ? key[r] : p;
                 }
             }
         }
@@ -198,8 +198,8 @@ __global__ void __launch_bounds__(RF_THREADS) raster_fwd_kernel(
     const void *__restrict__ gt, double *__restrict__ loss_sum, float *__restrict__ wpix,
     const int32_t *__restrict__ status) {
     __shared__ __align__(16) u64 sbuf[2 * SORT_CAP];  // sort exchange buffers, then the sorted ids
-    __shared__ __align__(16) float4 sA[RF_THREADS];   // mean2d.x, mean2d.y, opacity, sub-tile mask bits
-    __shared__ __align__(16) float4 sB[RF_THREADS];   // conic a, b, c, -
+    __shared__ __align__(16) float4 sAB[2 * RF_THREADS];  // per Gaussian: (mean2d.x, mean2d.y, opacity, sub-tile
+                                                          // mask bits) , (conic a, b, c, -)
     __shared__ float s_red[RF_THREADS / 32];
     uint32_t *sids = reinterpret_cast<uint32_t *>(sbuf);
 
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(RF_THREADS) raster_fwd_kernel(
     const float X0 = (float)(tile_x * EG_TILE), Y0 = (float)(tile_y * EG_TILE);
 
     float T = 1.0f, out = 0.0f;
-    int last = 0;
+    int last = -start;  // relative to the segment start; gsplat initialises the absolute index to 0
     bool done = !inside;
 
     for (int b0 = 0; b0 < L; b0 += RF_THREADS) {
@@ -267,28 +267,30 @@ __global__ void __launch_bounds__(RF_THREADS) raster_fwd_kernel(
                 for (int r = 0; r < 4; ++r)
                     if (cy & (1 << r)) mask |= cx << (2 * r);
             }
-            sA[tid] = make_float4(r0.x, r0.y, r0.z, __int_as_float(mask));
-            sB[tid] = r1;
+            sAB[2 * tid] = make_float4(r0.x, r0.y, r0.z, __int_as_float(mask));
+            sAB[2 * tid + 1] = r1;
         }
         __syncthreads();
         const int nb = min(RF_THREADS, L - b0);
         for (int c = 0; c < nb && !__all_sync(0xffffffffu, done); c += 32) {
-            const int m = (c + lane < nb) ? __float_as_int(sA[c + lane].w) : 0;
+            const int m = (c + lane < nb) ? __float_as_int(sAB[2 * (c + lane)].w) : 0;
             unsigned bits = __ballot_sync(0xffffffffu, (m >> warp) & 1);
             while (bits) {
                 const int t = c + __ffs(bits) - 1;
                 bits &= bits - 1;
-                const float4 a = sA[t];
-                const float4 cn = sB[t];
+                const float4 a = sAB[2 * t];
+                const float4 cn = sAB[2 * t + 1];
                 const float dx = a.x - px, dy = a.y - py;
                 const float sigma = eg_sigma(cn.x, cn.y, cn.z, dx, dy);
                 const float al = fminf(EG_ALPHA_MAX, __fmul_rn(a.z, eg_vis(sigma)));
-                if (done || sigma < 0.0f || al < EG_ALPHA_MIN) continue;
+                const bool valid = !done && sigma >= 0.0f && al >= EG_ALPHA_MIN;
                 const float nT = T * (1.0f - al);
-                if (nT <= EG_T_MIN) { done = true; continue; }
-                out = fmaf(al, T, out);
-                T = nT;
-                last = start + b0 + t;
+                const bool stop = valid && nT <= EG_T_MIN;
+                const bool take = valid && !stop;
+                done = done || stop;
+                out = take ? fmaf(al, T, out) : out;
+                T = take ? nT : T;
+                last = take ? (b0 + t) : last;
             }
         }
     }
@@ -299,7 +301,7 @@ __global__ void __launch_bounds__(RF_THREADS) raster_fwd_kernel(
         const long long pix = (long long)pyi * cfg.width + pxi;
         if (alpha_out) alpha_out[pix] = 1.0f - T;
         if (render0) render0[pix] = out;
-        last_ids[pix] = last;
+        last_ids[pix] = start + last;
         if (GT_KIND != EG_GT_NONE) {
             float g;
             if (GT_KIND == EG_GT_F32) g = __ldg(reinterpret_cast<const float *>(gt) + pix);

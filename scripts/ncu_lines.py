@@ -27,5 +27,5 @@ for r in rows:
 tot_s = sum(l[3] for l in lines) or 1
 tot_i = sum(l[4] for l in lines) or 1
 print(f"total samples {tot_s}, total warp-instructions {tot_i}")
-for f, ln, src, s, i in sorted(lines, key=lambda l: -l[3])[:top]:
+for f, ln, src, s, i in sorted(lines, key=lambda l: -(l[4] if len(sys.argv) > 4 else l[3]))[:top]:
     print(f"{100 * s / tot_s:5.1f}% smp {100 * i / tot_i:5.1f}% ins  {f}:{ln:<4d} {src}")

@@ -121,7 +121,9 @@ def test_backward_parity(case):
     meta["means2d"].retain_grad()
     loss = (render[0] * _t(v_render)).sum() + (alpha[0, ..., 0] * _t(v_alpha)).sum()
     loss.backward()
-    _check_grad(name, "v_means2d", meta["means2d"].grad[0].cpu().numpy(), gref["v_means2d"])
+    # v_means2d is a signed sum of per-pixel terms whose absolute sum is the abs-grad: fp32 accumulation
+    # noise scales with the latter (matters for footprints of thousands of pixels with random seeds)
+    _check_grad(name, "v_means2d", meta["means2d"].grad[0].cpu().numpy(), gref["v_means2d"], 4e-6 * gref["v_means2d_abs"])
     _check_grad(name, "absgrad", meta["means2d"].absgrad[0].cpu().numpy(), gref["v_means2d_abs"])
     floor = 1e-6 * np.abs(gref["v_means"]).max()
     for key, t in (("v_means", tm), ("v_quats", tq), ("v_scales", ts), ("v_opacities", to)):
