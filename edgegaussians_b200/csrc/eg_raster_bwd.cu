@@ -24,6 +24,7 @@
 namespace {
 
 constexpr int RB_THREADS = 256;
+constexpr int PAIR_CAP = 32;  // per-thread buffer of candidate pairs between the cheap and the heavy phase
 
 struct PairAcc {
     float gx, gy, ax, ay, ca, cb, cc, go;
@@ -49,6 +50,7 @@ __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
     __shared__ __align__(16) float4 sA[RB_THREADS];    // mean2d.x, mean2d.y, opacity, packed pixel rectangle
     __shared__ __align__(16) float4 sB[RB_THREADS];    // conic a, b, c, gaussian id
     __shared__ __align__(16) float4 sC[RB_THREADS];    // 2*A*tau, det(conic), 1/A (0 = no row span), -
+    __shared__ unsigned short s_buf[PAIR_CAP * RB_THREADS];  // candidate pairs: pixel index | local Gaussian << 8
     __shared__ int s_off[RB_THREADS + 1];              // exclusive prefix of the rectangle areas
     __shared__ int s_wsum[RB_THREADS / 32];
 
@@ -138,11 +140,10 @@ __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
         __syncthreads();
         if (total == 0) continue;
 
-        // ---- 3. every thread walks an equal slice of the (Gaussian, rectangle pixel) pair list ----
+        // ---- 3. every thread takes an equal slice of the (Gaussian, rectangle pixel) pair list ----
         const int chunk = (total + RB_THREADS - 1) / RB_THREADS;
         int p = tid * chunk;
         const int p_end = min(total, p + chunk);
-        if (p >= p_end) continue;
         // binary search: largest g with s_off[g] <= p
         int lo = 0, hi = RB_THREADS;
         while (hi - lo > 1) {
@@ -150,69 +151,93 @@ __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
             if (s_off[mid] <= p) lo = mid; else hi = mid;
         }
         int g = lo;
-        while (p < p_end) {
-            while (s_off[g + 1] <= p) ++g;  // skip Gaussians with an empty rectangle
-            const float4 a = sA[g], cn = sB[g], sp = sC[g];
-            const int rect = __float_as_int(a.w);
-            const int xlo = rect & 15, xhi = (rect >> 4) & 15, ylo = (rect >> 8) & 15;
-            const int wbox = xhi - xlo + 1;
-            const int local = p - s_off[g];
-            const int row0 = local / wbox;
-            int y = ylo + row0, x = xlo + local - row0 * wbox;
-            const int seg_end = min(p_end, s_off[g + 1]);
-            const int kk = b0 + g;  // position of the Gaussian in the tile's sorted list
-            PairAcc acc;
-            acc_zero(acc);
-            while (p < seg_end) {
-                // the part of row y that belongs to this slice: pixels x .. x + n_row - 1
-                const int n_row = min(xhi - x + 1, seg_end - p);
-                const float dy = a.y - (Y0f + (float)y);
-                int xs = x, xe = x + n_row - 1;
-                if (sp.z != 0.0f) {
-                    // sigma(dx, dy) <= tau  <=>  |dx - c| <= hw,  c = -B dy / A,  hw = sqrt(2 A tau - det dy^2) / A
-                    const float D = fmaf(-sp.y * dy, dy, sp.x);
-                    if (D < 0.0f) {
-                        xe = xs - 1;
-                    } else {
-                        const float hw = sqrtf(D) * sp.z * 1.0001f + 2e-3f;
-                        const float cpx = a.x + cn.y * dy * sp.z - X0f;  // pixel coordinate (in-tile) of the span centre
-                        xs = max(xs, (int)ceilf(fminf(cpx - hw, 64.0f)));
-                        xe = min(xe, (int)floorf(fmaxf(cpx + hw, -64.0f)));
-                    }
+        // walk state of the cheap phase (valid while p < seg_end)
+        int seg_end = p, x = 0, y = 0, xlo = 0, xhi = 0, xs = 0, xe = -1, kk = 0;
+        float two_tau_a = 0.f, det = 0.f, inv_a = 0.f, mx = 0.f, my = 0.f, cb = 0.f;
+        // accumulation state of the heavy phase
+        int cur_g = -1;
+        PairAcc acc;
+        acc_zero(acc);
+
+        for (;;) {
+            // ---- 3a. cheap phase: collect up to PAIR_CAP pairs that can contribute ----
+            int cnt = 0;
+            while (cnt < PAIR_CAP && p < p_end) {
+                if (p >= seg_end) {  // enter the next Gaussian of the slice
+                    while (s_off[g + 1] <= p) ++g;
+                    const float4 a = sA[g], sp = sC[g];
+                    const int rect = __float_as_int(a.w);
+                    xlo = rect & 15; xhi = (rect >> 4) & 15;
+                    const int ylo = (rect >> 8) & 15, wbox = xhi - xlo + 1;
+                    const int local = p - s_off[g], row0 = local / wbox;
+                    y = ylo + row0; x = xlo + local - row0 * wbox;
+                    seg_end = min(p_end, s_off[g + 1]);
+                    kk = b0 + g;
+                    mx = a.x; my = a.y; cb = sB[g].y;
+                    two_tau_a = sp.x; det = sp.y; inv_a = sp.z;
+                    xe = -2;  // forces the row span computation below
                 }
-                int idx = y * EG_TILE + xs;
-                float pxf = X0f + (float)xs;
-                for (int xx = xs; xx <= xe; ++xx, ++idx, pxf += 1.0f) {
-                    const float2 pw = s_pix[idx];
-                    if (pw.x != 0.0f && kk <= __float_as_int(pw.y)) {
-                        const float dx = a.x - pxf;
-                        const float sigma = eg_sigma(cn.x, cn.y, cn.z, dx, dy);
-                        const float vis = eg_vis(sigma);
-                        const float ov = __fmul_rn(a.z, vis);
-                        if (sigma >= 0.0f && ov >= EG_ALPHA_MIN && ov <= EG_ALPHA_MAX) {
-                            const float ra = __fdividef(1.0f, 1.0f - ov);
-                            const float v_al = pw.x * ra;
-                            const float v_sigma = -ov * v_al;
-                            const float gx = v_sigma * fmaf(cn.x, dx, cn.y * dy);
-                            const float gy = v_sigma * fmaf(cn.y, dx, cn.z * dy);
-                            const float hs = 0.5f * v_sigma;
-                            acc.gx += gx;
-                            acc.gy += gy;
-                            acc.ax += fabsf(gx);
-                            acc.ay += fabsf(gy);
-                            acc.ca = fmaf(hs * dx, dx, acc.ca);
-                            acc.cb = fmaf(v_sigma * dx, dy, acc.cb);
-                            acc.cc = fmaf(hs * dy, dy, acc.cc);
-                            acc.go = fmaf(vis, v_al, acc.go);
+                if (xe == -2) {  // first pixel of a row: sigma <= tau  <=>  |dx - c| <= hw
+                    xs = xlo; xe = xhi;
+                    if (inv_a != 0.0f) {
+                        const float dy = my - (Y0f + (float)y);
+                        const float D = fmaf(-det * dy, dy, two_tau_a);
+                        if (D < 0.0f) {
+                            xe = -1;
+                        } else {
+                            const float hw = sqrtf(D) * inv_a * 1.0001f + 2e-3f;
+                            const float cpx = mx + cb * dy * inv_a - X0f;
+                            xs = max(xs, (int)ceilf(fminf(cpx - hw, 64.0f)));
+                            xe = min(xe, (int)floorf(fmaxf(cpx + hw, -64.0f)));
                         }
                     }
                 }
-                p += n_row;
-                x = xlo;
-                ++y;
+                if (x >= xs && x <= xe) {
+                    const int idx = y * EG_TILE + x;
+                    const float2 pw = s_pix[idx];
+                    if (pw.x != 0.0f && kk <= __float_as_int(pw.y)) {
+                        s_buf[cnt * RB_THREADS + tid] = (unsigned short)(idx | (g << 8));
+                        ++cnt;
+                    }
+                }
+                ++p;
+                if (++x > xhi) { x = xlo; ++y; xe = -2; }
             }
-            acc_flush(acc, grad2d, __float_as_int(cn.w));
+            // ---- 3b. heavy phase: all lanes of the warp evaluate their collected pairs together ----
+            for (int i = 0; i < cnt; ++i) {
+                const int e = s_buf[i * RB_THREADS + tid];
+                const int eg = e >> 8;
+                if (eg != cur_g) {
+                    if (cur_g >= 0) acc_flush(acc, grad2d, __float_as_int(sB[cur_g].w));
+                    acc_zero(acc);
+                    cur_g = eg;
+                }
+                const float4 a = sA[eg], cn = sB[eg];
+                const float w = s_pix[e & 255].x;
+                const float dx = a.x - (X0f + (float)(e & 15)), dy = a.y - (Y0f + (float)((e >> 4) & 15));
+                const float sigma = eg_sigma(cn.x, cn.y, cn.z, dx, dy);
+                const float vis = eg_vis(sigma);
+                const float ov = __fmul_rn(a.z, vis);
+                if (sigma >= 0.0f && ov >= EG_ALPHA_MIN && ov <= EG_ALPHA_MAX) {
+                    const float ra = __fdividef(1.0f, 1.0f - ov);
+                    const float v_al = w * ra;
+                    const float v_sigma = -ov * v_al;
+                    const float gx = v_sigma * fmaf(cn.x, dx, cn.y * dy);
+                    const float gy = v_sigma * fmaf(cn.y, dx, cn.z * dy);
+                    const float hs = 0.5f * v_sigma;
+                    acc.gx += gx;
+                    acc.gy += gy;
+                    acc.ax += fabsf(gx);
+                    acc.ay += fabsf(gy);
+                    acc.ca = fmaf(hs * dx, dx, acc.ca);
+                    acc.cb = fmaf(v_sigma * dx, dy, acc.cb);
+                    acc.cc = fmaf(hs * dy, dy, acc.cc);
+                    acc.go = fmaf(vis, v_al, acc.go);
+                }
+            }
+            if (__all_sync(0xffffffffu, p >= p_end)) break;
         }
+        if (cur_g >= 0) acc_flush(acc, grad2d, __float_as_int(sB[cur_g].w));
     }
 }
 
