@@ -10,21 +10,24 @@
 // and therefore   d out(p) / d alpha_k = T_final(p) / (1 - alpha_k)   for every composited k:
 // gsplat's  (color*T_k - buffer_k*ra_k)  is this quantity computed with cancellation.  The backward
 // is thus a plain sum over (pixel, Gaussian) pairs with no ordering dependence, and is organised
-// Gaussian-major with a BALANCED pair distribution:
-//   1. batches of 256 Gaussians of the tile are staged in shared memory together with the pixel
-//      rectangle (inside the tile) their alpha >= 1/255 footprint can reach;
-//   2. a block-wide prefix sum over the rectangle areas linearises all (Gaussian, pixel) pairs of the
-//      batch; every thread takes an equal contiguous slice of that pair list and walks it,
-//      accumulating the 8 per-Gaussian gradient values in registers (no warp reductions);
-//   3. whenever the walk leaves a Gaussian its partial sums leave as two 128-bit vector reductions
-//      (red.global.add.v4.f32) -- about two flushes per thread.
+// Gaussian-major, in three divergence-free stages per batch of 256 Gaussians of the tile:
+//   A. one thread per Gaussian: record + the pixel rectangle (inside the tile) that its
+//      alpha >= 1/255 footprint can reach; block scan of the rectangle heights -> a list of
+//      (Gaussian, pixel row) work items;
+//   B. one thread per work item: the exact pixel span of that row inside the footprint ellipse
+//      (sigma <= ln(255*opacity), solved analytically) intersected with the row's bitmask of pixels
+//      whose backward seed is non-zero -> a 16-bit candidate mask per item;
+//   C. every thread takes an equal contiguous run of items and walks the set bits: each step is one
+//      (Gaussian, pixel) pair that almost surely contributes.  The 8 per-Gaussian gradient values
+//      accumulate in registers (no warp reductions) and leave as two 128-bit vector reductions
+//      (red.global.add.v4.f32) when the run moves on to the next Gaussian (about 2 flushes/thread).
 // The per-pixel state (seed * T_final, last contributor) lives in shared memory.
 #include "eg_common.cuh"
 
 namespace {
 
 constexpr int RB_THREADS = 256;
-constexpr int PAIR_CAP = 32;  // per-thread buffer of candidate pairs between the cheap and the heavy phase
+constexpr int MAX_ITEMS = RB_THREADS * EG_TILE;  // (Gaussian, row) items of one batch
 
 struct PairAcc {
     float gx, gy, ax, ay, ca, cb, cc, go;
@@ -47,12 +50,15 @@ __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
     const float *__restrict__ wpix, float seed_scale, float *__restrict__ grad2d,
     const int32_t *__restrict__ status) {
     __shared__ float2 s_pix[EG_TILE * EG_TILE];        // (seed * T_final, last contributor rel. to segment start)
+    __shared__ unsigned s_rowmask[EG_TILE];            // pixels of the row with a non-zero seed
+    __shared__ int s_rowlast[EG_TILE];                 // max last contributor over those pixels
     __shared__ __align__(16) float4 sA[RB_THREADS];    // mean2d.x, mean2d.y, opacity, packed pixel rectangle
     __shared__ __align__(16) float4 sB[RB_THREADS];    // conic a, b, c, gaussian id
     __shared__ __align__(16) float4 sC[RB_THREADS];    // 2*A*tau, det(conic), 1/A (0 = no row span), -
-    __shared__ unsigned short s_buf[PAIR_CAP * RB_THREADS];  // candidate pairs: pixel index | local Gaussian << 8
-    __shared__ int s_off[RB_THREADS + 1];              // exclusive prefix of the rectangle areas
+    __shared__ int s_roff[RB_THREADS + 1];             // exclusive prefix of the rectangle heights
     __shared__ int s_wsum[RB_THREADS / 32];
+    __shared__ unsigned char s_item_g[MAX_ITEMS];      // item -> Gaussian of the batch
+    __shared__ unsigned s_item[MAX_ITEMS];             // candidate mask | row << 16 | Gaussian << 20
 
     if (status[EG_ST_OVERFLOW]) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -82,22 +88,29 @@ __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
             last = __ldg(last_ids + pix) - start;
         }
         s_pix[tid] = make_float2(w, __int_as_float(last));
+        const unsigned bal = __ballot_sync(0xffffffffu, w != 0.0f);
+        int ml = (w != 0.0f) ? last : -1;
+#pragma unroll
+        for (int d = 8; d > 0; d >>= 1) ml = max(ml, __shfl_xor_sync(0xffffffffu, ml, d));
+        if ((lane & 15) == 0) {
+            s_rowmask[ly] = (lane == 0) ? (bal & 0xffffu) : (bal >> 16);
+            s_rowlast[ly] = ml;
+        }
     }
     const int xmax = min(EG_TILE, cfg.width - X0) - 1, ymax = min(EG_TILE, cfg.height - Y0) - 1;
-
     const float X0f = (float)X0 + 0.5f, Y0f = (float)Y0 + 0.5f;  // centre of pixel (0,0) of the tile
 
     for (int b0 = 0; b0 < L; b0 += RB_THREADS) {
-        __syncthreads();  // s_pix visible / previous batch fully consumed
-        // ---- 1. stage one Gaussian per thread, with its reachable pixel rectangle ----
+        __syncthreads();  // pixel state visible / previous batch fully consumed
+        // ---- A. one Gaussian per thread: record, reachable rectangle, row items ----
         const int k = b0 + tid;
-        int area = 0;
+        int nrows = 0;
         if (k < L) {
             const int gid = __ldg(flatten_ids + start + k);
             const float4 r0 = __ldg(rec + 2 * gid), r1 = __ldg(rec + 2 * gid + 1);
             float hx, hy, tau;
             int rect = 0;
-            float two_tau_a = 0.0f, det = 0.0f, inv_a = 0.0f;  // inv_a == 0: no per-row span (degenerate conic)
+            float two_tau_a = 0.0f, det = 0.0f, inv_a = 0.0f;
             if (eg_extent(r0.z, r1.x, r1.y, r1.z, hx, hy, tau)) {
                 // pixel j (centre j + 0.5) is reachable iff  mx - hx <= j + 0.5 <= mx + hx
                 const float fx0 = r0.x - (float)X0, fy0 = r0.y - (float)Y0;
@@ -106,7 +119,7 @@ __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
                 const int ylo = max(0, (int)ceilf(fminf(fy0 - hy - 0.5f, 64.0f)));
                 const int yhi = min(ymax, (int)floorf(fmaxf(fy0 + hy - 0.5f, -64.0f)));
                 if (xlo <= xhi && ylo <= yhi) {
-                    area = (xhi - xlo + 1) * (yhi - ylo + 1);
+                    nrows = yhi - ylo + 1;
                     rect = xlo | (xhi << 4) | (ylo << 8) | (yhi << 12);
                 }
                 if (hx < 1e29f) {
@@ -119,125 +132,111 @@ __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
             sB[tid] = make_float4(r1.x, r1.y, r1.z, __int_as_float(gid));
             sC[tid] = make_float4(two_tau_a, det, inv_a, 0.0f);
         }
-        // ---- 2. block-wide exclusive prefix sum of the areas ----
-        int incl = area;
+        int incl = nrows;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const int y = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += y;
+            const int v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
         }
         if (lane == 31) s_wsum[warp] = incl;
         __syncthreads();
-        int wbase = 0, total = 0;
+        int wbase = 0, n_items = 0;
 #pragma unroll
         for (int w = 0; w < RB_THREADS / 32; ++w) {
             const int v = s_wsum[w];
             if (w < warp) wbase += v;
-            total += v;
+            n_items += v;
         }
-        s_off[tid] = wbase + incl - area;
-        if (tid == 0) s_off[RB_THREADS] = total;
+        if (n_items == 0) continue;  // uniform over the CTA
+        const int excl = wbase + incl - nrows;
+        s_roff[tid] = excl;
+        for (int r = 0; r < nrows; ++r) s_item_g[excl + r] = (unsigned char)tid;
         __syncthreads();
-        if (total == 0) continue;
 
-        // ---- 3. every thread takes an equal slice of the (Gaussian, rectangle pixel) pair list ----
-        const int chunk = (total + RB_THREADS - 1) / RB_THREADS;
-        int p = tid * chunk;
-        const int p_end = min(total, p + chunk);
-        // binary search: largest g with s_off[g] <= p
-        int lo = 0, hi = RB_THREADS;
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (s_off[mid] <= p) lo = mid; else hi = mid;
+        // ---- B. one (Gaussian, row) item per thread: candidate pixel mask of the row ----
+        for (int i = tid; i < n_items; i += RB_THREADS) {
+            const int g = s_item_g[i];
+            const float4 a = sA[g], sp = sC[g];
+            const int rect = __float_as_int(a.w);
+            const int y = ((rect >> 8) & 15) + (i - s_roff[g]);
+            int xs = rect & 15, xe = (rect >> 4) & 15;
+            unsigned mask = 0;
+            if (b0 + g <= s_rowlast[y]) {
+                if (sp.z != 0.0f) {
+                    // sigma(dx, dy) <= tau  <=>  |dx - c| <= hw,  c = -B dy / A,  hw = sqrt(2 A tau - det dy^2) / A
+                    const float dy = a.y - (Y0f + (float)y);
+                    const float D = fmaf(-sp.y * dy, dy, sp.x);
+                    if (D < 0.0f) {
+                        xe = -1;
+                    } else {
+                        const float hw = sqrtf(D) * sp.z * 1.0001f + 2e-3f;
+                        const float cpx = a.x + sB[g].y * dy * sp.z - X0f;  // in-tile pixel coordinate of the span centre
+                        xs = max(xs, (int)ceilf(fminf(cpx - hw, 64.0f)));
+                        xe = min(xe, (int)floorf(fmaxf(cpx + hw, -64.0f)));
+                    }
+                }
+                if (xs <= xe) mask = ((2u << xe) - 1u) & ~((1u << xs) - 1u) & s_rowmask[y];
+            }
+            s_item[i] = mask | ((unsigned)y << 16) | ((unsigned)g << 20);
         }
-        int g = lo;
-        // walk state of the cheap phase (valid while p < seg_end)
-        int seg_end = p, x = 0, y = 0, xlo = 0, xhi = 0, xs = 0, xe = -1, kk = 0;
-        float two_tau_a = 0.f, det = 0.f, inv_a = 0.f, mx = 0.f, my = 0.f, cb = 0.f;
-        // accumulation state of the heavy phase
-        int cur_g = -1;
+        __syncthreads();
+
+        // ---- C. equal runs of items per thread; one candidate pixel per step ----
+        const int per = (n_items + RB_THREADS - 1) / RB_THREADS;
+        int i = tid * per;
+        const int i_end = min(n_items, i + per);
+        int cur_g = -1, kk = 0, rowbase = 0, gid = 0;
+        unsigned mask = 0;
+        float mx = 0.f, my = 0.f, op = 0.f, cA = 0.f, cB = 0.f, cC = 0.f, dy = 0.f;
         PairAcc acc;
         acc_zero(acc);
-
         for (;;) {
-            // ---- 3a. cheap phase: collect up to PAIR_CAP pairs that can contribute ----
-            int cnt = 0;
-            while (cnt < PAIR_CAP && p < p_end) {
-                if (p >= seg_end) {  // enter the next Gaussian of the slice
-                    while (s_off[g + 1] <= p) ++g;
-                    const float4 a = sA[g], sp = sC[g];
-                    const int rect = __float_as_int(a.w);
-                    xlo = rect & 15; xhi = (rect >> 4) & 15;
-                    const int ylo = (rect >> 8) & 15, wbox = xhi - xlo + 1;
-                    const int local = p - s_off[g], row0 = local / wbox;
-                    y = ylo + row0; x = xlo + local - row0 * wbox;
-                    seg_end = min(p_end, s_off[g + 1]);
-                    kk = b0 + g;
-                    mx = a.x; my = a.y; cb = sB[g].y;
-                    two_tau_a = sp.x; det = sp.y; inv_a = sp.z;
-                    xe = -2;  // forces the row span computation below
-                }
-                if (xe == -2) {  // first pixel of a row: sigma <= tau  <=>  |dx - c| <= hw
-                    xs = xlo; xe = xhi;
-                    if (inv_a != 0.0f) {
-                        const float dy = my - (Y0f + (float)y);
-                        const float D = fmaf(-det * dy, dy, two_tau_a);
-                        if (D < 0.0f) {
-                            xe = -1;
-                        } else {
-                            const float hw = sqrtf(D) * inv_a * 1.0001f + 2e-3f;
-                            const float cpx = mx + cb * dy * inv_a - X0f;
-                            xs = max(xs, (int)ceilf(fminf(cpx - hw, 64.0f)));
-                            xe = min(xe, (int)floorf(fmaxf(cpx + hw, -64.0f)));
-                        }
+            if (mask == 0) {
+                if (i >= i_end) break;
+                const unsigned item = s_item[i++];
+                mask = item & 0xffffu;
+                if (mask != 0) {
+                    const int g = (int)(item >> 20);
+                    const int y = (int)((item >> 16) & 15u);
+                    if (g != cur_g) {
+                        if (cur_g >= 0) acc_flush(acc, grad2d, gid);
+                        acc_zero(acc);
+                        const float4 a = sA[g], cn = sB[g];
+                        mx = a.x; my = a.y; op = a.z;
+                        cA = cn.x; cB = cn.y; cC = cn.z; gid = __float_as_int(cn.w);
+                        cur_g = g;
+                        kk = b0 + g;
                     }
+                    dy = my - (Y0f + (float)y);
+                    rowbase = y * EG_TILE;
                 }
-                if (x >= xs && x <= xe) {
-                    const int idx = y * EG_TILE + x;
-                    const float2 pw = s_pix[idx];
-                    if (pw.x != 0.0f && kk <= __float_as_int(pw.y)) {
-                        s_buf[cnt * RB_THREADS + tid] = (unsigned short)(idx | (g << 8));
-                        ++cnt;
-                    }
-                }
-                ++p;
-                if (++x > xhi) { x = xlo; ++y; xe = -2; }
+                continue;
             }
-            // ---- 3b. heavy phase: all lanes of the warp evaluate their collected pairs together ----
-            for (int i = 0; i < cnt; ++i) {
-                const int e = s_buf[i * RB_THREADS + tid];
-                const int eg = e >> 8;
-                if (eg != cur_g) {
-                    if (cur_g >= 0) acc_flush(acc, grad2d, __float_as_int(sB[cur_g].w));
-                    acc_zero(acc);
-                    cur_g = eg;
-                }
-                const float4 a = sA[eg], cn = sB[eg];
-                const float w = s_pix[e & 255].x;
-                const float dx = a.x - (X0f + (float)(e & 15)), dy = a.y - (Y0f + (float)((e >> 4) & 15));
-                const float sigma = eg_sigma(cn.x, cn.y, cn.z, dx, dy);
-                const float vis = eg_vis(sigma);
-                const float ov = __fmul_rn(a.z, vis);
-                if (sigma >= 0.0f && ov >= EG_ALPHA_MIN && ov <= EG_ALPHA_MAX) {
-                    const float ra = __fdividef(1.0f, 1.0f - ov);
-                    const float v_al = w * ra;
-                    const float v_sigma = -ov * v_al;
-                    const float gx = v_sigma * fmaf(cn.x, dx, cn.y * dy);
-                    const float gy = v_sigma * fmaf(cn.y, dx, cn.z * dy);
-                    const float hs = 0.5f * v_sigma;
-                    acc.gx += gx;
-                    acc.gy += gy;
-                    acc.ax += fabsf(gx);
-                    acc.ay += fabsf(gy);
-                    acc.ca = fmaf(hs * dx, dx, acc.ca);
-                    acc.cb = fmaf(v_sigma * dx, dy, acc.cb);
-                    acc.cc = fmaf(hs * dy, dy, acc.cc);
-                    acc.go = fmaf(vis, v_al, acc.go);
-                }
+            const int x = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float2 pw = s_pix[rowbase + x];
+            const float dx = mx - (X0f + (float)x);
+            const float sigma = eg_sigma(cA, cB, cC, dx, dy);
+            const float vis = eg_vis(sigma);
+            const float ov = __fmul_rn(op, vis);
+            if (kk <= __float_as_int(pw.y) && sigma >= 0.0f && ov >= EG_ALPHA_MIN && ov <= EG_ALPHA_MAX) {
+                const float ra = __fdividef(1.0f, 1.0f - ov);
+                const float v_al = pw.x * ra;
+                const float v_sigma = -ov * v_al;
+                const float gx = v_sigma * fmaf(cA, dx, cB * dy);
+                const float gy = v_sigma * fmaf(cB, dx, cC * dy);
+                const float hs = 0.5f * v_sigma;
+                acc.gx += gx;
+                acc.gy += gy;
+                acc.ax += fabsf(gx);
+                acc.ay += fabsf(gy);
+                acc.ca = fmaf(hs * dx, dx, acc.ca);
+                acc.cb = fmaf(v_sigma * dx, dy, acc.cb);
+                acc.cc = fmaf(hs * dy, dy, acc.cc);
+                acc.go = fmaf(vis, v_al, acc.go);
             }
-            if (__all_sync(0xffffffffu, p >= p_end)) break;
         }
-        if (cur_g >= 0) acc_flush(acc, grad2d, __float_as_int(sB[cur_g].w));
+        if (cur_g >= 0) acc_flush(acc, grad2d, gid);
     }
 }
 
