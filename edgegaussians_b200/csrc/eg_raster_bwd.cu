@@ -17,10 +17,13 @@
 //   B. one thread per work item: the exact pixel span of that row inside the footprint ellipse
 //      (sigma <= ln(255*opacity), solved analytically) intersected with the row's bitmask of pixels
 //      whose backward seed is non-zero -> a 16-bit candidate mask per item;
-//   C. every thread takes an equal contiguous run of items and walks the set bits: each step is one
-//      (Gaussian, pixel) pair that almost surely contributes.  The 8 per-Gaussian gradient values
-//      accumulate in registers (no warp reductions) and leave as two 128-bit vector reductions
-//      (red.global.add.v4.f32) when the run moves on to the next Gaussian (about 2 flushes/thread).
+//      the masks are expanded (block scan of their popcounts) into a flat list of candidate
+//      (Gaussian, pixel) pairs in shared memory;
+//   C. every thread takes an EQUAL contiguous slice of the candidate list: each step is one pair
+//      that almost surely contributes, every lane of every warp does the same work.  The 8
+//      per-Gaussian gradient values accumulate in registers (no warp reductions) and leave as two
+//      128-bit vector reductions (red.global.add.v4.f32) when the slice moves on to the next
+//      Gaussian (about 2 flushes per thread).
 // The per-pixel state (seed * T_final, last contributor) lives in shared memory.
 #include "eg_common.cuh"
 
@@ -28,6 +31,7 @@ namespace {
 
 constexpr int RB_THREADS = 256;
 constexpr int MAX_ITEMS = RB_THREADS * EG_TILE;  // (Gaussian, row) items of one batch
+constexpr int CAND_CAP = 8192;                   // candidate (Gaussian, pixel) pairs expanded per round
 
 struct PairAcc {
     float gx, gy, ax, ay, ca, cb, cc, go;
@@ -55,10 +59,9 @@ __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
     __shared__ __align__(16) float4 sA[RB_THREADS];    // mean2d.x, mean2d.y, opacity, packed pixel rectangle
     __shared__ __align__(16) float4 sB[RB_THREADS];    // conic a, b, c, gaussian id
     __shared__ __align__(16) float4 sC[RB_THREADS];    // 2*A*tau, det(conic), 1/A (0 = no row span), -
-    __shared__ int s_roff[RB_THREADS + 1];             // exclusive prefix of the rectangle heights
     __shared__ int s_wsum[RB_THREADS / 32];
-    __shared__ unsigned char s_item_g[MAX_ITEMS];      // item -> Gaussian of the batch
     __shared__ unsigned s_item[MAX_ITEMS];             // candidate mask | row << 16 | Gaussian << 20
+    __shared__ unsigned short s_cand[CAND_CAP];        // pixel (y << 4 | x) | Gaussian << 8
 
     if (status[EG_ST_OVERFLOW]) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -149,16 +152,21 @@ __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
         }
         if (n_items == 0) continue;  // uniform over the CTA
         const int excl = wbase + incl - nrows;
-        s_roff[tid] = excl;
-        for (int r = 0; r < nrows; ++r) s_item_g[excl + r] = (unsigned char)tid;
+        {
+            const int ylo = (__float_as_int(sA[tid].w) >> 8) & 15;
+            for (int r = 0; r < nrows; ++r) s_item[excl + r] = ((unsigned)(ylo + r) << 16) | ((unsigned)tid << 20);
+        }
         __syncthreads();
 
-        // ---- B. one (Gaussian, row) item per thread: candidate pixel mask of the row ----
-        for (int i = tid; i < n_items; i += RB_THREADS) {
-            const int g = s_item_g[i];
+        // ---- B. (Gaussian, row) items: candidate pixel mask of the row; equal runs of items per thread ----
+        const int per = (n_items + RB_THREADS - 1) / RB_THREADS;
+        const int i0 = tid * per, i1 = min(n_items, i0 + per);
+        int cnt = 0;
+        for (int i = i0; i < i1; ++i) {
+            const unsigned item = s_item[i];
+            const int g = (int)(item >> 20), y = (int)((item >> 16) & 15u);
             const float4 a = sA[g], sp = sC[g];
             const int rect = __float_as_int(a.w);
-            const int y = ((rect >> 8) & 15) + (i - s_roff[g]);
             int xs = rect & 15, xe = (rect >> 4) & 15;
             unsigned mask = 0;
             if (b0 + g <= s_rowlast[y]) {
@@ -177,66 +185,89 @@ __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
                 }
                 if (xs <= xe) mask = ((2u << xe) - 1u) & ~((1u << xs) - 1u) & s_rowmask[y];
             }
-            s_item[i] = mask | ((unsigned)y << 16) | ((unsigned)g << 20);
+            s_item[i] = item | mask;
+            cnt += __popc(mask);
         }
+        // block scan of the candidate counts
+        int cincl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, cincl, d);
+            if (lane >= d) cincl += v;
+        }
+        __syncthreads();  // everyone is done reading s_wsum of stage A
+        if (lane == 31) s_wsum[warp] = cincl;
         __syncthreads();
-
-        // ---- C. equal runs of items per thread; one candidate pixel per step ----
-        const int per = (n_items + RB_THREADS - 1) / RB_THREADS;
-        int i = tid * per;
-        const int i_end = min(n_items, i + per);
-        int cur_g = -1, kk = 0, rowbase = 0, gid = 0;
-        unsigned mask = 0;
-        float mx = 0.f, my = 0.f, op = 0.f, cA = 0.f, cB = 0.f, cC = 0.f, dy = 0.f;
-        PairAcc acc;
-        acc_zero(acc);
-        for (;;) {
-            if (mask == 0) {
-                if (i >= i_end) break;
-                const unsigned item = s_item[i++];
-                mask = item & 0xffffu;
-                if (mask != 0) {
-                    const int g = (int)(item >> 20);
-                    const int y = (int)((item >> 16) & 15u);
-                    if (g != cur_g) {
-                        if (cur_g >= 0) acc_flush(acc, grad2d, gid);
-                        acc_zero(acc);
-                        const float4 a = sA[g], cn = sB[g];
-                        mx = a.x; my = a.y; op = a.z;
-                        cA = cn.x; cB = cn.y; cC = cn.z; gid = __float_as_int(cn.w);
-                        cur_g = g;
-                        kk = b0 + g;
-                    }
-                    dy = my - (Y0f + (float)y);
-                    rowbase = y * EG_TILE;
-                }
-                continue;
-            }
-            const int x = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const float2 pw = s_pix[rowbase + x];
-            const float dx = mx - (X0f + (float)x);
-            const float sigma = eg_sigma(cA, cB, cC, dx, dy);
-            const float vis = eg_vis(sigma);
-            const float ov = __fmul_rn(op, vis);
-            if (kk <= __float_as_int(pw.y) && sigma >= 0.0f && ov >= EG_ALPHA_MIN && ov <= EG_ALPHA_MAX) {
-                const float ra = __fdividef(1.0f, 1.0f - ov);
-                const float v_al = pw.x * ra;
-                const float v_sigma = -ov * v_al;
-                const float gx = v_sigma * fmaf(cA, dx, cB * dy);
-                const float gy = v_sigma * fmaf(cB, dx, cC * dy);
-                const float hs = 0.5f * v_sigma;
-                acc.gx += gx;
-                acc.gy += gy;
-                acc.ax += fabsf(gx);
-                acc.ay += fabsf(gy);
-                acc.ca = fmaf(hs * dx, dx, acc.ca);
-                acc.cb = fmaf(v_sigma * dx, dy, acc.cb);
-                acc.cc = fmaf(hs * dy, dy, acc.cc);
-                acc.go = fmaf(vis, v_al, acc.go);
-            }
+        int cbase = 0, n_cand = 0;
+#pragma unroll
+        for (int w = 0; w < RB_THREADS / 32; ++w) {
+            const int v = s_wsum[w];
+            if (w < warp) cbase += v;
+            n_cand += v;
         }
-        if (cur_g >= 0) acc_flush(acc, grad2d, gid);
+        const int coff = cbase + cincl - cnt;  // index of this thread's first candidate
+
+        for (int r0 = 0; r0 < n_cand; r0 += CAND_CAP) {  // one round unless the batch has > CAND_CAP candidates
+            if (r0 > 0) __syncthreads();                 // previous round fully consumed
+            // expand this thread's items into the flat candidate list of the round
+            int j = coff - r0;
+            for (int i = i0; i < i1 && j < CAND_CAP; ++i) {
+                const unsigned item = s_item[i];
+                unsigned mask = item & 0xffffu;
+                const unsigned hi = ((item >> 20) << 8) | (((item >> 16) & 15u) << 4);
+                while (mask) {
+                    const int x = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    if (j >= 0 && j < CAND_CAP) s_cand[j] = (unsigned short)(hi | (unsigned)x);
+                    ++j;
+                }
+            }
+            __syncthreads();
+
+            // ---- C. equal slices of the candidate list; one (Gaussian, pixel) pair per step ----
+            const int n_round = min(CAND_CAP, n_cand - r0);
+            const int per_c = (n_round + RB_THREADS - 1) / RB_THREADS;
+            const int c0 = tid * per_c, c1 = min(n_round, c0 + per_c);
+            int cur_g = -1, kk = 0, gid = 0;
+            float mx = 0.f, my = 0.f, op = 0.f, cA = 0.f, cB = 0.f, cC = 0.f;
+            PairAcc acc;
+            acc_zero(acc);
+            for (int c = c0; c < c1; ++c) {
+                const unsigned e = s_cand[c];
+                const int g = (int)(e >> 8);
+                if (g != cur_g) {
+                    if (cur_g >= 0) acc_flush(acc, grad2d, gid);
+                    acc_zero(acc);
+                    const float4 a = sA[g], cn = sB[g];
+                    mx = a.x; my = a.y; op = a.z;
+                    cA = cn.x; cB = cn.y; cC = cn.z; gid = __float_as_int(cn.w);
+                    cur_g = g;
+                    kk = b0 + g;
+                }
+                const float2 pw = s_pix[e & 255u];
+                const float dx = mx - (X0f + (float)(e & 15u)), dy = my - (Y0f + (float)((e >> 4) & 15u));
+                const float sigma = eg_sigma(cA, cB, cC, dx, dy);
+                const float vis = eg_vis(sigma);
+                const float ov = __fmul_rn(op, vis);
+                if (kk <= __float_as_int(pw.y) && sigma >= 0.0f && ov >= EG_ALPHA_MIN && ov <= EG_ALPHA_MAX) {
+                    const float ra = __fdividef(1.0f, 1.0f - ov);
+                    const float v_al = pw.x * ra;
+                    const float v_sigma = -ov * v_al;
+                    const float gx = v_sigma * fmaf(cA, dx, cB * dy);
+                    const float gy = v_sigma * fmaf(cB, dx, cC * dy);
+                    const float hs = 0.5f * v_sigma;
+                    acc.gx += gx;
+                    acc.gy += gy;
+                    acc.ax += fabsf(gx);
+                    acc.ay += fabsf(gy);
+                    acc.ca = fmaf(hs * dx, dx, acc.ca);
+                    acc.cb = fmaf(v_sigma * dx, dy, acc.cb);
+                    acc.cc = fmaf(hs * dy, dy, acc.cc);
+                    acc.go = fmaf(vis, v_al, acc.go);
+                }
+            }
+            if (cur_g >= 0) acc_flush(acc, grad2d, gid);
+        }
     }
 }
 
