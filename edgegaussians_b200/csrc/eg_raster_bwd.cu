@@ -17,9 +17,8 @@
 //   B. one thread per work item: the exact pixel span of that row inside the footprint ellipse
 //      (sigma <= ln(255*opacity), solved analytically) intersected with the row's bitmask of pixels
 //      whose backward seed is non-zero -> a 16-bit candidate mask per item;
-//      the masks are expanded (block scan of their popcounts) into a flat list of candidate
-//      (Gaussian, pixel) pairs in shared memory;
-//   C. every thread takes an EQUAL contiguous slice of the candidate list: each step is one pair
+//      a block scan of the popcounts linearises all candidate (Gaussian, pixel) pairs of the batch;
+//   C. every thread takes an EQUAL contiguous slice of that candidate list: each step is one pair
 //      that almost surely contributes, every lane of every warp does the same work.  The 8
 //      per-Gaussian gradient values accumulate in registers (no warp reductions) and leave as two
 //      128-bit vector reductions (red.global.add.v4.f32) when the slice moves on to the next
@@ -31,7 +30,6 @@ namespace {
 
 constexpr int RB_THREADS = 256;
 constexpr int MAX_ITEMS = RB_THREADS * EG_TILE;  // (Gaussian, row) items of one batch
-constexpr int CAND_CAP = 8192;                   // candidate (Gaussian, pixel) pairs expanded per round
 
 struct PairAcc {
     float gx, gy, ax, ay, ca, cb, cc, go;
@@ -61,7 +59,7 @@ __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
     __shared__ __align__(16) float4 sC[RB_THREADS];    // 2*A*tau, det(conic), 1/A (0 = no row span), -
     __shared__ int s_wsum[RB_THREADS / 32];
     __shared__ unsigned s_item[MAX_ITEMS];             // candidate mask | row << 16 | Gaussian << 20
-    __shared__ unsigned short s_cand[CAND_CAP];        // pixel (y << 4 | x) | Gaussian << 8
+    __shared__ int s_ioff[MAX_ITEMS];                  // exclusive prefix of the items' candidate counts
 
     if (status[EG_ST_OVERFLOW]) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -186,9 +184,10 @@ __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
                 if (xs <= xe) mask = ((2u << xe) - 1u) & ~((1u << xs) - 1u) & s_rowmask[y];
             }
             s_item[i] = item | mask;
+            s_ioff[i] = cnt;  // thread-local exclusive candidate offset, rebased below
             cnt += __popc(mask);
         }
-        // block scan of the candidate counts
+        // block scan of the per-thread candidate counts
         int cincl = cnt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -205,69 +204,78 @@ __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
             if (w < warp) cbase += v;
             n_cand += v;
         }
-        const int coff = cbase + cincl - cnt;  // index of this thread's first candidate
+        const int coff = cbase + cincl - cnt;
+        for (int i = i0; i < i1; ++i) s_ioff[i] += coff;
+        __syncthreads();
+        if (n_cand == 0) continue;  // uniform over the CTA
 
-        for (int r0 = 0; r0 < n_cand; r0 += CAND_CAP) {  // one round unless the batch has > CAND_CAP candidates
-            if (r0 > 0) __syncthreads();                 // previous round fully consumed
-            // expand this thread's items into the flat candidate list of the round
-            int j = coff - r0;
-            for (int i = i0; i < i1 && j < CAND_CAP; ++i) {
-                const unsigned item = s_item[i];
-                unsigned mask = item & 0xffffu;
-                const unsigned hi = ((item >> 20) << 8) | (((item >> 16) & 15u) << 4);
-                while (mask) {
-                    const int x = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    if (j >= 0 && j < CAND_CAP) s_cand[j] = (unsigned short)(hi | (unsigned)x);
-                    ++j;
-                }
-            }
-            __syncthreads();
-
-            // ---- C. equal slices of the candidate list; one (Gaussian, pixel) pair per step ----
-            const int n_round = min(CAND_CAP, n_cand - r0);
-            const int per_c = (n_round + RB_THREADS - 1) / RB_THREADS;
-            const int c0 = tid * per_c, c1 = min(n_round, c0 + per_c);
-            int cur_g = -1, kk = 0, gid = 0;
-            float mx = 0.f, my = 0.f, op = 0.f, cA = 0.f, cB = 0.f, cC = 0.f;
-            PairAcc acc;
-            acc_zero(acc);
-            for (int c = c0; c < c1; ++c) {
-                const unsigned e = s_cand[c];
-                const int g = (int)(e >> 8);
-                if (g != cur_g) {
-                    if (cur_g >= 0) acc_flush(acc, grad2d, gid);
+        // ---- C. equal slices of the (implicit) candidate list; one (Gaussian, pixel) pair per step ----
+        const int per_c = (n_cand + RB_THREADS - 1) / RB_THREADS;
+        const int c0 = tid * per_c;
+        int remaining = min(n_cand, c0 + per_c) - c0;
+        if (remaining <= 0) continue;
+        // largest item i with s_ioff[i] <= c0 that still has candidates beyond c0
+        int lo = 0, hi = n_items;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (s_ioff[mid] <= c0) lo = mid; else hi = mid;
+        }
+        int i = lo;
+        unsigned item = s_item[i];
+        unsigned mask = item & 0xffffu;
+        for (int q = c0 - s_ioff[i]; q > 0; --q) mask &= mask - 1;  // candidates of this item owned by the previous slice
+        int g = (int)(item >> 20);
+        float4 a = sA[g], cn = sB[g];
+        int y = (int)((item >> 16) & 15u);
+        float dy = a.y - (Y0f + (float)y);
+        int rowbase = y * EG_TILE, kk = b0 + g;
+        PairAcc acc;
+        acc_zero(acc);
+        while (remaining > 0) {
+            if (mask == 0) {  // next non-empty item (exists because remaining > 0)
+                do {
+                    item = s_item[++i];
+                    mask = item & 0xffffu;
+                } while (mask == 0);
+                const int gn = (int)(item >> 20);
+                if (gn != g) {
+                    acc_flush(acc, grad2d, __float_as_int(cn.w));
                     acc_zero(acc);
-                    const float4 a = sA[g], cn = sB[g];
-                    mx = a.x; my = a.y; op = a.z;
-                    cA = cn.x; cB = cn.y; cC = cn.z; gid = __float_as_int(cn.w);
-                    cur_g = g;
+                    g = gn;
+                    a = sA[g];
+                    cn = sB[g];
                     kk = b0 + g;
                 }
-                const float2 pw = s_pix[e & 255u];
-                const float dx = mx - (X0f + (float)(e & 15u)), dy = my - (Y0f + (float)((e >> 4) & 15u));
-                const float sigma = eg_sigma(cA, cB, cC, dx, dy);
-                const float vis = eg_vis(sigma);
-                const float ov = __fmul_rn(op, vis);
-                if (kk <= __float_as_int(pw.y) && sigma >= 0.0f && ov >= EG_ALPHA_MIN && ov <= EG_ALPHA_MAX) {
-                    const float ra = __fdividef(1.0f, 1.0f - ov);
-                    const float v_al = pw.x * ra;
-                    const float v_sigma = -ov * v_al;
-                    const float gx = v_sigma * fmaf(cA, dx, cB * dy);
-                    const float gy = v_sigma * fmaf(cB, dx, cC * dy);
-                    const float hs = 0.5f * v_sigma;
-                    acc.gx += gx;
-                    acc.gy += gy;
-                    acc.ax += fabsf(gx);
-                    acc.ay += fabsf(gy);
-                    acc.ca = fmaf(hs * dx, dx, acc.ca);
-                    acc.cb = fmaf(v_sigma * dx, dy, acc.cb);
-                    acc.cc = fmaf(hs * dy, dy, acc.cc);
-                    acc.go = fmaf(vis, v_al, acc.go);
-                }
+                y = (int)((item >> 16) & 15u);
+                dy = a.y - (Y0f + (float)y);
+                rowbase = y * EG_TILE;
             }
-            if (cur_g >= 0) acc_flush(acc, grad2d, gid);
+            const int x = __ffs(mask) - 1;
+            mask &= mask - 1;
+            --remaining;
+            const float2 pw = s_pix[rowbase + x];
+            const float dx = a.x - (X0f + (float)x);
+            const float sigma = eg_sigma(cn.x, cn.y, cn.z, dx, dy);
+            const float vis = eg_vis(sigma);
+            const float ov = __fmul_rn(a.z, vis);
+            if (kk <= __float_as_int(pw.y) && sigma >= 0.0f && ov >= EG_ALPHA_MIN && ov <= EG_ALPHA_MAX) {
+                const float ra = __fdividef(1.0f, 1.0f - ov);
+                const float v_al = pw.x * ra;
+                const float v_sigma = -ov * v_al;
+                const float gx = v_sigma * fmaf(cn.x, dx, cn.y * dy);
+                const float gy = v_sigma * fmaf(cn.y, dx, cn.z * dy);
+                const float hs = 0.5f * v_sigma;
+                acc.gx += gx;
+                acc.gy += gy;
+                acc.ax += fabsf(gx);
+                acc.ay += fabsf(gy);
+                acc.ca = fmaf(hs * dx, dx, acc.ca);
+                acc.cb = fmaf(v_sigma * dx, dy, acc.cb);
+                acc.cc = fmaf(hs * dy, dy, acc.cc);
+                acc.go = fmaf(vis, v_al, acc.go);
+            }
         }
+        acc_flush(acc, grad2d, __float_as_int(cn.w));
     }
 }
 
