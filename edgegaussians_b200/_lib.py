@@ -12,7 +12,7 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_C", "libedgegs.so")
 
-EG_ST_NISECT, EG_ST_OVERFLOW, EG_ST_BADCOLOR, EG_ST_NVISIBLE, EG_ST_WORDS = 0, 1, 2, 3, 8
+EG_ST_NISECT, EG_ST_OVERFLOW, EG_ST_BADCOLOR, EG_ST_MAXTILE, EG_ST_WORDS = 0, 1, 2, 3, 8
 EG_GT_NONE, EG_GT_F32, EG_GT_U8 = 0, 1, 2
 EG_CNT_STRIDE = 32
 
@@ -23,7 +23,8 @@ EXPORTS = ["eg_last_error", "eg_abi_version", "eg_tile_grid", "eg_project_fwd", 
 class EgConfig(Structure):
     _fields_ = [("n", c_int32), ("width", c_int32), ("height", c_int32), ("tile_size", c_int32),
                 ("eps2d", c_float), ("near_plane", c_float), ("far_plane", c_float), ("radius_clip", c_float),
-                ("antialiased", c_int32), ("raw_params", c_int32), ("isect_capacity", c_int64)]
+                ("antialiased", c_int32), ("raw_params", c_int32), ("isect_capacity", c_int64),
+                ("tile_capacity", c_int32), ("reserved", c_int32)]
 
 
 _lib = None
@@ -48,11 +49,11 @@ def load(build_if_missing: bool = True):
     P = c_void_p
     cfgp = POINTER(EgConfig)
     lib.eg_tile_grid.argtypes = [c_int, c_int, c_int, POINTER(c_int), POINTER(c_int)]
-    lib.eg_project_fwd.argtypes = [cfgp] + [P] * 12
-    lib.eg_bin.argtypes = [cfgp] + [P] * 7
+    lib.eg_project_fwd.argtypes = [cfgp] + [P] * 13
+    lib.eg_bin.argtypes = [cfgp] + [P] * 4
     lib.eg_raster_fwd.argtypes = [cfgp] + [P] * 9 + [c_int, P, P, P, P]
     lib.eg_raster_bwd.argtypes = [cfgp] + [P] * 6 + [c_int, P, P, c_float, P, P, P]
-    lib.eg_project_bwd.argtypes = [cfgp] + [P] * 16
+    lib.eg_project_bwd.argtypes = [cfgp] + [P] * 9 + [c_int] + [P] * 7
     lib.eg_reg_fwd_bwd.argtypes = [c_int, P, P, P, P, c_int, c_int, c_int, c_float, c_float, P, P, P, P, P]
     for name in EXPORTS[2:]:
         getattr(lib, name).restype = c_int

@@ -12,26 +12,35 @@
 namespace {
 
 template <bool RAW>
-__global__ void __launch_bounds__(256) project_bwd_kernel(
+__global__ void __launch_bounds__(128) project_bwd_kernel(
     const eg_config cfg, const float *__restrict__ means, const float *__restrict__ quats,
     const float *__restrict__ scales, const float *__restrict__ opacities, const float *__restrict__ viewmat,
     const float *__restrict__ Kmat, const float4 *__restrict__ rec, const int2 *__restrict__ gint,
-    const float4 *__restrict__ grad2d, const float *__restrict__ v_depths, float *__restrict__ v_means,
+    float4 *__restrict__ grad2d, int zero_grad2d, const float *__restrict__ v_depths, float *__restrict__ v_means,
     float *__restrict__ v_quats, float *__restrict__ v_scales, float *__restrict__ v_opacities,
     float *__restrict__ absgrad_accum) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= cfg.n) return;
     float vm[3] = {0.f, 0.f, 0.f}, vs[3] = {0.f, 0.f, 0.f}, vq[4] = {0.f, 0.f, 0.f, 0.f}, vo = 0.f;
+    // issue every load up front (streaming kernel: bytes in flight per thread are what hides DRAM latency)
     const int2 gi = __ldg(gint + g);
+    const float4 r1 = __ldg(rec + 2 * g + 1);
+    const float4 g0 = grad2d[2 * g], g1 = grad2d[2 * g + 1];
+    const float4 q4 = __ldg(reinterpret_cast<const float4 *>(quats) + g);
+    const float mx = __ldg(means + 3 * g), my = __ldg(means + 3 * g + 1), mz = __ldg(means + 3 * g + 2);
+    float s[3];
+    s[0] = __ldg(scales + 3 * g); s[1] = __ldg(scales + 3 * g + 1); s[2] = __ldg(scales + 3 * g + 2);
+    float o = __ldg(opacities + g);
+    if (zero_grad2d) {  // leave the accumulator clean for the next iteration's atomics
+        grad2d[2 * g] = make_float4(0.f, 0.f, 0.f, 0.f);
+        grad2d[2 * g + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     if (gi.x > 0) {
         const EgCam cam = eg_load_cam(viewmat, Kmat);
         const float *R = cam.R;
-        const float4 r0 = __ldg(rec + 2 * g), r1 = __ldg(rec + 2 * g + 1);
-        const float4 g0 = __ldg(grad2d + 2 * g), g1 = __ldg(grad2d + 2 * g + 1);
         const float A = r1.x, B = r1.y, C = r1.z, comp = r1.w;
         if (absgrad_accum != nullptr) absgrad_accum[g] += sqrtf(g0.z * g0.z + g0.w * g0.w);
 
-        float o = __ldg(opacities + g);
         if (RAW) o = 1.0f / (1.0f + expf(-o));
         float v_comp = 0.0f;
         if (cfg.antialiased) {
@@ -59,11 +68,9 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(
         }
 
         // recompute the forward intermediates
-        const float mx = __ldg(means + 3 * g), my = __ldg(means + 3 * g + 1), mz = __ldg(means + 3 * g + 2);
         const float x = R[0] * mx + R[1] * my + R[2] * mz + cam.t[0];
         const float y = R[3] * mx + R[4] * my + R[5] * mz + cam.t[1];
         const float z = R[6] * mx + R[7] * my + R[8] * mz + cam.t[2];
-        const float4 q4 = __ldg(reinterpret_cast<const float4 *>(quats) + g);
         const float qn = sqrtf(q4.x * q4.x + q4.y * q4.y + q4.z * q4.z + q4.w * q4.w);
         const float iqn = 1.0f / qn;
         const float qw = q4.x * iqn, qx = q4.y * iqn, qy = q4.z * iqn, qz = q4.w * iqn;
@@ -71,8 +78,6 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(
         Rq[0][0] = 1.f - 2.f * (qy * qy + qz * qz); Rq[0][1] = 2.f * (qx * qy - qw * qz); Rq[0][2] = 2.f * (qx * qz + qw * qy);
         Rq[1][0] = 2.f * (qx * qy + qw * qz); Rq[1][1] = 1.f - 2.f * (qx * qx + qz * qz); Rq[1][2] = 2.f * (qy * qz - qw * qx);
         Rq[2][0] = 2.f * (qx * qz - qw * qy); Rq[2][1] = 2.f * (qy * qz + qw * qx); Rq[2][2] = 1.f - 2.f * (qx * qx + qy * qy);
-        float s[3];
-        s[0] = __ldg(scales + 3 * g); s[1] = __ldg(scales + 3 * g + 1); s[2] = __ldg(scales + 3 * g + 2);
         if (RAW) { s[0] = expf(s[0]); s[1] = expf(s[1]); s[2] = expf(s[2]); }
         float M[3][3], S[3][3], Tm[3][3], Sc[3][3];
 #pragma unroll
@@ -181,23 +186,25 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(
 
 extern "C" int eg_project_bwd(const eg_config *cfg, const float *means, const float *quats, const float *scales,
                               const float *opacities, const float *viewmat, const float *K, const float *rec,
-                              const int32_t *gint, const float *grad2d, const float *v_depths, float *v_means,
-                              float *v_quats, float *v_scales, float *v_opacities, float *absgrad_accum,
-                              void *stream) {
+                              const int32_t *gint, float *grad2d, int zero_grad2d, const float *v_depths,
+                              float *v_means, float *v_quats, float *v_scales, float *v_opacities,
+                              float *absgrad_accum, void *stream) {
     if (cfg == nullptr) {
         eg_set_error("eg_project_bwd: null config");
         return 1;
     }
     if (cfg->n <= 0) return 0;
-    const int block = 256, grid = (cfg->n + block - 1) / block;
+    const int block = 128, grid = (cfg->n + block - 1) / block;
     cudaStream_t s = (cudaStream_t)stream;
     if (cfg->raw_params)
         project_bwd_kernel<true><<<grid, block, 0, s>>>(*cfg, means, quats, scales, opacities, viewmat, K,
-                                                        (const float4 *)rec, (const int2 *)gint, (const float4 *)grad2d,
-                                                        v_depths, v_means, v_quats, v_scales, v_opacities, absgrad_accum);
+                                                        (const float4 *)rec, (const int2 *)gint, (float4 *)grad2d,
+                                                        zero_grad2d, v_depths, v_means, v_quats, v_scales, v_opacities,
+                                                        absgrad_accum);
     else
         project_bwd_kernel<false><<<grid, block, 0, s>>>(*cfg, means, quats, scales, opacities, viewmat, K,
-                                                         (const float4 *)rec, (const int2 *)gint, (const float4 *)grad2d,
-                                                         v_depths, v_means, v_quats, v_scales, v_opacities, absgrad_accum);
+                                                         (const float4 *)rec, (const int2 *)gint, (float4 *)grad2d,
+                                                         zero_grad2d, v_depths, v_means, v_quats, v_scales, v_opacities,
+                                                         absgrad_accum);
     return eg_check_launch("eg_project_bwd");
 }

@@ -27,7 +27,8 @@ __global__ void __launch_bounds__(256) project_fwd_kernel(
     const eg_config cfg, const float *__restrict__ means, const float *__restrict__ quats,
     const float *__restrict__ scales, const float *__restrict__ opacities, const float *__restrict__ colors,
     const float *__restrict__ viewmat, const float *__restrict__ Kmat, float4 *__restrict__ rec,
-    int2 *__restrict__ gint, int32_t *__restrict__ tile_counts, int32_t *__restrict__ status, int tw, int th) {
+    int2 *__restrict__ gint, int32_t *__restrict__ tile_counts, unsigned long long *__restrict__ keys,
+    int32_t *__restrict__ status, int tw, int th) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= cfg.n) return;
     const EgCam cam = eg_load_cam(viewmat, Kmat);
@@ -137,15 +138,22 @@ __global__ void __launch_bounds__(256) project_fwd_kernel(
     rec[2 * g] = r0;
     rec[2 * g + 1] = r1;
     gint[g] = make_int2(radius_i, ntiles);
+    // K2 emission: append (depth_bits << 32 | id) to the bucket of every tile of the rectangle
+    const unsigned long long key = ((unsigned long long)__float_as_uint(r0.w) << 32) | (unsigned int)g;
     for (uint32_t i = y0; i < y1; ++i)
-        for (uint32_t j = x0; j < x1; ++j) atomicAdd(tile_counts + (size_t)(i * tw + j) * EG_CNT_STRIDE, 1);
+        for (uint32_t j = x0; j < x1; ++j) {
+            const size_t t = (size_t)(i * tw + j);
+            const int pos = atomicAdd(tile_counts + t * EG_CNT_STRIDE, 1);
+            if (pos < cfg.tile_capacity) keys[t * (size_t)cfg.tile_capacity + pos] = key;
+        }
 }
 
 }  // namespace
 
 extern "C" int eg_project_fwd(const eg_config *cfg, const float *means, const float *quats, const float *scales,
                               const float *opacities, const float *colors, const float *viewmat, const float *K,
-                              float *rec, int32_t *gint, int32_t *tile_counts, int32_t *status, void *stream) {
+                              float *rec, int32_t *gint, int32_t *tile_counts, uint64_t *keys, int32_t *status,
+                              void *stream) {
     if (cfg == nullptr || cfg->tile_size != EG_TILE) {
         eg_set_error("eg_project_fwd: tile_size must be %d", EG_TILE);
         return 1;
@@ -157,9 +165,11 @@ extern "C" int eg_project_fwd(const eg_config *cfg, const float *means, const fl
     cudaStream_t s = (cudaStream_t)stream;
     if (cfg->raw_params)
         project_fwd_kernel<true><<<grid, block, 0, s>>>(*cfg, means, quats, scales, opacities, colors, viewmat, K,
-                                                        (float4 *)rec, (int2 *)gint, tile_counts, status, tw, th);
+                                                        (float4 *)rec, (int2 *)gint, tile_counts,
+                                                        (unsigned long long *)keys, status, tw, th);
     else
         project_fwd_kernel<false><<<grid, block, 0, s>>>(*cfg, means, quats, scales, opacities, colors, viewmat, K,
-                                                         (float4 *)rec, (int2 *)gint, tile_counts, status, tw, th);
+                                                         (float4 *)rec, (int2 *)gint, tile_counts,
+                                                         (unsigned long long *)keys, status, tw, th);
     return eg_check_launch("eg_project_fwd");
 }

@@ -214,21 +214,22 @@ __global__ void __launch_bounds__(RF_THREADS) raster_fwd_kernel(
     const bool on_chip = L <= SORT_CAP;
     if (L > 0) {
         const long long tile_hi = (long long)tile << 32;
+        u64 *bucket = keys + (size_t)tile * (size_t)cfg.tile_capacity;
         long long *isect = isect_ids ? isect_ids + start : nullptr;
         if (L <= 256) {
             int n_pad = 32;
             while (n_pad < L) n_pad <<= 1;
-            sort_segment_regs<1>(keys + start, L, n_pad, sbuf, sids, flatten_ids + start, isect, tile_hi, tid);
+            sort_segment_regs<1>(bucket, L, n_pad, sbuf, sids, flatten_ids + start, isect, tile_hi, tid);
         } else if (L <= 512) {
-            sort_segment_regs<2>(keys + start, L, 512, sbuf, sids, flatten_ids + start, isect, tile_hi, tid);
+            sort_segment_regs<2>(bucket, L, 512, sbuf, sids, flatten_ids + start, isect, tile_hi, tid);
         } else if (L <= 1024) {
-            sort_segment_regs<4>(keys + start, L, 1024, sbuf, sids, flatten_ids + start, isect, tile_hi, tid);
+            sort_segment_regs<4>(bucket, L, 1024, sbuf, sids, flatten_ids + start, isect, tile_hi, tid);
         } else if (L <= 2048) {
-            sort_segment_regs<8>(keys + start, L, 2048, sbuf, sids, flatten_ids + start, isect, tile_hi, tid);
+            sort_segment_regs<8>(bucket, L, 2048, sbuf, sids, flatten_ids + start, isect, tile_hi, tid);
         } else {
-            sort_large(keys + start, L, sbuf, tid);
+            sort_large(bucket, L, sbuf, tid);
             for (int i = tid; i < L; i += RF_THREADS) {
-                const u64 k = keys[start + i];
+                const u64 k = bucket[i];
                 flatten_ids[start + i] = (int32_t)(uint32_t)k;
                 if (isect) isect[i] = tile_hi | (long long)(k >> 32);
             }

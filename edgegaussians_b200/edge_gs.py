@@ -28,7 +28,7 @@ import torch
 
 from . import _lib
 from .cameras import BaseCamera
-from .engine import TILE, SplatState, get_engine, tile_grid, _p, _stream
+from .engine import TILE, SplatState, get_engine, tile_capacity_for, tile_grid, _p, _stream
 from .losses import MaskedL1Loss, WeightedL1Loss
 from .rasterization import rasterization
 
@@ -58,25 +58,26 @@ def random_quat_tensor(N, generator: Optional[torch.Generator] = None):
 class RasterStepWorkspace:
     """Persistent device buffers of the fused iteration for fixed (N, W, H, capacity)."""
 
-    def __init__(self, N: int, W: int, H: int, capacity: int, device):
+    def __init__(self, N: int, W: int, H: int, capacity: int, device, max_tile: int = 0):
         tw, th = tile_grid(W, H)
         T = tw * th
         f32, i32 = torch.float32, torch.int32
         self.N, self.W, self.H, self.T, self.capacity = N, W, H, T, int(capacity)
+        self.tile_capacity = tile_capacity_for(self.capacity, T, max_tile)
         self.rec = torch.empty((N, 8), dtype=f32, device=device)
         self.gint = torch.empty((N, 2), dtype=i32, device=device)
         # tile_counts | status share one allocation so a single memset clears both
-        self.zero_block = torch.zeros(T * _lib.EG_CNT_STRIDE + _lib.EG_ST_WORDS, dtype=i32, device=device)
+        self.zero_block = torch.zeros(T * _lib.EG_CNT_STRIDE + _lib.EG_ST_WORDS + 2, dtype=i32, device=device)
         self.tile_counts = self.zero_block[:T * _lib.EG_CNT_STRIDE]
-        self.status = self.zero_block[T * _lib.EG_CNT_STRIDE:]
+        self.status = self.zero_block[T * _lib.EG_CNT_STRIDE:T * _lib.EG_CNT_STRIDE + _lib.EG_ST_WORDS]
+        self.loss_sum = self.zero_block[T * _lib.EG_CNT_STRIDE + _lib.EG_ST_WORDS:].view(torch.float64)
         self.tile_offsets = torch.empty(T + 1, dtype=i32, device=device)
-        self.keys = torch.empty(self.capacity, dtype=torch.int64, device=device)
+        self.keys = torch.empty(T * self.tile_capacity, dtype=torch.int64, device=device)
         self.flatten_ids = torch.empty(self.capacity, dtype=i32, device=device)
         self.last_ids = torch.empty((H, W), dtype=i32, device=device)
         self.wpix = torch.empty((H, W), dtype=f32, device=device)
         self.render0 = torch.empty((H, W), dtype=f32, device=device)
         self.grad2d = torch.zeros((N, 8), dtype=f32, device=device)
-        self.loss_sum = torch.zeros(1, dtype=torch.float64, device=device)
         self.grads = torch.zeros(11 * N, dtype=f32, device=device)  # means | scales | quats | opacities
 
 
@@ -249,8 +250,9 @@ class EdgeGaussianSplatting(torch.nn.Module):
         ws = self._ws
         eng = get_engine(self.means.device)
         want = int(capacity) if capacity is not None else max(eng._ensure_capacity(N), ws.capacity if ws else 0)
-        if ws is None or (ws.N, ws.W, ws.H) != (N, W, H) or ws.capacity < want:
-            ws = RasterStepWorkspace(N, W, H, want, self.means.device)
+        if (ws is None or (ws.N, ws.W, ws.H) != (N, W, H) or ws.capacity < want
+                or ws.tile_capacity < tile_capacity_for(0, ws.T, eng.max_tile)):
+            ws = RasterStepWorkspace(N, W, H, want, self.means.device, eng.max_tile)
             self._ws = ws
         return ws
 
@@ -268,23 +270,20 @@ class EdgeGaussianSplatting(torch.nn.Module):
         N = ws.N
         cfg = _lib.EgConfig(n=N, width=W, height=H, tile_size=TILE, eps2d=0.3, near_plane=0.01, far_plane=1e10,
                             radius_clip=0.0, antialiased=1 if self.config.rasterize_mode == "antialiased" else 0,
-                            raw_params=1, isect_capacity=ws.capacity)
+                            raw_params=1, isect_capacity=ws.capacity, tile_capacity=ws.tile_capacity)
         c = ctypes.byref(cfg)
         s = _stream()
         gt_kind = _lib.EG_GT_U8 if gt.dtype == torch.uint8 else _lib.EG_GT_F32
         means, quats, scales, opac = self.means.data, self.quats.data, self.scales.data, self.opacities.data
         cb = stage_cb if stage_cb is not None else (lambda name: None)
         cb("begin")
-        ws.zero_block.zero_()
-        ws.grad2d.zero_()
-        ws.loss_sum.zero_()
+        ws.zero_block.zero_()   # tile counters + status + loss accumulator (grad2d is re-zeroed by eg_project_bwd)
         cb("memset")
         chk = _lib.check
         chk(lib.eg_project_fwd(c, _p(means), _p(quats), _p(scales), _p(opac), None, _p(viewmat), _p(K), _p(ws.rec),
-                               _p(ws.gint), _p(ws.tile_counts), _p(ws.status), s), "eg_project_fwd")
+                               _p(ws.gint), _p(ws.tile_counts), _p(ws.keys), _p(ws.status), s), "eg_project_fwd")
         cb("project_fwd")
-        chk(lib.eg_bin(c, _p(ws.rec), _p(ws.gint), _p(ws.tile_counts), _p(ws.tile_offsets), _p(ws.keys),
-                       _p(ws.status), s), "eg_bin")
+        chk(lib.eg_bin(c, _p(ws.tile_counts), _p(ws.tile_offsets), _p(ws.status), s), "eg_bin")
         cb("bin")
         chk(lib.eg_raster_fwd(c, _p(ws.rec), _p(ws.tile_offsets), _p(ws.keys), _p(ws.flatten_ids), None,
                               _p(ws.render0) if want_render else None, None, _p(ws.last_ids), _p(gt), gt_kind,
@@ -296,7 +295,7 @@ class EdgeGaussianSplatting(torch.nn.Module):
         cb("raster_bwd")
         g = ws.grads
         chk(lib.eg_project_bwd(c, _p(means), _p(quats), _p(scales), _p(opac), _p(viewmat), _p(K), _p(ws.rec),
-                               _p(ws.gint), _p(ws.grad2d), None, _p(g[0:3 * N]), _p(g[6 * N:10 * N]),
+                               _p(ws.gint), _p(ws.grad2d), 1, None, _p(g[0:3 * N]), _p(g[6 * N:10 * N]),
                                _p(g[3 * N:6 * N]), _p(g[10 * N:11 * N]),
                                _p(self.absgrads) if accumulate_absgrad else None, s), "eg_project_bwd")
         cb("project_bwd")
@@ -328,8 +327,7 @@ class EdgeGaussianSplatting(torch.nn.Module):
             if not int(hs[_lib.EG_ST_OVERFLOW]):
                 break
             # roll back the abs-grad accumulation is unnecessary: overflowed runs are no-ops in raster kernels
-            eng = get_engine(self.means.device)
-            eng.capacity = max(eng.capacity, int(int(hs[_lib.EG_ST_NISECT]) * 1.25) + 1024)
+            get_engine(self.means.device).note_status(int(hs[_lib.EG_ST_NISECT]), int(hs[_lib.EG_ST_MAXTILE]))
         self.install_grads(ws)
         self.absgrads_normalize_factor += 1
         self.step += 1

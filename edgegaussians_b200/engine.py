@@ -16,7 +16,8 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import EG_GT_F32, EG_GT_NONE, EG_GT_U8, EG_ST_BADCOLOR, EG_ST_NISECT, EG_ST_OVERFLOW, EG_ST_WORDS, EgConfig
+from ._lib import (EG_GT_F32, EG_GT_NONE, EG_GT_U8, EG_ST_BADCOLOR, EG_ST_MAXTILE, EG_ST_NISECT, EG_ST_OVERFLOW,
+                   EG_ST_WORDS, EgConfig)
 
 TILE = 16
 
@@ -33,6 +34,13 @@ def tile_grid(width: int, height: int):
     return (width + TILE - 1) // TILE, (height + TILE - 1) // TILE
 
 
+def tile_capacity_for(isect_capacity: int, n_tiles: int, max_tile: int = 0) -> int:
+    """Keys per tile bucket: 4x the mean tile load implied by the intersection capacity, at least
+    1.25x the largest tile seen so far, rounded up to a multiple of 64."""
+    want = max(256, 4 * isect_capacity // max(n_tiles, 1), int(max_tile * 1.25) + 1)
+    return (want + 63) // 64 * 64
+
+
 @dataclass
 class SplatState:
     """Everything one forward call produced that the backward (or gsplat's ``meta``) needs."""
@@ -45,7 +53,7 @@ class SplatState:
     rec: torch.Tensor            # [N,8] f32
     gint: torch.Tensor           # [N,2] i32
     tile_offsets: torch.Tensor   # [T+1] i32
-    keys: torch.Tensor           # [cap] i64 storage of the u64 keys
+    keys: torch.Tensor           # [T * tile_capacity] i64 storage of the u64 keys (one bucket per tile)
     flatten_ids: torch.Tensor    # [cap] i32
     status: torch.Tensor         # [8] i32
     last_ids: Optional[torch.Tensor] = None   # [H,W] i32
@@ -68,15 +76,21 @@ class Engine:
         self.device = device
         self.lib = _lib.load()
         self.capacity = 0
+        self.max_tile = 0  # largest per-tile intersection count seen so far
         self._host_status = torch.zeros(EG_ST_WORDS, dtype=torch.int32).pin_memory()
         self._event = torch.cuda.Event()
 
     # ------------------------------------------------------------------ helpers
     def make_cfg(self, n, width, height, *, eps2d=0.3, near_plane=0.01, far_plane=1e10, radius_clip=0.0,
-                 antialiased=True, raw_params=False, capacity=0) -> EgConfig:
+                 antialiased=True, raw_params=False, capacity=0, tile_capacity=0) -> EgConfig:
         return EgConfig(n=n, width=width, height=height, tile_size=TILE, eps2d=eps2d, near_plane=near_plane,
                         far_plane=far_plane, radius_clip=radius_clip, antialiased=1 if antialiased else 0,
-                        raw_params=1 if raw_params else 0, isect_capacity=capacity)
+                        raw_params=1 if raw_params else 0, isect_capacity=capacity, tile_capacity=tile_capacity)
+
+    def note_status(self, n_isects: int, max_tile: int) -> None:
+        """Grow the capacity estimates after an overflow report."""
+        self.capacity = max(self.capacity, int(n_isects * 1.25) + 1024)
+        self.max_tile = max(self.max_tile, int(max_tile))
 
     def _ensure_capacity(self, n: int) -> int:
         if self.capacity <= 0:
@@ -107,16 +121,17 @@ class Engine:
         tile_offsets = torch.empty(T + 1, dtype=torch.int32, device=dev)
         status = torch.zeros(EG_ST_WORDS, dtype=torch.int32, device=dev)
         while True:
+            tcap = tile_capacity_for(cap, T, self.max_tile)
             cfg = self.make_cfg(N, width, height, eps2d=eps2d, near_plane=near_plane, far_plane=far_plane,
                                 radius_clip=radius_clip, antialiased=antialiased, raw_params=raw_params,
-                                capacity=cap)
-            keys = torch.empty(cap, dtype=torch.int64, device=dev)
+                                capacity=cap, tile_capacity=tcap)
+            keys = torch.empty(T * tcap, dtype=torch.int64, device=dev)
             flatten_ids = torch.empty(cap, dtype=torch.int32, device=dev)
             _lib.check(self.lib.eg_project_fwd(ctypes.byref(cfg), _p(means), _p(quats), _p(scales), _p(opacities),
                                                _p(colors), _p(viewmat), _p(K), _p(rec), _p(gint),
-                                               _p(tile_counts), _p(status), _stream()), "eg_project_fwd")
-            _lib.check(self.lib.eg_bin(ctypes.byref(cfg), _p(rec), _p(gint), _p(tile_counts), _p(tile_offsets),
-                                       _p(keys), _p(status), _stream()), "eg_bin")
+                                               _p(tile_counts), _p(keys), _p(status), _stream()), "eg_project_fwd")
+            _lib.check(self.lib.eg_bin(ctypes.byref(cfg), _p(tile_counts), _p(tile_offsets), _p(status), _stream()),
+                       "eg_bin")
             st = SplatState(cfg=cfg, N=N, width=width, height=height, tile_w=tw, tile_h=th, rec=rec, gint=gint,
                             tile_offsets=tile_offsets, keys=keys, flatten_ids=flatten_ids, status=status)
             if not sync:
@@ -133,9 +148,9 @@ class Engine:
             st.n_isects = n_isects
             if not int(hs[EG_ST_OVERFLOW]):
                 return st
-            # too small: grow geometrically and redo the binning (projection outputs are still valid)
-            cap = int(n_isects * 1.25) + 1024
-            self.capacity = max(self.capacity, cap)
+            # too small: grow geometrically and redo projection + binning
+            self.note_status(n_isects, int(hs[EG_ST_MAXTILE]))
+            cap = max(cap, self.capacity) if int(n_isects) > cap else cap
             status.zero_()
             tile_counts.zero_()
 
@@ -207,7 +222,7 @@ class Engine:
         v_quats = out[6 * N:10 * N].view(N, 4)
         v_opac = out[10 * N:11 * N]
         _lib.check(self.lib.eg_project_bwd(ctypes.byref(st.cfg), _p(means), _p(quats), _p(scales), _p(opacities),
-                                           _p(viewmat), _p(K), _p(st.rec), _p(st.gint), _p(grad2d), _p(v_depths),
+                                           _p(viewmat), _p(K), _p(st.rec), _p(st.gint), _p(grad2d), 0, _p(v_depths),
                                            _p(v_means), _p(v_quats), _p(v_scales), _p(v_opac), _p(absgrad_accum),
                                            _stream()), "eg_project_bwd")
         return v_means, v_quats, v_scales, v_opac
@@ -216,7 +231,8 @@ class Engine:
     def read_status(self, st: SplatState):
         """Blocking read of the device status words -> dict (n_isects, overflow, bad_color)."""
         hs = st.status.cpu()
-        return dict(n_isects=int(hs[EG_ST_NISECT]), overflow=bool(hs[EG_ST_OVERFLOW]), bad_color=bool(hs[EG_ST_BADCOLOR]))
+        return dict(n_isects=int(hs[EG_ST_NISECT]), overflow=bool(hs[EG_ST_OVERFLOW]), bad_color=bool(hs[EG_ST_BADCOLOR]),
+                    max_tile=int(hs[EG_ST_MAXTILE]))
 
 
 _engines = {}

@@ -13,6 +13,7 @@ from typing import Dict, Optional
 import torch
 
 from .edge_gs import EdgeGaussianSplatting, RasterStepWorkspace
+from .engine import get_engine
 
 
 class GraphedRasterStep:
@@ -49,6 +50,8 @@ class GraphedRasterStep:
                 hs = ws.status.cpu()
                 n_isects = int(hs[0])
                 need = max(need, n_isects)
+                eng = get_engine(self.model.means.device)
+                eng.max_tile = max(eng.max_tile, int(hs[3]))
                 if not int(hs[1]):
                     break
                 self._capacity = int(n_isects * margin) + 1024

@@ -29,8 +29,8 @@
  *                  intersections of the tile, column 1 = append cursor (scratch of eg_bin); one 128-byte
  *                  line per tile so that the L2 atomic units do not serialise neighbouring tiles.
  *   tile_offsets [T+1] i32 (exclusive scan; [T] = n_isects).
- *   keys  [cap] u64 = depth_bits<<32 | gaussian_id, unsorted per tile after eg_bin, sorted (per tile)
- *                  after eg_raster_fwd.
+ *   keys  [T, tile_capacity] u64 = depth_bits<<32 | gaussian_id: one fixed-capacity bucket per tile,
+ *                  filled in arbitrary order by eg_project_fwd, consumed (sorted on chip) by eg_raster_fwd.
  *   flatten_ids [cap] i32 : gsplat's flatten_ids (sorted by tile, depth bits, id).
  *   isect_ids   [cap] i64 : gsplat's isect_ids (tile<<32 | depth bits), optional (may be NULL).
  *   alpha [P], render0 [P] (channel 0 of render; all three channels are equal because the reference
@@ -49,10 +49,10 @@
 extern "C" {
 #endif
 
-#define EG_ABI_VERSION 2
+#define EG_ABI_VERSION 3
 #define EG_CNT_STRIDE 32
 
-enum { EG_ST_NISECT = 0, EG_ST_OVERFLOW = 1, EG_ST_BADCOLOR = 2, EG_ST_NVISIBLE = 3, EG_ST_WORDS = 8 };
+enum { EG_ST_NISECT = 0, EG_ST_OVERFLOW = 1, EG_ST_BADCOLOR = 2, EG_ST_MAXTILE = 3, EG_ST_WORDS = 8 };
 
 enum { EG_GT_NONE = 0, EG_GT_F32 = 1, EG_GT_U8 = 2 };
 
@@ -67,7 +67,9 @@ typedef struct eg_config {
     float radius_clip;    /* 0.0                                                   */
     int32_t antialiased;  /* 1 = rasterize_mode "antialiased" (edge_gs.py:50)      */
     int32_t raw_params;   /* 1 = log-scales / logit-opacities, activations fused   */
-    int64_t isect_capacity; /* elements available in keys / flatten_ids / isect_ids */
+    int64_t isect_capacity; /* elements available in flatten_ids / isect_ids          */
+    int32_t tile_capacity;  /* keys per tile bucket (keys holds T * tile_capacity)    */
+    int32_t reserved;
 } eg_config;
 
 const char *eg_last_error(void);
@@ -77,16 +79,20 @@ int eg_tile_grid(int width, int height, int tile_size, int *tile_w, int *tile_h)
 
 /* K1 (+ K2 pass 1): projection forward + per-tile intersection counts.
  * Replaces gsplat fully_fused_projection fwd + isect_tiles pass 1 behind edge_gs.py:250-268.
+ * Also K2 emission: every Gaussian appends its (depth,id) key to the bucket of each tile it touches
+ * (one atomic per intersection; no second pass, no global sort).
  * colors: [N,3] or NULL; when given it is only VERIFIED to be all-ones (status[EG_ST_BADCOLOR]). */
 int eg_project_fwd(const eg_config *cfg, const float *means, const float *quats, const float *scales,
                    const float *opacities, const float *colors, const float *viewmat, const float *K,
-                   float *rec, int32_t *gint, int32_t *tile_counts, int32_t *status, void *stream);
+                   float *rec, int32_t *gint, int32_t *tile_counts, uint64_t *keys, int32_t *status,
+                   void *stream);
 
-/* K2 pass 2: exclusive scan of the tile counts + emission of (depth,id) keys into per-tile segments.
- * Replaces gsplat cumsum + isect_tiles pass 2 + isect_offset_encode (the sort itself is per tile
- * inside eg_raster_fwd). */
-int eg_bin(const eg_config *cfg, const float *rec, const int32_t *gint, int32_t *tile_counts,
-           int32_t *tile_offsets, uint64_t *keys, int32_t *status, void *stream);
+/* K2/K4: exclusive scan of the tile counts -> tile_offsets (== gsplat isect_offsets), n_isects and
+ * the largest tile count, all kept on the device (status).  Replaces gsplat cumsum + the n_isects
+ * D2H sync + isect_offset_encode (keys were already emitted into the tile buckets by eg_project_fwd;
+ * the sort itself is per tile inside eg_raster_fwd). */
+int eg_bin(const eg_config *cfg, const int32_t *tile_counts, int32_t *tile_offsets, int32_t *status,
+           void *stream);
 
 /* K3 + K5 (+ a8 "whole" L1): per-tile sort, front-to-back compositing, optional fused edge-map loss.
  * Replaces cub radix sort + gsplat rasterize_to_pixels fwd; with gt != NULL also
@@ -114,12 +120,13 @@ int eg_raster_bwd(const eg_config *cfg, const float *rec, const int32_t *tile_of
  * the opacity*compensation VJP, Exp/Sigmoid backward and update_absgrads (edge_gs.py:603-613).
  * grads are WRITTEN (not accumulated): v_means [N,3], v_quats [N,4], v_scales [N,3],
  * v_opacities [N] w.r.t. the inputs as given (raw or activated per cfg->raw_params).
- * v_depths may be NULL.  absgrad_accum [N] (may be NULL) += ||absgrad||_2 . */
+ * v_depths may be NULL.  absgrad_accum [N] (may be NULL) += ||absgrad||_2 .
+ * zero_grad2d != 0: grad2d is cleared after it has been consumed (ready for the next iteration). */
 int eg_project_bwd(const eg_config *cfg, const float *means, const float *quats, const float *scales,
                    const float *opacities, const float *viewmat, const float *K, const float *rec,
-                   const int32_t *gint, const float *grad2d, const float *v_depths, float *v_means,
-                   float *v_quats, float *v_scales, float *v_opacities, float *absgrad_accum,
-                   void *stream);
+                   const int32_t *gint, float *grad2d, int zero_grad2d, const float *v_depths,
+                   float *v_means, float *v_quats, float *v_scales, float *v_opacities,
+                   float *absgrad_accum, void *stream);
 
 /* a10 + a11: edge-direction and anisotropy regularisers, forward + backward in one pass.
  * Replaces compute_direction_loss / compute_ratio_loss + autograd (edge_gs.py:346-380).
