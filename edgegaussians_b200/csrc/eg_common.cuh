@@ -65,6 +65,26 @@ __device__ __forceinline__ float eg_sigma(float A, float B, float C, float dx, f
 }
 __device__ __forceinline__ float eg_vis(float sigma) { return eg_ex2(__fmul_rn(-sigma, EG_LOG2E)); }
 
+// Folded form used by the raster kernels: with  fa = -0.5*log2(e)*A, fb = -log2(e)*B, fc = -0.5*log2(e)*C,
+// lo = log2(opacity)  the exponent  p = lo - sigma*log2(e)  is six multiply-adds and
+// opacity*exp(-sigma) = 2^p  (one MUFU.EX2, no extra multiplies);  sigma >= 0  <=>  p <= lo.
+// Both raster kernels derive (fa, fb, fc, lo) from the same record with these exact expressions, so
+// their skip decisions agree bit for bit.
+struct EgFold {
+    float fa, fb, fc, lo;
+};
+__device__ __forceinline__ EgFold eg_fold(float A, float B, float C, float o) {
+    EgFold f;
+    f.fa = __fmul_rn(A, -0.5f * EG_LOG2E);
+    f.fb = __fmul_rn(B, -EG_LOG2E);
+    f.fc = __fmul_rn(C, -0.5f * EG_LOG2E);
+    f.lo = __log2f(o);
+    return f;
+}
+__device__ __forceinline__ float eg_pow2arg(float fa, float fb, float fc, float lo, float dx, float dy) {
+    return __fmaf_rn(__fmul_rn(fa, dx), dx, __fmaf_rn(__fmul_rn(fc, dy), dy, __fmaf_rn(__fmul_rn(fb, dx), dy, lo)));
+}
+
 // Conservative half-extents (pixels) of the region where a Gaussian can reach alpha >= 1/255:
 // { p : sigma(p) <= tau },  tau = ln(255 * opacity) (+ safety margin).  Returns false when the
 // Gaussian can never contribute (opacity < 1/255).  Used ONLY to skip work whose result the

@@ -32,17 +32,17 @@ constexpr int RB_THREADS = 256;
 constexpr int MAX_ITEMS = RB_THREADS * EG_TILE;  // (Gaussian, row) items of one batch
 
 struct PairAcc {
-    float gx, gy, ax, ay, ca, cb, cc, go;
+    float gx, gy, ax, ay, ca, cb, cc, gs;  // gs = sum of v_sigma = -opacity * sum(vis * v_alpha)
 };
 
-__device__ __forceinline__ void acc_zero(PairAcc &a) { a.gx = a.gy = a.ax = a.ay = a.ca = a.cb = a.cc = a.go = 0.0f; }
+__device__ __forceinline__ void acc_zero(PairAcc &a) { a.gx = a.gy = a.ax = a.ay = a.ca = a.cb = a.cc = a.gs = 0.0f; }
 
-__device__ __forceinline__ void acc_flush(const PairAcc &a, float *__restrict__ grad2d, int gid) {
-    if (a.go != 0.0f || a.ax != 0.0f || a.ay != 0.0f || a.ca != 0.0f || a.cc != 0.0f) {
-        float *dst = grad2d + 8ll * gid;
-        eg_red_add_v4(dst, a.gx, a.gy, a.ax, a.ay);
-        eg_red_add_v4(dst + 4, a.ca, a.cb, a.cc, a.go);
-    }
+// v_opacity = sum(vis * v_alpha) = -gs / opacity
+__device__ __forceinline__ void acc_flush(const PairAcc &a, float *__restrict__ grad2d, int gid, float opac) {
+    // unconditional: candidates are pre-filtered, a segment without any contribution is rare (adds zeros)
+    float *dst = grad2d + 8ll * gid;
+    eg_red_add_v4(dst, a.gx, a.gy, a.ax, a.ay);
+    eg_red_add_v4(dst + 4, a.ca, a.cb, a.cc, __fdividef(-a.gs, opac));
 }
 
 __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
@@ -226,6 +226,7 @@ __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
         for (int q = c0 - s_ioff[i]; q > 0; --q) mask &= mask - 1;  // candidates of this item owned by the previous slice
         int g = (int)(item >> 20);
         float4 a = sA[g], cn = sB[g];
+        EgFold f = eg_fold(cn.x, cn.y, cn.z, a.z);
         int y = (int)((item >> 16) & 15u);
         float dy = a.y - (Y0f + (float)y);
         int rowbase = y * EG_TILE, kk = b0 + g;
@@ -239,11 +240,12 @@ __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
                 } while (mask == 0);
                 const int gn = (int)(item >> 20);
                 if (gn != g) {
-                    acc_flush(acc, grad2d, __float_as_int(cn.w));
+                    acc_flush(acc, grad2d, __float_as_int(cn.w), a.z);
                     acc_zero(acc);
                     g = gn;
                     a = sA[g];
                     cn = sB[g];
+                    f = eg_fold(cn.x, cn.y, cn.z, a.z);
                     kk = b0 + g;
                 }
                 y = (int)((item >> 16) & 15u);
@@ -255,13 +257,11 @@ __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
             --remaining;
             const float2 pw = s_pix[rowbase + x];
             const float dx = a.x - (X0f + (float)x);
-            const float sigma = eg_sigma(cn.x, cn.y, cn.z, dx, dy);
-            const float vis = eg_vis(sigma);
-            const float ov = __fmul_rn(a.z, vis);
-            if (kk <= __float_as_int(pw.y) && sigma >= 0.0f && ov >= EG_ALPHA_MIN && ov <= EG_ALPHA_MAX) {
+            const float pw2 = eg_pow2arg(f.fa, f.fb, f.fc, f.lo, dx, dy);
+            const float ov = eg_ex2(pw2);  // opacity * exp(-sigma), exactly as the forward computed it
+            if (kk <= __float_as_int(pw.y) && pw2 <= f.lo && ov >= EG_ALPHA_MIN && ov <= EG_ALPHA_MAX) {
                 const float ra = __fdividef(1.0f, 1.0f - ov);
-                const float v_al = pw.x * ra;
-                const float v_sigma = -ov * v_al;
+                const float v_sigma = -ov * pw.x * ra;
                 const float gx = v_sigma * fmaf(cn.x, dx, cn.y * dy);
                 const float gy = v_sigma * fmaf(cn.y, dx, cn.z * dy);
                 const float hs = 0.5f * v_sigma;
@@ -272,10 +272,10 @@ __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
                 acc.ca = fmaf(hs * dx, dx, acc.ca);
                 acc.cb = fmaf(v_sigma * dx, dy, acc.cb);
                 acc.cc = fmaf(hs * dy, dy, acc.cc);
-                acc.go = fmaf(vis, v_al, acc.go);
+                acc.gs += v_sigma;
             }
         }
-        acc_flush(acc, grad2d, __float_as_int(cn.w));
+        acc_flush(acc, grad2d, __float_as_int(cn.w), a.z);
     }
 }
 

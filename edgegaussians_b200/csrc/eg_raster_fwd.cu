@@ -198,8 +198,8 @@ __global__ void __launch_bounds__(RF_THREADS) raster_fwd_kernel(
     const void *__restrict__ gt, double *__restrict__ loss_sum, float *__restrict__ wpix,
     const int32_t *__restrict__ status) {
     __shared__ __align__(16) u64 sbuf[2 * SORT_CAP];  // sort exchange buffers, then the sorted ids
-    __shared__ __align__(16) float4 sAB[2 * RF_THREADS];  // per Gaussian: (mean2d.x, mean2d.y, opacity, sub-tile
-                                                          // mask bits) , (conic a, b, c, -)
+    __shared__ __align__(16) float4 sAB[2 * RF_THREADS];  // per Gaussian: (mean2d.x, mean2d.y, log2 opacity,
+                                                          // sub-tile mask bits) , (folded conic fa, fb, fc, -)
     __shared__ float s_red[RF_THREADS / 32];
     uint32_t *sids = reinterpret_cast<uint32_t *>(sbuf);
 
@@ -268,8 +268,9 @@ __global__ void __launch_bounds__(RF_THREADS) raster_fwd_kernel(
                 for (int r = 0; r < 4; ++r)
                     if (cy & (1 << r)) mask |= cx << (2 * r);
             }
-            sAB[2 * tid] = make_float4(r0.x, r0.y, r0.z, __int_as_float(mask));
-            sAB[2 * tid + 1] = r1;
+            const EgFold f = eg_fold(r1.x, r1.y, r1.z, r0.z);
+            sAB[2 * tid] = make_float4(r0.x, r0.y, f.lo, __int_as_float(mask));
+            sAB[2 * tid + 1] = make_float4(f.fa, f.fb, f.fc, 0.0f);
         }
         __syncthreads();
         const int nb = min(RF_THREADS, L - b0);
@@ -282,9 +283,9 @@ __global__ void __launch_bounds__(RF_THREADS) raster_fwd_kernel(
                 const float4 a = sAB[2 * t];
                 const float4 cn = sAB[2 * t + 1];
                 const float dx = a.x - px, dy = a.y - py;
-                const float sigma = eg_sigma(cn.x, cn.y, cn.z, dx, dy);
-                const float al = fminf(EG_ALPHA_MAX, __fmul_rn(a.z, eg_vis(sigma)));
-                const bool valid = !done && sigma >= 0.0f && al >= EG_ALPHA_MIN;
+                const float pw2 = eg_pow2arg(cn.x, cn.y, cn.z, a.z, dx, dy);  // log2(opacity * exp(-sigma))
+                const float al = fminf(EG_ALPHA_MAX, eg_ex2(pw2));
+                const bool valid = !done && pw2 <= a.z && al >= EG_ALPHA_MIN;  // sigma >= 0 and alpha >= 1/255
                 const float nT = T * (1.0f - al);
                 const bool stop = valid && nT <= EG_T_MIN;
                 const bool take = valid && !stop;
