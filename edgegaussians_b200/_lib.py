@@ -17,7 +17,7 @@ EG_GT_NONE, EG_GT_F32, EG_GT_U8 = 0, 1, 2
 EG_CNT_STRIDE = 32
 
 EXPORTS = ["eg_last_error", "eg_abi_version", "eg_tile_grid", "eg_project_fwd", "eg_bin", "eg_raster_fwd",
-           "eg_raster_bwd", "eg_project_bwd", "eg_reg_fwd_bwd"]
+           "eg_raster_bwd", "eg_project_bwd", "eg_reg_fwd_bwd", "eg_knn_workspace_bytes", "eg_knn", "eg_adam_step"]
 
 
 class EgConfig(Structure):
@@ -55,8 +55,12 @@ def load(build_if_missing: bool = True):
     lib.eg_raster_bwd.argtypes = [cfgp] + [P] * 6 + [c_int, P, P, c_float, P, P, P]
     lib.eg_project_bwd.argtypes = [cfgp] + [P] * 9 + [c_int] + [P] * 7
     lib.eg_reg_fwd_bwd.argtypes = [c_int, P, P, P, P, c_int, c_int, c_int, c_float, c_float, P, P, P, P, P]
+    lib.eg_knn_workspace_bytes.argtypes = [c_int]
+    lib.eg_knn.argtypes = [c_int, P, c_int, c_int, P, P, ctypes.c_size_t, P]
+    lib.eg_adam_step.argtypes = [c_int64, P, P, P, P] + [c_float] * 6 + [c_int, P]
     for name in EXPORTS[2:]:
         getattr(lib, name).restype = c_int
+    lib.eg_knn_workspace_bytes.restype = ctypes.c_size_t
     _lib = lib
     return lib
 

@@ -1,0 +1,80 @@
+"""View-sharded data parallelism for the raster iteration.
+
+The reference is strictly single-GPU, one view per step (train_gaussians.py:71,311).  The path shards
+naturally by VIEW: parameters are replicated, rank r renders view ``perm[step * G + r]`` and the
+per-view gradients (additive over views) are summed with ONE all-reduce over the flat fp32 gradient
+buffer laid out  means | scales | quats | opacities  (11 N floats) -- optionally followed by the [N]
+abs-grad statistics.  One process per GPU, ``torch.distributed`` (NCCL on GPUs, gloo in CPU tests).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def view_permutation(n_views: int, epoch: int, seed: int = 0) -> List[int]:
+    """Rank-independent shuffle of the views of one epoch (the reference shuffles with an unseeded
+    DataLoader, train_gaussians.py:311; every rank must draw the same permutation)."""
+    g = torch.Generator()
+    g.manual_seed(seed * 1_000_003 + epoch)
+    return torch.randperm(n_views, generator=g).tolist()
+
+
+def views_for_step(perm: Sequence[int], step: int, world_size: int) -> List[Optional[int]]:
+    """The views rendered at ``step`` by ranks 0..G-1 (None = the rank idles: ragged last step)."""
+    base = step * world_size
+    return [perm[base + r] if base + r < len(perm) else None for r in range(world_size)]
+
+
+def steps_per_epoch(n_views: int, world_size: int) -> int:
+    return (n_views + world_size - 1) // world_size
+
+
+def flat_grad_views(flat: torch.Tensor, n: int):
+    """(v_means [N,3], v_scales [N,3], v_quats [N,4], v_opacities [N,1]) views of the flat buffer."""
+    return (flat[0:3 * n].view(n, 3), flat[3 * n:6 * n].view(n, 3), flat[6 * n:10 * n].view(n, 4),
+            flat[10 * n:11 * n].view(n, 1))
+
+
+def allreduce_gradients(flat: torch.Tensor, absgrad_increment: Optional[torch.Tensor] = None, group=None,
+                        average: bool = False) -> None:
+    """Sum (or average) the per-view gradients of all ranks in place.  An idle rank passes zeros."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    if absgrad_increment is not None:
+        dist.all_reduce(absgrad_increment, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        flat.div_(dist.get_world_size(group))
+
+
+class ViewShardedStep:
+    """Drives ``EdgeGaussianSplatting.raster_step`` on this rank's view and all-reduces the result.
+
+    ``model`` holds replicated parameters; ``gts`` maps view id -> device edge map.  The abs-grad
+    statistics are accumulated from all views (the reference accumulates one view per step)."""
+
+    def __init__(self, model, gts, group=None):
+        self.model, self.gts, self.group = model, gts, group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+
+    def step(self, perm: Sequence[int], step: int, loss_weight: float = 1.0) -> torch.Tensor:
+        view = views_for_step(perm, step, self.world)[self.rank]
+        model = self.model
+        before = model.absgrads.clone()
+        if view is None:
+            ws = model._ws
+            ws.grads.zero_()
+            loss = torch.zeros((), device=ws.grads.device)
+        else:
+            loss = model.raster_step(view, self.gts[view], loss_weight=loss_weight)
+        ws = model._ws
+        inc = model.absgrads - before
+        allreduce_gradients(ws.grads, inc, self.group)
+        model.absgrads.copy_(before + inc)
+        if self.world > 1:
+            dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=self.group)
+        return loss

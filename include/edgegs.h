@@ -140,6 +140,22 @@ int eg_reg_fwd_bwd(int n, const float *means, const float *quats, const float *l
                    float ratio_weight, double *losses, float *v_means, float *v_quats,
                    float *v_log_scales, void *stream);
 
+/* a12 ("next"): exact k-nearest neighbours on the device.  Replaces
+ * k_nearest_sklearn / update_nearest_neighbors (edge_gs.py:135-151, 326-344).  points [N,3] fp32;
+ * out [N,kk] i32 = neighbours of rank skip .. skip+kk-1 by (distance, index), rank 0 being the point
+ * itself; the reference's "ask for kk+2, drop the first column twice" is skip = 2.  kk + skip <= 48.
+ * workspace: eg_knn_workspace_bytes(n) bytes of device memory (host helper, no CUDA call). */
+size_t eg_knn_workspace_bytes(int n);
+int eg_knn(int n, const float *points, int kk, int skip, int32_t *out, void *workspace,
+           size_t workspace_bytes, void *stream);
+
+/* a13 ("next"): fused Adam update of one parameter tensor, torch.optim.Adam
+ * semantics as configured at utils/train_utils.py:48-65 (no weight decay, no amsgrad);
+ * bias_correction{1,2} = 1 - beta{1,2}^t.  zero_grad != 0 also clears the gradient. */
+int eg_adam_step(int64_t n, float *param, float *grad, float *exp_avg, float *exp_avg_sq, float lr,
+                 float beta1, float beta2, float eps, float bias_correction1, float bias_correction2,
+                 int zero_grad, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

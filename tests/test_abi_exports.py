@@ -1,0 +1,82 @@
+"""The C-ABI library loads on a CPU-only box and exports every entry point include/edgegs.h declares
+(no compute calls without a GPU), and the Python host layer refuses to run without CUDA."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "edgegs.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(eg_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from edgegaussians_b200 import _lib, build
+    path = build.build()
+    lib = ctypes.CDLL(path)
+    names = _declared_symbols()
+    assert {"eg_project_fwd", "eg_bin", "eg_raster_fwd", "eg_raster_bwd", "eg_project_bwd", "eg_reg_fwd_bwd",
+            "eg_knn", "eg_adam_step", "eg_last_error", "eg_abi_version", "eg_tile_grid"} <= set(names)
+    for n in names:
+        assert hasattr(lib, n), f"libedgegs.so does not export {n}"
+    assert sorted(_lib.EXPORTS) == names, "edgegaussians_b200/_lib.py EXPORTS out of sync with include/edgegs.h"
+    lib.eg_abi_version.restype = ctypes.c_int
+    hdr = open(os.path.join(ROOT, "include", "edgegs.h")).read()
+    assert lib.eg_abi_version() == int(re.search(r"#define EG_ABI_VERSION (\d+)", hdr).group(1))
+
+
+def test_host_helpers_without_gpu():
+    from edgegaussians_b200 import _lib
+    lib = _lib.load()
+    tw, th = ctypes.c_int(), ctypes.c_int()
+    assert lib.eg_tile_grid(1600, 1200, 16, ctypes.byref(tw), ctypes.byref(th)) == 0
+    assert (tw.value, th.value) == (100, 75)
+    assert lib.eg_tile_grid(403, 301, 16, ctypes.byref(tw), ctypes.byref(th)) == 0
+    assert (tw.value, th.value) == (26, 19)
+    assert lib.eg_tile_grid(0, 10, 16, None, None) != 0 and b"eg_tile_grid" in lib.eg_last_error()
+    # struct layout the ctypes mirror assumes (include/edgegs.h: eg_config)
+    assert ctypes.sizeof(_lib.EgConfig) == 56
+    assert _lib.EgConfig.isect_capacity.offset == 40 and _lib.EgConfig.tile_capacity.offset == 48
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-CPU-fallback behaviour")
+def test_no_cpu_fallback():
+    from edgegaussians_b200 import rasterization
+    from edgegaussians_b200.engine import get_engine
+    from edgegaussians_b200.edge_gs import EdgeGaussianSplatting
+    N = 8
+    args = [torch.zeros(N, 3), torch.ones(N, 4), torch.ones(N, 3), torch.ones(N)]
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        rasterization(*args, None, torch.eye(4)[None], torch.eye(3)[None], 64, 64, packed=False)
+    with pytest.raises(RuntimeError, match="CUDA devices only"):
+        get_engine(torch.device("cpu"))
+    m = EdgeGaussianSplatting(device="cpu")
+    m.set_params(np.zeros((N, 3), np.float32), np.zeros((N, 3), np.float32), np.ones((N, 4), np.float32),
+                 np.zeros((N, 1), np.float32))
+    with pytest.raises(RuntimeError):
+        m.enqueue_raster_step(torch.eye(4), torch.eye(3), 64, 64, torch.zeros(64, 64))
+
+
+def test_cameras_mirror_reference_golden(golden_dir):
+    """edgegaussians_b200.cameras (product code) against the reference's own K / viewmat (a1)."""
+    from edgegaussians_b200.cameras import Camera, OpenCVCamera
+    g = np.load(os.path.join(golden_dir, "cameras_abc.npz"))
+    for i in (0, 11, 49):
+        c2w = np.linalg.inv(g["viewmats"][i].astype(np.float64))
+        cam = OpenCVCamera.from_emap_frame(800, 800, c2w, g["Ks"][i])
+        assert cam.get_K().shape == (1, 3, 3) and cam.get_viewmat().shape == (1, 4, 4)
+        np.testing.assert_array_equal(cam.get_K()[0].numpy(), g["Ks"][i])
+        np.testing.assert_allclose(cam.get_viewmat()[0].numpy(), g["viewmats"][i], atol=2e-6)
+        assert cam.width == 800 and cam.height == 800
+    cam = Camera(480, 640, 500.0, 510.0, 320.0, 240.0, np.array([1.0, 0.0, 0.0, 0.0]), np.array([0.1, 0.2, 0.3]))
+    np.testing.assert_allclose(cam.get_viewmat()[0, :3, :3].numpy(), np.eye(3), atol=1e-7)
+    np.testing.assert_allclose(cam.get_viewmat()[0, :3, 3].numpy(), [0.1, 0.2, 0.3], atol=1e-7)
+    cam.scale_translation(2.0)
+    np.testing.assert_allclose(cam.get_viewmat()[0, :3, 3].numpy(), [0.2, 0.4, 0.6], atol=1e-7)

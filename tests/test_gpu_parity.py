@@ -25,7 +25,7 @@ from tests.helpers import activate
 pytestmark = pytest.mark.gpu
 
 if torch.cuda.is_available():
-    from edgegaussians_b200 import rasterization as rz
+    from edgegaussians_b200 import rasterization
     from edgegaussians_b200.cameras import OpenCVCamera
     from edgegaussians_b200.edge_gs import EdgeGaussianSplatting
     from oracle import oracle
@@ -54,7 +54,7 @@ def _t(a):
 
 def _gpu_forward(m, q, sc, op, vm, K, W, H, requires_grad=False, full_meta=True):
     tm, tq, ts, to = (_t(a).requires_grad_(requires_grad) for a in (m, q, sc, op))
-    render, alpha, meta = rz.rasterization(tm, tq, ts, to, None, _t(vm)[None], _t(K)[None], W, H, packed=False,
+    render, alpha, meta = rasterization(tm, tq, ts, to, None, _t(vm)[None], _t(K)[None], W, H, packed=False,
                                            absgrad=True, rasterize_mode="antialiased", full_meta=full_meta)
     return (tm, tq, ts, to), render, alpha, meta
 
@@ -212,13 +212,13 @@ def test_unsupported_arguments_raise():
     vms, Ks = synth.make_cameras(1, 64, 64)
     args = [_t(m), _t(q), _t(sc), _t(op)]
     with pytest.raises(NotImplementedError):
-        rz.rasterization(*args, None, _t(vms), _t(Ks), 64, 64, tile_size=8)
+        rasterization(*args, None, _t(vms), _t(Ks), 64, 64, tile_size=8)
     with pytest.raises(NotImplementedError):
-        rz.rasterization(*args, _t(np.full((10, 3), 0.5, np.float32)), _t(vms), _t(Ks), 64, 64, packed=False)
+        rasterization(*args, _t(np.full((10, 3), 0.5, np.float32)), _t(vms), _t(Ks), 64, 64, packed=False)
     with pytest.raises(RuntimeError):
-        rz.rasterization(*[a.cpu() for a in args], None, _t(vms).cpu(), _t(Ks).cpu(), 64, 64)
+        rasterization(*[a.cpu() for a in args], None, _t(vms).cpu(), _t(Ks).cpu(), 64, 64)
     # colors == 1 passes the device-side check
-    rz.rasterization(*args, _t(np.ones((10, 3), np.float32)), _t(vms), _t(Ks), 64, 64, packed=False)
+    rasterization(*args, _t(np.ones((10, 3), np.float32)), _t(vms), _t(Ks), 64, 64, packed=False)
 
 
 def test_capacity_growth_is_transparent():
