@@ -57,7 +57,7 @@ def load(build_if_missing: bool = True):
     lib.eg_reg_fwd_bwd.argtypes = [c_int, P, P, P, P, c_int, c_int, c_int, c_float, c_float, P, P, P, P, P]
     lib.eg_knn_workspace_bytes.argtypes = [c_int]
     lib.eg_knn.argtypes = [c_int, P, c_int, c_int, P, P, ctypes.c_size_t, P]
-    lib.eg_adam_step.argtypes = [c_int64, P, P, P, P] + [c_float] * 6 + [c_int, P]
+    lib.eg_adam_step.argtypes = [c_int64, P, P, P, P] + [c_double] * 6 + [c_int, P]
     for name in EXPORTS[2:]:
         getattr(lib, name).restype = c_int
     lib.eg_knn_workspace_bytes.restype = ctypes.c_size_t

@@ -151,9 +151,11 @@ int eg_knn(int n, const float *points, int kk, int skip, int32_t *out, void *wor
 
 /* a13 ("next"): fused Adam update of one parameter tensor, torch.optim.Adam
  * semantics as configured at utils/train_utils.py:48-65 (no weight decay, no amsgrad);
- * bias_correction{1,2} = 1 - beta{1,2}^t.  zero_grad != 0 also clears the gradient. */
-int eg_adam_step(int64_t n, float *param, float *grad, float *exp_avg, float *exp_avg_sq, float lr,
-                 float beta1, float beta2, float eps, float bias_correction1, float bias_correction2,
+ * bias_correction{1,2} = 1 - beta{1,2}^t.  Hyper-parameters are doubles (as Python floats are) and are
+ * rounded to fp32 only after 1 - beta etc. have been formed, exactly like torch does.
+ * zero_grad != 0 also clears the gradient. */
+int eg_adam_step(int64_t n, float *param, float *grad, float *exp_avg, float *exp_avg_sq, double lr,
+                 double beta1, double beta2, double eps, double bias_correction1, double bias_correction2,
                  int zero_grad, void *stream);
 
 #ifdef __cplusplus
