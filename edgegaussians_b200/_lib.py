@@ -51,7 +51,7 @@ def load(build_if_missing: bool = True):
     lib.eg_tile_grid.argtypes = [c_int, c_int, c_int, POINTER(c_int), POINTER(c_int)]
     lib.eg_project_fwd.argtypes = [cfgp] + [P] * 13
     lib.eg_bin.argtypes = [cfgp] + [P] * 4
-    lib.eg_raster_fwd.argtypes = [cfgp] + [P] * 9 + [c_int, P, P, P, P]
+    lib.eg_raster_fwd.argtypes = [cfgp] + [P] * 10 + [c_int, P, P, P, P]
     lib.eg_raster_bwd.argtypes = [cfgp] + [P] * 6 + [c_int, P, P, c_float, P, P, P]
     lib.eg_project_bwd.argtypes = [cfgp] + [P] * 9 + [c_int] + [P] * 7
     lib.eg_reg_fwd_bwd.argtypes = [c_int, P, P, P, P, c_int, c_int, c_int, c_float, c_float, P, P, P, P, P]

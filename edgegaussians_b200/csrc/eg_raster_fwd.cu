@@ -12,6 +12,9 @@
 //            pixel sub-tile and only walks the Gaussians whose alpha >= 1/255 footprint can reach
 //            that sub-tile (a conservative bounding test done once per (tile, Gaussian) by the
 //            staging thread) -- the sequence of Gaussians each pixel composites is exactly gsplat's;
+//            Every (warp, Gaussian) step also records WHICH of its 32 pixels composited the Gaussian
+//            (one ballot): the 256-bit contribution mask per tile intersection is what the backward
+//            kernel walks, so it never re-derives footprints or skip/stop decisions;
 //   epilogue alpha = 1 - T, render channel 0, last_ids, and optionally the reference's
 //            clamp -> channel 0 -> mean |render - gt| (edge_gs.py:279,290-296; train_gaussians.py:84-94)
 //            as a per-CTA partial sum plus the per-pixel backward seed.
@@ -195,13 +198,14 @@ __global__ void __launch_bounds__(RF_THREADS) raster_fwd_kernel(
     const eg_config cfg, int tw, const float4 *__restrict__ rec, const int32_t *__restrict__ tile_offsets,
     u64 *__restrict__ keys, int32_t *__restrict__ flatten_ids, long long *__restrict__ isect_ids,
     float *__restrict__ render0, float *__restrict__ alpha_out, int32_t *__restrict__ last_ids,
-    const void *__restrict__ gt, double *__restrict__ loss_sum, float *__restrict__ wpix,
-    const int32_t *__restrict__ status) {
+    uint4 *__restrict__ cmask, const void *__restrict__ gt, double *__restrict__ loss_sum,
+    float *__restrict__ wpix, const int32_t *__restrict__ status) {
     __shared__ __align__(16) u64 sbuf[2 * SORT_CAP];  // sort exchange buffers, then the sorted ids
     __shared__ __align__(16) float4 sAB[2 * RF_THREADS];  // per Gaussian: (mean2d.x, mean2d.y, log2 opacity,
                                                           // sub-tile mask bits) , (folded conic fa, fb, fc, -)
     __shared__ float s_red[RF_THREADS / 32];
-    uint32_t *sids = reinterpret_cast<uint32_t *>(sbuf);
+    uint32_t *sids = reinterpret_cast<uint32_t *>(sbuf);             // first 8 KB of the (dead) exchange buffers
+    uint32_t *s_cm = reinterpret_cast<uint32_t *>(sbuf + SORT_CAP);  // second half: contribution masks [256][8]
 
     if (status[EG_ST_OVERFLOW]) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -244,6 +248,7 @@ __global__ void __launch_bounds__(RF_THREADS) raster_fwd_kernel(
     const float X0 = (float)(tile_x * EG_TILE), Y0 = (float)(tile_y * EG_TILE);
 
     float T = 1.0f, out = 0.0f;
+    int b_done = 0;  // Gaussians [0, b_done) of the segment have their contribution masks written
     int last = -start;  // relative to the segment start; gsplat initialises the absolute index to 0
     bool done = !inside;
 
@@ -272,6 +277,10 @@ __global__ void __launch_bounds__(RF_THREADS) raster_fwd_kernel(
             sAB[2 * tid] = make_float4(r0.x, r0.y, f.lo, __int_as_float(mask));
             sAB[2 * tid + 1] = make_float4(f.fa, f.fb, f.fc, 0.0f);
         }
+        if (cmask != nullptr) {
+            reinterpret_cast<uint4 *>(s_cm)[2 * tid] = make_uint4(0u, 0u, 0u, 0u);
+            reinterpret_cast<uint4 *>(s_cm)[2 * tid + 1] = make_uint4(0u, 0u, 0u, 0u);
+        }
         __syncthreads();
         const int nb = min(RF_THREADS, L - b0);
         for (int c = 0; c < nb && !__all_sync(0xffffffffu, done); c += 32) {
@@ -293,9 +302,26 @@ __global__ void __launch_bounds__(RF_THREADS) raster_fwd_kernel(
                 out = take ? fmaf(al, T, out) : out;
                 T = take ? nT : T;
                 last = take ? (b0 + t) : last;
+                if (cmask != nullptr) {
+                    const unsigned bal = __ballot_sync(0xffffffffu, take);
+                    if (lane == 0) s_cm[t * 8 + warp] = bal;
+                }
             }
         }
+        if (cmask != nullptr) {  // contribution masks of this batch -> global (32 B per intersection)
+            __syncthreads();
+            if (k < L) {
+                cmask[2 * (size_t)(start + k)] = reinterpret_cast<const uint4 *>(s_cm)[2 * tid];
+                cmask[2 * (size_t)(start + k) + 1] = reinterpret_cast<const uint4 *>(s_cm)[2 * tid + 1];
+            }
+            b_done = b0 + RF_THREADS;
+        }
     }
+    if (cmask != nullptr)  // batches skipped by the all-pixels-done early exit contribute nothing
+        for (int k = b_done + tid; k < L; k += RF_THREADS) {
+            cmask[2 * (size_t)(start + k)] = make_uint4(0u, 0u, 0u, 0u);
+            cmask[2 * (size_t)(start + k) + 1] = make_uint4(0u, 0u, 0u, 0u);
+        }
 
     // ---------------- epilogue ----------------
     float absd = 0.0f;
@@ -303,7 +329,7 @@ __global__ void __launch_bounds__(RF_THREADS) raster_fwd_kernel(
         const long long pix = (long long)pyi * cfg.width + pxi;
         if (alpha_out) alpha_out[pix] = 1.0f - T;
         if (render0) render0[pix] = out;
-        last_ids[pix] = start + last;
+        if (last_ids) last_ids[pix] = start + last;
         if (GT_KIND != EG_GT_NONE) {
             float g;
             if (GT_KIND == EG_GT_F32) g = __ldg(reinterpret_cast<const float *>(gt) + pix);
@@ -334,14 +360,14 @@ __global__ void __launch_bounds__(RF_THREADS) raster_fwd_kernel(
 
 extern "C" int eg_raster_fwd(const eg_config *cfg, const float *rec, const int32_t *tile_offsets, uint64_t *keys,
                              int32_t *flatten_ids, int64_t *isect_ids, float *render0, float *alpha,
-                             int32_t *last_ids, const void *gt, int gt_kind, double *loss_sum, float *wpix,
-                             const int32_t *status, void *stream) {
+                             int32_t *last_ids, uint32_t *cmask, const void *gt, int gt_kind, double *loss_sum,
+                             float *wpix, const int32_t *status, void *stream) {
     if (cfg == nullptr || cfg->tile_size != EG_TILE) {
         eg_set_error("eg_raster_fwd: tile_size must be %d", EG_TILE);
         return 1;
     }
-    if (last_ids == nullptr || flatten_ids == nullptr) {
-        eg_set_error("eg_raster_fwd: last_ids and flatten_ids are required");
+    if (flatten_ids == nullptr) {
+        eg_set_error("eg_raster_fwd: flatten_ids is required");
         return 1;
     }
     if (gt == nullptr) gt_kind = EG_GT_NONE;
@@ -352,7 +378,7 @@ extern "C" int eg_raster_fwd(const eg_config *cfg, const float *rec, const int32
 #define EG_LAUNCH(KIND)                                                                                          \
     raster_fwd_kernel<KIND><<<grid, RF_THREADS, 0, s>>>(*cfg, tw, (const float4 *)rec, tile_offsets, (u64 *)keys, \
                                                         flatten_ids, (long long *)isect_ids, render0, alpha,      \
-                                                        last_ids, gt, loss_sum, wpix, status)
+                                                        last_ids, (uint4 *)cmask, gt, loss_sum, wpix, status)
     switch (gt_kind) {
         case EG_GT_NONE: EG_LAUNCH(EG_GT_NONE); break;
         case EG_GT_F32: EG_LAUNCH(EG_GT_F32); break;

@@ -74,7 +74,7 @@ class RasterStepWorkspace:
         self.tile_offsets = torch.empty(T + 1, dtype=i32, device=device)
         self.keys = torch.empty(T * self.tile_capacity, dtype=torch.int64, device=device)
         self.flatten_ids = torch.empty(self.capacity, dtype=i32, device=device)
-        self.last_ids = torch.empty((H, W), dtype=i32, device=device)
+        self.cmask = torch.empty((self.capacity, 8), dtype=i32, device=device)
         self.wpix = torch.empty((H, W), dtype=f32, device=device)
         self.render0 = torch.empty((H, W), dtype=f32, device=device)
         self.grad2d = torch.zeros((N, 8), dtype=f32, device=device)
@@ -286,10 +286,10 @@ class EdgeGaussianSplatting(torch.nn.Module):
         chk(lib.eg_bin(c, _p(ws.tile_counts), _p(ws.tile_offsets), _p(ws.status), s), "eg_bin")
         cb("bin")
         chk(lib.eg_raster_fwd(c, _p(ws.rec), _p(ws.tile_offsets), _p(ws.keys), _p(ws.flatten_ids), None,
-                              _p(ws.render0) if want_render else None, None, _p(ws.last_ids), _p(gt), gt_kind,
+                              _p(ws.render0) if want_render else None, None, None, _p(ws.cmask), _p(gt), gt_kind,
                               _p(ws.loss_sum), _p(ws.wpix), _p(ws.status), s), "eg_raster_fwd")
         cb("raster_fwd")
-        chk(lib.eg_raster_bwd(c, _p(ws.rec), _p(ws.tile_offsets), _p(ws.flatten_ids), _p(ws.last_ids), None, None, 0,
+        chk(lib.eg_raster_bwd(c, _p(ws.rec), _p(ws.tile_offsets), _p(ws.flatten_ids), _p(ws.cmask), None, None, 0,
                               None, _p(ws.wpix), float(loss_weight) / float(W * H), _p(ws.grad2d), _p(ws.status), s),
             "eg_raster_bwd")
         cb("raster_bwd")

@@ -62,6 +62,7 @@ class SplatState:
     wpix: Optional[torch.Tensor] = None       # [H,W] f32
     loss_sum: Optional[torch.Tensor] = None   # [1] f64
     isect_ids: Optional[torch.Tensor] = None  # [cap] i64
+    cmask: Optional[torch.Tensor] = None      # [cap,8] i32: per-intersection contribution masks (backward work list)
     grad2d: Optional[torch.Tensor] = None     # [N,8] f32, written by raster_bwd
     n_isects: Optional[int] = None            # known on the host only after a status read
 
@@ -155,14 +156,16 @@ class Engine:
             tile_counts.zero_()
 
     def raster_fwd(self, st: SplatState, *, gt: Optional[torch.Tensor] = None, want_alpha=True, want_render=True,
-                   want_isect_ids=False, want_wpix=False) -> SplatState:
+                   want_isect_ids=False, want_wpix=False, want_cmask=True) -> SplatState:
         dev = st.rec.device
         H, W = st.height, st.width
         st.last_ids = torch.empty((H, W), dtype=torch.int32, device=dev)
         st.alpha = torch.empty((H, W), dtype=torch.float32, device=dev) if want_alpha else None
         st.render0 = torch.empty((H, W), dtype=torch.float32, device=dev) if want_render else None
         if want_isect_ids:
-            st.isect_ids = torch.empty(st.keys.shape[0], dtype=torch.int64, device=dev)
+            st.isect_ids = torch.empty(st.flatten_ids.shape[0], dtype=torch.int64, device=dev)
+        if want_cmask:
+            st.cmask = torch.empty((st.flatten_ids.shape[0], 8), dtype=torch.int32, device=dev)
         gt_kind = EG_GT_NONE
         if gt is not None:
             _lib.require_cuda(gt, "gt")
@@ -178,7 +181,7 @@ class Engine:
             st.wpix = torch.empty((H, W), dtype=torch.float32, device=dev) if want_wpix else None
         _lib.check(self.lib.eg_raster_fwd(ctypes.byref(st.cfg), _p(st.rec), _p(st.tile_offsets), _p(st.keys),
                                           _p(st.flatten_ids), _p(st.isect_ids), _p(st.render0), _p(st.alpha),
-                                          _p(st.last_ids), _p(gt), gt_kind, _p(st.loss_sum), _p(st.wpix),
+                                          _p(st.last_ids), _p(st.cmask), _p(gt), gt_kind, _p(st.loss_sum), _p(st.wpix),
                                           _p(st.status), _stream()), "eg_raster_fwd")
         return st
 
@@ -204,8 +207,10 @@ class Engine:
                 ch = v_render.shape[-1] if v_render.dim() == 3 else 1
             if v_alpha is not None:
                 v_alpha = v_alpha.contiguous()
+        if st.cmask is None:
+            raise RuntimeError("raster_bwd needs the contribution masks of the forward (raster_fwd(want_cmask=True))")
         _lib.check(self.lib.eg_raster_bwd(ctypes.byref(st.cfg), _p(st.rec), _p(st.tile_offsets), _p(st.flatten_ids),
-                                          _p(st.last_ids), _p(st.alpha), _p(v_render), ch, _p(v_alpha), _p(wpix),
+                                          _p(st.cmask), _p(st.alpha), _p(v_render), ch, _p(v_alpha), _p(wpix),
                                           float(seed_scale), _p(grad2d), _p(st.status), _stream()), "eg_raster_bwd")
         return grad2d
 

@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define EG_ABI_VERSION 3
+#define EG_ABI_VERSION 4
 #define EG_CNT_STRIDE 32
 
 enum { EG_ST_NISECT = 0, EG_ST_OVERFLOW = 1, EG_ST_BADCOLOR = 2, EG_ST_MAXTILE = 3, EG_ST_WORDS = 8 };
@@ -100,18 +100,21 @@ int eg_bin(const eg_config *cfg, const int32_t *tile_counts, int32_t *tile_offse
  *   loss_sum[0] += sum_p |clamp(render0) - gt|      (one fp64 word; caller divides by P)
  *   wpix[p]      = sign(clamp(render0) - gt) * T_final   (the backward seed of pixel p, unscaled)
  * gt_kind: EG_GT_F32 (values in [0,1]) or EG_GT_U8 (value/255, train_gaussians.py:87).
- * Any of render0 / alpha / isect_ids / gt / loss_sum / wpix may be NULL. */
+ * cmask [cap,8] u32: per tile intersection (in flatten_ids order) the 256-bit mask of the tile's pixels
+ * that composited that Gaussian; word w covers the 8x4 pixel block (x0 = 8*(w&1), y0 = 4*(w>>1)),
+ * bit l the pixel (x0 + (l&7), y0 + (l>>3)).  It is the backward kernel's work list.
+ * Any of render0 / alpha / last_ids / isect_ids / cmask / gt / loss_sum / wpix may be NULL. */
 int eg_raster_fwd(const eg_config *cfg, const float *rec, const int32_t *tile_offsets, uint64_t *keys,
                   int32_t *flatten_ids, int64_t *isect_ids, float *render0, float *alpha,
-                  int32_t *last_ids, const void *gt, int gt_kind, double *loss_sum, float *wpix,
-                  const int32_t *status, void *stream);
+                  int32_t *last_ids, uint32_t *cmask, const void *gt, int gt_kind, double *loss_sum,
+                  float *wpix, const int32_t *status, void *stream);
 
 /* K6: compositing backward with abs-grad.  Replaces gsplat rasterize_to_pixels bwd.
  * The seed of pixel p is  w_p = (sum_ch v_render[p,ch] + v_alpha[p]) * (1 - alpha[p])  when
  * v_render/v_alpha/alpha are given (generic autograd path; v_render has `v_render_channels`
  * interleaved channels), or  w_p = seed_scale * wpix[p]  (fused-loss path). */
 int eg_raster_bwd(const eg_config *cfg, const float *rec, const int32_t *tile_offsets,
-                  const int32_t *flatten_ids, const int32_t *last_ids, const float *alpha,
+                  const int32_t *flatten_ids, const uint32_t *cmask, const float *alpha,
                   const float *v_render, int v_render_channels, const float *v_alpha,
                   const float *wpix, float seed_scale, float *grad2d, const int32_t *status,
                   void *stream);
