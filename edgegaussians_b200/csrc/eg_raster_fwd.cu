@@ -277,17 +277,19 @@ __global__ void __launch_bounds__(RF_THREADS) raster_fwd_kernel(
             sAB[2 * tid] = make_float4(r0.x, r0.y, f.lo, __int_as_float(mask));
             sAB[2 * tid + 1] = make_float4(f.fa, f.fb, f.fc, 0.0f);
         }
-        if (cmask != nullptr) {
-            reinterpret_cast<uint4 *>(s_cm)[2 * tid] = make_uint4(0u, 0u, 0u, 0u);
-            reinterpret_cast<uint4 *>(s_cm)[2 * tid + 1] = make_uint4(0u, 0u, 0u, 0u);
+        if (cmask != nullptr) {  // zero the [8 warps][256 Gaussians] contribution words of the batch
+            reinterpret_cast<uint4 *>(s_cm)[tid] = make_uint4(0u, 0u, 0u, 0u);
+            reinterpret_cast<uint4 *>(s_cm)[tid + RF_THREADS] = make_uint4(0u, 0u, 0u, 0u);
         }
         __syncthreads();
         const int nb = min(RF_THREADS, L - b0);
         for (int c = 0; c < nb && !__all_sync(0xffffffffu, done); c += 32) {
             const int m = (c + lane < nb) ? __float_as_int(sAB[2 * (c + lane)].w) : 0;
             unsigned bits = __ballot_sync(0xffffffffu, (m >> warp) & 1);
+            unsigned myword = 0;  // lane j keeps the contribution mask of Gaussian c + j for this warp's pixels
             while (bits) {
-                const int t = c + __ffs(bits) - 1;
+                const int j = __ffs(bits) - 1;
+                const int t = c + j;
                 bits &= bits - 1;
                 const float4 a = sAB[2 * t];
                 const float4 cn = sAB[2 * t + 1];
@@ -302,17 +304,18 @@ __global__ void __launch_bounds__(RF_THREADS) raster_fwd_kernel(
                 out = take ? fmaf(al, T, out) : out;
                 T = take ? nT : T;
                 last = take ? (b0 + t) : last;
-                if (cmask != nullptr) {
-                    const unsigned bal = __ballot_sync(0xffffffffu, take);
-                    if (lane == 0) s_cm[t * 8 + warp] = bal;
-                }
+                const unsigned bal = __ballot_sync(0xffffffffu, take);
+                myword = (lane == j) ? bal : myword;
             }
+            s_cm[warp * RF_THREADS + c + lane] = myword;  // [warp][Gaussian]: conflict-free
         }
         if (cmask != nullptr) {  // contribution masks of this batch -> global (32 B per intersection)
             __syncthreads();
             if (k < L) {
-                cmask[2 * (size_t)(start + k)] = reinterpret_cast<const uint4 *>(s_cm)[2 * tid];
-                cmask[2 * (size_t)(start + k) + 1] = reinterpret_cast<const uint4 *>(s_cm)[2 * tid + 1];
+                cmask[2 * (size_t)(start + k)] = make_uint4(s_cm[tid], s_cm[RF_THREADS + tid], s_cm[2 * RF_THREADS + tid],
+                                                            s_cm[3 * RF_THREADS + tid]);
+                cmask[2 * (size_t)(start + k) + 1] = make_uint4(s_cm[4 * RF_THREADS + tid], s_cm[5 * RF_THREADS + tid],
+                                                                s_cm[6 * RF_THREADS + tid], s_cm[7 * RF_THREADS + tid]);
             }
             b_done = b0 + RF_THREADS;
         }
