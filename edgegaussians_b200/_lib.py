@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(HERE, "_C", "libedgegs.so")
 EG_ST_NISECT, EG_ST_OVERFLOW, EG_ST_BADCOLOR, EG_ST_MAXTILE, EG_ST_WORDS = 0, 1, 2, 3, 8
 EG_GT_NONE, EG_GT_F32, EG_GT_U8 = 0, 1, 2
 EG_CNT_STRIDE = 32
+EG_FLAG_LAZY_SORT = 1
 
 EXPORTS = ["eg_last_error", "eg_abi_version", "eg_tile_grid", "eg_project_fwd", "eg_bin", "eg_raster_fwd",
            "eg_raster_bwd", "eg_project_bwd", "eg_reg_fwd_bwd", "eg_knn_workspace_bytes", "eg_knn", "eg_adam_step"]
@@ -24,7 +25,7 @@ class EgConfig(Structure):
     _fields_ = [("n", c_int32), ("width", c_int32), ("height", c_int32), ("tile_size", c_int32),
                 ("eps2d", c_float), ("near_plane", c_float), ("far_plane", c_float), ("radius_clip", c_float),
                 ("antialiased", c_int32), ("raw_params", c_int32), ("isect_capacity", c_int64),
-                ("tile_capacity", c_int32), ("reserved", c_int32)]
+                ("tile_capacity", c_int32), ("flags", c_int32)]
 
 
 _lib = None

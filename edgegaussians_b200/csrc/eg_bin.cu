@@ -26,10 +26,17 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const int32_t *__res
     if (tid == 0) carry_s = 0;
     int32_t vmax = 0;
     __syncthreads();
-    for (int base = 0; base < T; base += SCAN_THREADS) {
-        const int i = base + tid;
-        const int32_t v = i < T ? counts[(size_t)i * EG_CNT_STRIDE] : 0;
-        vmax = max(vmax, v);
+    constexpr int PER = 8;  // consecutive tiles per thread: 8 independent loads in flight, one block scan per 8192 tiles
+    for (int base = 0; base < T; base += SCAN_THREADS * PER) {
+        const int i0 = base + tid * PER;
+        int32_t vals[PER];
+        int32_t v = 0;
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            vals[q] = (i0 + q < T) ? counts[(size_t)(i0 + q) * EG_CNT_STRIDE] : 0;
+            vmax = max(vmax, vals[q]);
+            v += vals[q];
+        }
         int32_t x = v;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -50,7 +57,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const int32_t *__res
         __syncthreads();
         const int32_t carry = carry_s;
         const int32_t incl = x + (wid > 0 ? warp_sums[wid - 1] : 0) + carry;
-        if (i < T) offsets[i] = incl - v;
+        int32_t run = incl - v;
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            if (i0 + q < T) offsets[i0 + q] = run;
+            run += vals[q];
+        }
         __syncthreads();
         if (tid == SCAN_THREADS - 1) carry_s = incl;
         __syncthreads();

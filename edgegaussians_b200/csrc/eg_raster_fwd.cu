@@ -214,11 +214,33 @@ __global__ void __launch_bounds__(RF_THREADS) raster_fwd_kernel(
     const int start = tile_offsets[tile];
     const int L = tile_offsets[tile + 1] - start;
 
-    // ---------------- phase A: sort the segment ----------------
+    const int sub_x = tile_x * EG_TILE + 8 * (warp & 1), sub_y = tile_y * EG_TILE + 4 * (warp >> 1);
+    const int pxi = sub_x + (lane & 7), pyi = sub_y + (lane >> 3);
+    const bool inside = pxi < cfg.width && pyi < cfg.height;
+    const float px = (float)pxi + 0.5f, py = (float)pyi + 0.5f;
+    const float X0 = (float)(tile_x * EG_TILE), Y0 = (float)(tile_y * EG_TILE);
     const bool on_chip = L <= SORT_CAP;
-    if (L > 0) {
+    u64 *bucket = keys + (size_t)tile * (size_t)cfg.tile_capacity;
+
+    // EG_FLAG_LAZY_SORT: composite once in bucket (arbitrary) order.  If no pixel of the tile comes near the
+    // transmittance stop threshold, no prefix product in ANY order can cross it, so gsplat's result is the
+    // order-free product and the sort is skipped (flatten_ids then holds the tile's ids unsorted).  Otherwise
+    // the tile is redone in sorted order (pass 1), which is always exact.
+    const bool lazy = (cfg.flags & EG_FLAG_LAZY_SORT) != 0 && isect_ids == nullptr && last_ids == nullptr;
+    float T = 1.0f, out = 0.0f;
+    int last = -start;
+    for (int pass = lazy ? 0 : 1; pass < 2; ++pass) {
+    const bool sorted = pass == 1;
+    const float t_stop = sorted ? EG_T_MIN : EG_T_MIN * 1.0002f;
+    // ---------------- phase A: sort the segment ----------------
+    if (L > 0 && !sorted) {
+        for (int i = tid; i < L; i += RF_THREADS) {
+            const uint32_t id = (uint32_t)bucket[i];
+            flatten_ids[start + i] = (int32_t)id;
+            if (on_chip) sids[i] = id;
+        }
+    } else if (L > 0) {
         const long long tile_hi = (long long)tile << 32;
-        u64 *bucket = keys + (size_t)tile * (size_t)cfg.tile_capacity;
         long long *isect = isect_ids ? isect_ids + start : nullptr;
         if (L <= 256) {
             int n_pad = 32;
@@ -241,16 +263,12 @@ __global__ void __launch_bounds__(RF_THREADS) raster_fwd_kernel(
     }
 
     // ---------------- phase B: compositing ----------------
-    const int sub_x = tile_x * EG_TILE + 8 * (warp & 1), sub_y = tile_y * EG_TILE + 4 * (warp >> 1);
-    const int pxi = sub_x + (lane & 7), pyi = sub_y + (lane >> 3);
-    const bool inside = pxi < cfg.width && pyi < cfg.height;
-    const float px = (float)pxi + 0.5f, py = (float)pyi + 0.5f;
-    const float X0 = (float)(tile_x * EG_TILE), Y0 = (float)(tile_y * EG_TILE);
-
-    float T = 1.0f, out = 0.0f;
+    T = 1.0f;
+    out = 0.0f;
     int b_done = 0;  // Gaussians [0, b_done) of the segment have their contribution masks written
-    int last = -start;  // relative to the segment start; gsplat initialises the absolute index to 0
+    last = -start;   // relative to the segment start; gsplat initialises the absolute index to 0
     bool done = !inside;
+    bool near_stop = false;
 
     for (int b0 = 0; b0 < L; b0 += RF_THREADS) {
         // barrier doubles as "sorted ids / previous batch visible" and the all-pixels-done early exit
@@ -298,7 +316,8 @@ __global__ void __launch_bounds__(RF_THREADS) raster_fwd_kernel(
                 const float al = fminf(EG_ALPHA_MAX, eg_ex2(pw2));
                 const bool valid = !done && pw2 <= a.z && al >= EG_ALPHA_MIN;  // sigma >= 0 and alpha >= 1/255
                 const float nT = T * (1.0f - al);
-                const bool stop = valid && nT <= EG_T_MIN;
+                const bool stop = valid && nT <= t_stop;
+                near_stop = near_stop || stop;
                 const bool take = valid && !stop;
                 done = done || stop;
                 out = take ? fmaf(al, T, out) : out;
@@ -325,6 +344,8 @@ __global__ void __launch_bounds__(RF_THREADS) raster_fwd_kernel(
             cmask[2 * (size_t)(start + k)] = make_uint4(0u, 0u, 0u, 0u);
             cmask[2 * (size_t)(start + k) + 1] = make_uint4(0u, 0u, 0u, 0u);
         }
+    if (sorted || !__syncthreads_or(near_stop)) break;
+    }  // pass
 
     // ---------------- epilogue ----------------
     float absd = 0.0f;

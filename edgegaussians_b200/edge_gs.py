@@ -87,6 +87,7 @@ class EdgeGaussianSplatting(torch.nn.Module):
         super().__init__()
         self.device = device
         self.step = 0
+        self.lazy_sort = True  # fused step: skip the per-tile sort where the blend order provably cannot matter
         self.crop_box = None
         self._ws: Optional[RasterStepWorkspace] = None
         self.config = EdgeGaussianSplattingConfig()
@@ -257,7 +258,7 @@ class EdgeGaussianSplatting(torch.nn.Module):
         return ws
 
     def enqueue_raster_step(self, viewmat, K, W, H, gt, *, loss_weight=1.0, accumulate_absgrad=True, capacity=None,
-                            want_render=False, stage_cb=None) -> RasterStepWorkspace:
+                            want_render=False, stage_cb=None, lazy_sort=None) -> RasterStepWorkspace:
         """Enqueue one fused forward+backward iteration on the current stream. No host sync, no
         allocation after the first call for a given (N, W, H): CUDA-graph capturable.
 
@@ -270,7 +271,8 @@ class EdgeGaussianSplatting(torch.nn.Module):
         N = ws.N
         cfg = _lib.EgConfig(n=N, width=W, height=H, tile_size=TILE, eps2d=0.3, near_plane=0.01, far_plane=1e10,
                             radius_clip=0.0, antialiased=1 if self.config.rasterize_mode == "antialiased" else 0,
-                            raw_params=1, isect_capacity=ws.capacity, tile_capacity=ws.tile_capacity)
+                            raw_params=1, isect_capacity=ws.capacity, tile_capacity=ws.tile_capacity,
+                            flags=_lib.EG_FLAG_LAZY_SORT if (self.lazy_sort if lazy_sort is None else lazy_sort) else 0)
         c = ctypes.byref(cfg)
         s = _stream()
         gt_kind = _lib.EG_GT_U8 if gt.dtype == torch.uint8 else _lib.EG_GT_F32

@@ -49,12 +49,18 @@
 extern "C" {
 #endif
 
-#define EG_ABI_VERSION 4
+#define EG_ABI_VERSION 5
 #define EG_CNT_STRIDE 32
 
 enum { EG_ST_NISECT = 0, EG_ST_OVERFLOW = 1, EG_ST_BADCOLOR = 2, EG_ST_MAXTILE = 3, EG_ST_WORDS = 8 };
 
 enum { EG_GT_NONE = 0, EG_GT_F32 = 1, EG_GT_U8 = 2 };
+
+/* eg_config.flags.  EG_FLAG_LAZY_SORT (fused training step only; ignored when isect_ids or last_ids are
+ * requested): eg_raster_fwd composites each tile once in arbitrary order and sorts + redoes it only if some
+ * pixel came near gsplat's transmittance stop threshold -- when none does, the blend result cannot depend on
+ * the order.  flatten_ids is then unordered inside such tiles (cmask stays aligned with it). */
+enum { EG_FLAG_LAZY_SORT = 1 };
 
 typedef struct eg_config {
     int32_t n;            /* number of Gaussians                                   */
@@ -69,7 +75,7 @@ typedef struct eg_config {
     int32_t raw_params;   /* 1 = log-scales / logit-opacities, activations fused   */
     int64_t isect_capacity; /* elements available in flatten_ids / isect_ids          */
     int32_t tile_capacity;  /* keys per tile bucket (keys holds T * tile_capacity)    */
-    int32_t reserved;
+    int32_t flags;          /* EG_FLAG_*                                              */
 } eg_config;
 
 const char *eg_last_error(void);
