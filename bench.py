@@ -193,7 +193,7 @@ def run_b200(args):
     model = EdgeGaussianSplatting(device=dev)
     cams = [OpenCVCamera.from_matrices(H, W, Ks[v], vms[v]).to(dev) for v in my_views]
     model.set_params(m, s, q, o, viewcams=cams)
-    model.lazy_sort = not args.no_lazy_sort
+    model.lazy_sort = False if args.no_lazy_sort else "auto"
 
     step = GraphedRasterStep(model, W, H, n_slots=V, gt_dtype=torch.uint8)
     host_vm = [torch.from_numpy(vms[v]).pin_memory() for v in my_views]
@@ -336,7 +336,7 @@ def run_b200(args):
             "config": {"workload": f"{N} Gaussians x {W}x{H}, 1 view/iter/GPU, regime={args.regime}, {V} views cycled per GPU",
                        "n_isects": I_mean, "isect_per_gaussian": I_mean / N, "overflow": overflow,
                        "l2": "flushed between timed iterations (256 MiB fill)" if flush_buf is not None else "not flushed",
-                       "tile_sort": "lazy (only tiles near the transmittance stop threshold)" if model.lazy_sort else "every tile",
+                       "tile_sort": "lazy (only tiles near the transmittance stop threshold)" if model._use_lazy() else "every tile",
                        "execution": "CUDA graph replay per iteration (1 memset + 5 kernels)" + (", + NCCL all-reduce of the 11N fp32 gradient buffer" if world > 1 else ""),
                        "parallelism": f"view-sharded dp{world}" if world > 1 else "single GPU"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",

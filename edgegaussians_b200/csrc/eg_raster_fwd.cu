@@ -194,12 +194,12 @@ __device__ void sort_large(u64 *__restrict__ gk, int L, u64 *s, int tid) {
 }
 
 template <int GT_KIND>
-__global__ void __launch_bounds__(RF_THREADS) raster_fwd_kernel(
+__global__ void __launch_bounds__(RF_THREADS, 5) raster_fwd_kernel(
     const eg_config cfg, int tw, const float4 *__restrict__ rec, const int32_t *__restrict__ tile_offsets,
     u64 *__restrict__ keys, int32_t *__restrict__ flatten_ids, long long *__restrict__ isect_ids,
     float *__restrict__ render0, float *__restrict__ alpha_out, int32_t *__restrict__ last_ids,
     uint4 *__restrict__ cmask, const void *__restrict__ gt, double *__restrict__ loss_sum,
-    float *__restrict__ wpix, const int32_t *__restrict__ status) {
+    float *__restrict__ wpix, int32_t *__restrict__ status) {
     __shared__ __align__(16) u64 sbuf[2 * SORT_CAP];  // sort exchange buffers, then the sorted ids
     __shared__ __align__(16) float4 sAB[2 * RF_THREADS];  // per Gaussian: (mean2d.x, mean2d.y, log2 opacity,
                                                           // sub-tile mask bits) , (folded conic fa, fb, fc, -)
@@ -345,6 +345,7 @@ __global__ void __launch_bounds__(RF_THREADS) raster_fwd_kernel(
             cmask[2 * (size_t)(start + k) + 1] = make_uint4(0u, 0u, 0u, 0u);
         }
     if (sorted || !__syncthreads_or(near_stop)) break;
+    if (tid == 0) atomicAdd(status + EG_ST_REDO, 1);  // lets the host switch lazy sorting off when it stops paying
     }  // pass
 
     // ---------------- epilogue ----------------
@@ -385,7 +386,7 @@ __global__ void __launch_bounds__(RF_THREADS) raster_fwd_kernel(
 extern "C" int eg_raster_fwd(const eg_config *cfg, const float *rec, const int32_t *tile_offsets, uint64_t *keys,
                              int32_t *flatten_ids, int64_t *isect_ids, float *render0, float *alpha,
                              int32_t *last_ids, uint32_t *cmask, const void *gt, int gt_kind, double *loss_sum,
-                             float *wpix, const int32_t *status, void *stream) {
+                             float *wpix, int32_t *status, void *stream) {
     if (cfg == nullptr || cfg->tile_size != EG_TILE) {
         eg_set_error("eg_raster_fwd: tile_size must be %d", EG_TILE);
         return 1;

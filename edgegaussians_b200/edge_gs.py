@@ -87,7 +87,11 @@ class EdgeGaussianSplatting(torch.nn.Module):
         super().__init__()
         self.device = device
         self.step = 0
-        self.lazy_sort = True  # fused step: skip the per-tile sort where the blend order provably cannot matter
+        # fused step: skip the per-tile sort where the blend order provably cannot matter.  "auto" starts lazy and
+        # switches it off for good once more than a quarter of the tiles had to be redone in sorted order
+        # (opaque, saturating scenes late in training), as reported by status[EG_ST_REDO].
+        self.lazy_sort = "auto"
+        self._lazy_on = True
         self.crop_box = None
         self._ws: Optional[RasterStepWorkspace] = None
         self.config = EdgeGaussianSplattingConfig()
@@ -272,7 +276,7 @@ class EdgeGaussianSplatting(torch.nn.Module):
         cfg = _lib.EgConfig(n=N, width=W, height=H, tile_size=TILE, eps2d=0.3, near_plane=0.01, far_plane=1e10,
                             radius_clip=0.0, antialiased=1 if self.config.rasterize_mode == "antialiased" else 0,
                             raw_params=1, isect_capacity=ws.capacity, tile_capacity=ws.tile_capacity,
-                            flags=_lib.EG_FLAG_LAZY_SORT if (self.lazy_sort if lazy_sort is None else lazy_sort) else 0)
+                            flags=_lib.EG_FLAG_LAZY_SORT if self._use_lazy(lazy_sort) else 0)
         c = ctypes.byref(cfg)
         s = _stream()
         gt_kind = _lib.EG_GT_U8 if gt.dtype == torch.uint8 else _lib.EG_GT_F32
@@ -303,6 +307,15 @@ class EdgeGaussianSplatting(torch.nn.Module):
         cb("project_bwd")
         return ws
 
+    def _use_lazy(self, override=None) -> bool:
+        mode = self.lazy_sort if override is None else override
+        return self._lazy_on if mode == "auto" else bool(mode)
+
+    def note_redo(self, redo_tiles: int, n_tiles: int) -> None:
+        """Feed back status[EG_ST_REDO] of a finished step (any host read of the status words)."""
+        if self.lazy_sort == "auto" and self._lazy_on and redo_tiles > 0.25 * n_tiles:
+            self._lazy_on = False
+
     def install_grads(self, ws: RasterStepWorkspace):
         N, g = ws.N, ws.grads
         self.means.grad = g[0:3 * N].view(N, 3)
@@ -326,6 +339,7 @@ class EdgeGaussianSplatting(torch.nn.Module):
             if not sync:
                 break
             hs = ws.status.cpu()
+            self.note_redo(int(hs[_lib.EG_ST_REDO]), ws.T)
             if not int(hs[_lib.EG_ST_OVERFLOW]):
                 break
             # roll back the abs-grad accumulation is unnecessary: overflowed runs are no-ops in raster kernels

@@ -52,14 +52,15 @@ extern "C" {
 #define EG_ABI_VERSION 5
 #define EG_CNT_STRIDE 32
 
-enum { EG_ST_NISECT = 0, EG_ST_OVERFLOW = 1, EG_ST_BADCOLOR = 2, EG_ST_MAXTILE = 3, EG_ST_WORDS = 8 };
+enum { EG_ST_NISECT = 0, EG_ST_OVERFLOW = 1, EG_ST_BADCOLOR = 2, EG_ST_MAXTILE = 3, EG_ST_REDO = 4, EG_ST_WORDS = 8 };
 
 enum { EG_GT_NONE = 0, EG_GT_F32 = 1, EG_GT_U8 = 2 };
 
 /* eg_config.flags.  EG_FLAG_LAZY_SORT (fused training step only; ignored when isect_ids or last_ids are
  * requested): eg_raster_fwd composites each tile once in arbitrary order and sorts + redoes it only if some
  * pixel came near gsplat's transmittance stop threshold -- when none does, the blend result cannot depend on
- * the order.  flatten_ids is then unordered inside such tiles (cmask stays aligned with it). */
+ * the order.  flatten_ids is then unordered inside such tiles (cmask stays aligned with it).
+ * status[EG_ST_REDO] counts the tiles that had to be redone. */
 enum { EG_FLAG_LAZY_SORT = 1 };
 
 typedef struct eg_config {
@@ -113,7 +114,7 @@ int eg_bin(const eg_config *cfg, const int32_t *tile_counts, int32_t *tile_offse
 int eg_raster_fwd(const eg_config *cfg, const float *rec, const int32_t *tile_offsets, uint64_t *keys,
                   int32_t *flatten_ids, int64_t *isect_ids, float *render0, float *alpha,
                   int32_t *last_ids, uint32_t *cmask, const void *gt, int gt_kind, double *loss_sum,
-                  float *wpix, const int32_t *status, void *stream);
+                  float *wpix, int32_t *status, void *stream);
 
 /* K6: compositing backward with abs-grad.  Replaces gsplat rasterize_to_pixels bwd.
  * The seed of pixel p is  w_p = (sum_ch v_render[p,ch] + v_alpha[p]) * (1 - alpha[p])  when
