@@ -140,12 +140,30 @@ __global__ void __launch_bounds__(256) project_fwd_kernel(
     gint[g] = make_int2(radius_i, ntiles);
     // K2 emission: append (depth_bits << 32 | id) to the bucket of every tile of the rectangle
     const unsigned long long key = ((unsigned long long)__float_as_uint(r0.w) << 32) | (unsigned int)g;
-    for (uint32_t i = y0; i < y1; ++i)
-        for (uint32_t j = x0; j < x1; ++j) {
-            const size_t t = (size_t)(i * tw + j);
-            const int pos = atomicAdd(tile_counts + t * EG_CNT_STRIDE, 1);
-            if (pos < cfg.tile_capacity) keys[t * (size_t)cfg.tile_capacity + pos] = key;
-        }
+    const uint32_t w = x1 - x0;
+    if (ntiles > 0 && ntiles <= 12) {
+        // common case: issue all the (independent) atomics first so that they overlap, then the stores
+        int pos[12];
+#pragma unroll
+        for (int q = 0; q < 12; ++q)
+            if (q < ntiles) {
+                const uint32_t i = y0 + (uint32_t)q / w, j = x0 + (uint32_t)q % w;
+                pos[q] = atomicAdd(tile_counts + (size_t)(i * tw + j) * EG_CNT_STRIDE, 1);
+            }
+#pragma unroll
+        for (int q = 0; q < 12; ++q)
+            if (q < ntiles) {
+                const uint32_t i = y0 + (uint32_t)q / w, j = x0 + (uint32_t)q % w;
+                if (pos[q] < cfg.tile_capacity) keys[(size_t)(i * tw + j) * (size_t)cfg.tile_capacity + pos[q]] = key;
+            }
+    } else {
+        for (uint32_t i = y0; i < y1; ++i)
+            for (uint32_t j = x0; j < x1; ++j) {
+                const size_t t = (size_t)(i * tw + j);
+                const int pos = atomicAdd(tile_counts + t * EG_CNT_STRIDE, 1);
+                if (pos < cfg.tile_capacity) keys[t * (size_t)cfg.tile_capacity + pos] = key;
+            }
+    }
 }
 
 }  // namespace
