@@ -195,7 +195,7 @@ def run_b200(args):
     model.set_params(m, s, q, o, viewcams=cams)
     model.lazy_sort = False if args.no_lazy_sort else "auto"
 
-    step = GraphedRasterStep(model, W, H, n_slots=V, gt_dtype=torch.uint8)
+    step = GraphedRasterStep(model, W, H, n_slots=V, gt_dtype=torch.uint8, allreduce=world > 1)
     host_vm = [torch.from_numpy(vms[v]).pin_memory() for v in my_views]
     host_K = [torch.from_numpy(Ks[v]).pin_memory() for v in my_views]
     host_gt = [torch.from_numpy(g).pin_memory() for g in gts_u8]
@@ -215,9 +215,7 @@ def run_b200(args):
             flush_buf.fill_(1)
 
     def one_step(i):
-        step.replay(i % V)
-        if world > 1:
-            dist.all_reduce(grads)
+        step.replay(i % V)   # includes the NCCL all-reduce of the gradient buffer when world > 1
 
     def barrier():
         if world > 1:
@@ -296,8 +294,6 @@ def run_b200(args):
                     copy_stream.wait_event(done[nslot])
                 pend = upload(nslot, i + 1)
             step.replay(slot)
-            if world > 1:
-                dist.all_reduce(grads)
             loss_host.copy_(ws.loss_sum, non_blocking=True)
             e = torch.cuda.Event()
             e.record(cur)
@@ -337,7 +333,7 @@ def run_b200(args):
                        "n_isects": I_mean, "isect_per_gaussian": I_mean / N, "overflow": overflow,
                        "l2": "flushed between timed iterations (256 MiB fill)" if flush_buf is not None else "not flushed",
                        "tile_sort": "lazy (only tiles near the transmittance stop threshold)" if model._use_lazy() else "every tile",
-                       "execution": "CUDA graph replay per iteration (1 memset + 5 kernels)" + (", + NCCL all-reduce of the 11N fp32 gradient buffer" if world > 1 else ""),
+                       "execution": "CUDA graph replay per iteration (1 memset + 5 kernels)" + ((", + NCCL all-reduce of the 11N fp32 gradient buffer " + ("captured in the graph" if step.allreduce_in_graph else "issued after the replay")) if world > 1 else ""),
                        "parallelism": f"view-sharded dp{world}" if world > 1 else "single GPU"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,

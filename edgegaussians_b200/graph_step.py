@@ -18,13 +18,17 @@ from .engine import get_engine
 
 class GraphedRasterStep:
     def __init__(self, model: EdgeGaussianSplatting, width: int, height: int, n_slots: int, gt_dtype=torch.uint8,
-                 loss_weight: float = 1.0, accumulate_absgrad: bool = True):
+                 loss_weight: float = 1.0, accumulate_absgrad: bool = True, allreduce_group=None, allreduce: bool = False):
         dev = model.means.device
         self.model, self.W, self.H, self.n_slots = model, width, height, n_slots
         self.loss_weight, self.accumulate_absgrad = loss_weight, accumulate_absgrad
         self.viewmats = torch.zeros((n_slots, 4, 4), dtype=torch.float32, device=dev)
         self.Ks = torch.zeros((n_slots, 3, 3), dtype=torch.float32, device=dev)
         self.gts = torch.zeros((n_slots, height, width), dtype=gt_dtype, device=dev)
+        # view-sharded data parallelism: the NCCL all-reduce of the flat gradient buffer is captured INSIDE the
+        # graph, right behind eg_project_bwd (no host launch latency between the last kernel and the collective)
+        self.allreduce, self.allreduce_group = allreduce, allreduce_group
+        self.allreduce_in_graph = False
         self.graphs: Dict[int, torch.cuda.CUDAGraph] = {}
         self.ws: Optional[RasterStepWorkspace] = None
         self._capacity = None
@@ -65,10 +69,25 @@ class GraphedRasterStep:
     def capture(self, slot: int, stage_cb=None) -> torch.cuda.CUDAGraph:
         if self.ws is None:
             self.calibrate([slot])
+        import torch.distributed as dist
         g = torch.cuda.CUDAGraph()
         torch.cuda.synchronize()
-        with torch.cuda.graph(g):
-            ws = self._enqueue(slot, stage_cb=stage_cb)
+        want_ar = self.allreduce and stage_cb is None and dist.is_initialized() and dist.get_world_size(self.allreduce_group) > 1
+        try:
+            with torch.cuda.graph(g):
+                ws = self._enqueue(slot, stage_cb=stage_cb)
+                if want_ar:
+                    dist.all_reduce(ws.grads, group=self.allreduce_group)
+            self.allreduce_in_graph = bool(want_ar)
+        except Exception:
+            if not want_ar:
+                raise
+            # NCCL capture unavailable: capture the kernels only, issue the collective eagerly after replay
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                ws = self._enqueue(slot, stage_cb=stage_cb)
+            self.allreduce_in_graph = False
         assert ws is self.ws, "workspace changed during capture"
         if stage_cb is None:
             self.graphs[slot] = g
@@ -79,6 +98,10 @@ class GraphedRasterStep:
         if g is None:
             g = self.capture(slot)
         g.replay()
+        if self.allreduce and not self.allreduce_in_graph:
+            import torch.distributed as dist
+            if dist.is_initialized() and dist.get_world_size(self.allreduce_group) > 1:
+                dist.all_reduce(self.ws.grads, group=self.allreduce_group)
         return self.ws
 
     def loss(self) -> torch.Tensor:

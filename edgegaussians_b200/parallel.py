@@ -50,6 +50,14 @@ def allreduce_gradients(flat: torch.Tensor, absgrad_increment: Optional[torch.Te
         flat.div_(dist.get_world_size(group))
 
 
+def sync_absgrads(model, group=None) -> None:
+    """Sum the per-rank abs-grad statistics (model.absgrads, accumulated locally by the fused step) over all
+    ranks.  Needed only where the reference reads them: at densification (edge_gs.py:544-576), i.e. once per
+    epoch boundary, not per step."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(model.absgrads, op=dist.ReduceOp.SUM, group=group)
+
+
 class ViewShardedStep:
     """Drives ``EdgeGaussianSplatting.raster_step`` on this rank's view and all-reduces the result.
 
