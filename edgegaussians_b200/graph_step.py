@@ -8,6 +8,7 @@ static per-slot device buffers that are refreshed by (async) copies before the r
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import torch
@@ -72,7 +73,13 @@ class GraphedRasterStep:
         import torch.distributed as dist
         g = torch.cuda.CUDAGraph()
         torch.cuda.synchronize()
-        want_ar = self.allreduce and stage_cb is None and dist.is_initialized() and dist.get_world_size(self.allreduce_group) > 1
+        # capturing the collective is opt-in (EG_GRAPH_ALLREDUCE=1): NCCL capture needs a warmed-up communicator
+        # and has hung on some driver/NCCL combinations; the default issues the all-reduce right after the replay
+        want_ar = (self.allreduce and stage_cb is None and os.environ.get("EG_GRAPH_ALLREDUCE") == "1"
+                   and dist.is_initialized() and dist.get_world_size(self.allreduce_group) > 1)
+        if want_ar:  # make sure the communicator exists before the capture starts
+            dist.all_reduce(torch.zeros(1, device=self.viewmats.device), group=self.allreduce_group)
+            torch.cuda.synchronize()
         try:
             with torch.cuda.graph(g):
                 ws = self._enqueue(slot, stage_cb=stage_cb)
