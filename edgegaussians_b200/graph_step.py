@@ -8,7 +8,6 @@ static per-slot device buffers that are refreshed by (async) copies before the r
 """
 from __future__ import annotations
 
-import os
 from typing import Dict, Optional
 
 import torch
@@ -26,8 +25,9 @@ class GraphedRasterStep:
         self.viewmats = torch.zeros((n_slots, 4, 4), dtype=torch.float32, device=dev)
         self.Ks = torch.zeros((n_slots, 3, 3), dtype=torch.float32, device=dev)
         self.gts = torch.zeros((n_slots, height, width), dtype=gt_dtype, device=dev)
-        # view-sharded data parallelism: the NCCL all-reduce of the flat gradient buffer is captured INSIDE the
-        # graph, right behind eg_project_bwd (no host launch latency between the last kernel and the collective)
+        # view-sharded data parallelism: the NCCL all-reduce of the flat gradient buffer is issued on the same
+        # stream right behind the replay.  (Capturing the collective inside the graph was tried and hung on this
+        # stack -- torch 2.11 / NCCL 2.28.9 -- so it is not done.)
         self.allreduce, self.allreduce_group = allreduce, allreduce_group
         self.allreduce_in_graph = False
         self.graphs: Dict[int, torch.cuda.CUDAGraph] = {}
@@ -70,31 +70,10 @@ class GraphedRasterStep:
     def capture(self, slot: int, stage_cb=None) -> torch.cuda.CUDAGraph:
         if self.ws is None:
             self.calibrate([slot])
-        import torch.distributed as dist
         g = torch.cuda.CUDAGraph()
         torch.cuda.synchronize()
-        # capturing the collective is opt-in (EG_GRAPH_ALLREDUCE=1): NCCL capture needs a warmed-up communicator
-        # and has hung on some driver/NCCL combinations; the default issues the all-reduce right after the replay
-        want_ar = (self.allreduce and stage_cb is None and os.environ.get("EG_GRAPH_ALLREDUCE") == "1"
-                   and dist.is_initialized() and dist.get_world_size(self.allreduce_group) > 1)
-        if want_ar:  # make sure the communicator exists before the capture starts
-            dist.all_reduce(torch.zeros(1, device=self.viewmats.device), group=self.allreduce_group)
-            torch.cuda.synchronize()
-        try:
-            with torch.cuda.graph(g):
-                ws = self._enqueue(slot, stage_cb=stage_cb)
-                if want_ar:
-                    dist.all_reduce(ws.grads, group=self.allreduce_group)
-            self.allreduce_in_graph = bool(want_ar)
-        except Exception:
-            if not want_ar:
-                raise
-            # NCCL capture unavailable: capture the kernels only, issue the collective eagerly after replay
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                ws = self._enqueue(slot, stage_cb=stage_cb)
-            self.allreduce_in_graph = False
+        with torch.cuda.graph(g):
+            ws = self._enqueue(slot, stage_cb=stage_cb)
         assert ws is self.ws, "workspace changed during capture"
         if stage_cb is None:
             self.graphs[slot] = g
