@@ -16,6 +16,7 @@ EG_ST_NISECT, EG_ST_OVERFLOW, EG_ST_BADCOLOR, EG_ST_MAXTILE, EG_ST_REDO, EG_ST_W
 EG_GT_NONE, EG_GT_F32, EG_GT_U8 = 0, 1, 2
 EG_CNT_STRIDE = 32
 EG_FLAG_LAZY_SORT = 1
+EG_FLAG_COMPACT_KEYS = 2
 
 EXPORTS = ["eg_last_error", "eg_abi_version", "eg_tile_grid", "eg_project_fwd", "eg_bin", "eg_raster_fwd",
            "eg_raster_bwd", "eg_project_bwd", "eg_reg_fwd_bwd", "eg_knn_workspace_bytes", "eg_knn", "eg_adam_step"]
@@ -51,7 +52,7 @@ def load(build_if_missing: bool = True):
     cfgp = POINTER(EgConfig)
     lib.eg_tile_grid.argtypes = [c_int, c_int, c_int, POINTER(c_int), POINTER(c_int)]
     lib.eg_project_fwd.argtypes = [cfgp] + [P] * 13
-    lib.eg_bin.argtypes = [cfgp] + [P] * 4
+    lib.eg_bin.argtypes = [cfgp] + [P] * 7
     lib.eg_raster_fwd.argtypes = [cfgp] + [P] * 10 + [c_int, P, P, P, P]
     lib.eg_raster_bwd.argtypes = [cfgp] + [P] * 6 + [c_int, P, P, c_float, P, P, P]
     lib.eg_project_bwd.argtypes = [cfgp] + [P] * 9 + [c_int] + [P] * 7

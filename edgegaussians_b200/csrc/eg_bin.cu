@@ -15,10 +15,10 @@ namespace {
 
 constexpr int SCAN_THREADS = 1024;
 
-__global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const int32_t *__restrict__ counts,
+__global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(int32_t *__restrict__ counts,
                                                            int32_t *__restrict__ offsets, int T,
                                                            int32_t *__restrict__ status, long long capacity,
-                                                           int tile_capacity) {
+                                                           int tile_capacity, int compact) {
     __shared__ int32_t warp_sums[SCAN_THREADS / 32];
     __shared__ int32_t warp_max[SCAN_THREADS / 32];
     __shared__ int32_t carry_s;
@@ -60,7 +60,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const int32_t *__res
         int32_t run = incl - v;
 #pragma unroll
         for (int q = 0; q < PER; ++q) {
-            if (i0 + q < T) offsets[i0 + q] = run;
+            if (i0 + q < T) {
+                offsets[i0 + q] = run;
+                if (compact) counts[(size_t)(i0 + q) * EG_CNT_STRIDE + 1] = run;  // append cursor of the tile
+            }
             run += vals[q];
         }
         __syncthreads();
@@ -78,21 +81,54 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const int32_t *__res
         offsets[T] = total;
         status[EG_ST_NISECT] = total;
         status[EG_ST_MAXTILE] = m;
-        if ((long long)total > capacity || m > tile_capacity) status[EG_ST_OVERFLOW] = 1;
+        if ((long long)total > capacity || (!compact && m > tile_capacity)) status[EG_ST_OVERFLOW] = 1;
     }
+}
+
+// EG_FLAG_COMPACT_KEYS: second pass over the Gaussians, appending keys into the compact per-tile segments
+__global__ void __launch_bounds__(256) emit_kernel(int n, const float4 *__restrict__ rec,
+                                                   const int2 *__restrict__ gint, int32_t *__restrict__ counts,
+                                                   unsigned long long *__restrict__ keys, long long capacity,
+                                                   int tw, int th) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    const int2 gi = __ldg(gint + g);
+    if (gi.y <= 0) return;
+    const float4 r0 = __ldg(rec + 2 * g);
+    uint32_t x0, y0, x1, y1;
+    eg_tile_rect(r0.x, r0.y, gi.x, tw, th, x0, y0, x1, y1);
+    const unsigned long long key = ((unsigned long long)__float_as_uint(r0.w) << 32) | (unsigned int)g;
+    for (uint32_t i = y0; i < y1; ++i)
+        for (uint32_t j = x0; j < x1; ++j) {
+            const long long pos = atomicAdd(counts + (size_t)(i * tw + j) * EG_CNT_STRIDE + 1, 1);
+            if (pos < capacity) keys[pos] = key;
+        }
 }
 
 }  // namespace
 
-extern "C" int eg_bin(const eg_config *cfg, const int32_t *tile_counts, int32_t *tile_offsets, int32_t *status,
-                      void *stream) {
+extern "C" int eg_bin(const eg_config *cfg, int32_t *tile_counts, int32_t *tile_offsets, int32_t *status,
+                      const float *rec, const int32_t *gint, uint64_t *keys, void *stream) {
     if (cfg == nullptr || cfg->tile_size != EG_TILE) {
         eg_set_error("eg_bin: tile_size must be %d", EG_TILE);
         return 1;
     }
     int tw, th;
     eg_tile_grid(cfg->width, cfg->height, cfg->tile_size, &tw, &th);
+    const int compact = (cfg->flags & EG_FLAG_COMPACT_KEYS) ? 1 : 0;
     scan_kernel<<<1, SCAN_THREADS, 0, (cudaStream_t)stream>>>(tile_counts, tile_offsets, tw * th, status,
-                                                             (long long)cfg->isect_capacity, cfg->tile_capacity);
-    return eg_check_launch("eg_bin/scan");
+                                                             (long long)cfg->isect_capacity, cfg->tile_capacity,
+                                                             compact);
+    if (int e = eg_check_launch("eg_bin/scan")) return e;
+    if (compact && cfg->n > 0) {
+        if (rec == nullptr || gint == nullptr || keys == nullptr) {
+            eg_set_error("eg_bin: EG_FLAG_COMPACT_KEYS needs rec, gint and keys");
+            return 1;
+        }
+        emit_kernel<<<(cfg->n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+            cfg->n, (const float4 *)rec, (const int2 *)gint, tile_counts, (unsigned long long *)keys,
+            (long long)cfg->isect_capacity, tw, th);
+        return eg_check_launch("eg_bin/emit");
+    }
+    return 0;
 }

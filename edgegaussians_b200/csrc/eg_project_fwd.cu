@@ -141,7 +141,10 @@ __global__ void __launch_bounds__(256) project_fwd_kernel(
     // K2 emission: append (depth_bits << 32 | id) to the bucket of every tile of the rectangle
     const unsigned long long key = ((unsigned long long)__float_as_uint(r0.w) << 32) | (unsigned int)g;
     const uint32_t w = x1 - x0;
-    if (ntiles > 0 && ntiles <= 12) {
+    if (cfg.flags & EG_FLAG_COMPACT_KEYS) {  // count only; eg_bin emits after the scan
+        for (uint32_t i = y0; i < y1; ++i)
+            for (uint32_t j = x0; j < x1; ++j) atomicAdd(tile_counts + (size_t)(i * tw + j) * EG_CNT_STRIDE, 1);
+    } else if (ntiles > 0 && ntiles <= 12) {
         // common case: issue all the (independent) atomics first so that they overlap, then the stores
         int pos[12];
 #pragma unroll

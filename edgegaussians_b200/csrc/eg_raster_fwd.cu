@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(RF_THREADS, 5) raster_fwd_kernel(
     const float px = (float)pxi + 0.5f, py = (float)pyi + 0.5f;
     const float X0 = (float)(tile_x * EG_TILE), Y0 = (float)(tile_y * EG_TILE);
     const bool on_chip = L <= SORT_CAP;
-    u64 *bucket = keys + (size_t)tile * (size_t)cfg.tile_capacity;
+    u64 *bucket = (cfg.flags & EG_FLAG_COMPACT_KEYS) ? keys + start : keys + (size_t)tile * (size_t)cfg.tile_capacity;
 
     // EG_FLAG_LAZY_SORT: composite once in bucket (arbitrary) order.  If no pixel of the tile comes near the
     // transmittance stop threshold, no prefix product in ANY order can cross it, so gsplat's result is the

@@ -28,7 +28,7 @@ import torch
 
 from . import _lib
 from .cameras import BaseCamera
-from .engine import TILE, SplatState, get_engine, tile_capacity_for, tile_grid, _p, _stream
+from .engine import TILE, SplatState, get_engine, tile_capacity_for, tile_grid, use_compact_keys, _p, _stream
 from .losses import MaskedL1Loss, WeightedL1Loss
 from .rasterization import rasterization
 
@@ -72,7 +72,9 @@ class RasterStepWorkspace:
         self.status = self.zero_block[T * _lib.EG_CNT_STRIDE:T * _lib.EG_CNT_STRIDE + _lib.EG_ST_WORDS]
         self.loss_sum = self.zero_block[T * _lib.EG_CNT_STRIDE + _lib.EG_ST_WORDS:].view(torch.float64)
         self.tile_offsets = torch.empty(T + 1, dtype=i32, device=device)
-        self.keys = torch.empty(T * self.tile_capacity, dtype=torch.int64, device=device)
+        self.compact_keys = use_compact_keys(T, self.tile_capacity)
+        self.keys = torch.empty(self.capacity if self.compact_keys else T * self.tile_capacity, dtype=torch.int64,
+                                device=device)
         self.flatten_ids = torch.empty(self.capacity, dtype=i32, device=device)
         self.cmask = torch.empty((self.capacity, 8), dtype=i32, device=device)
         self.wpix = torch.empty((H, W), dtype=f32, device=device)
@@ -256,7 +258,7 @@ class EdgeGaussianSplatting(torch.nn.Module):
         eng = get_engine(self.means.device)
         want = int(capacity) if capacity is not None else max(eng._ensure_capacity(N), ws.capacity if ws else 0)
         if (ws is None or (ws.N, ws.W, ws.H) != (N, W, H) or ws.capacity < want
-                or ws.tile_capacity < tile_capacity_for(0, ws.T, eng.max_tile)):
+                or (not ws.compact_keys and ws.tile_capacity < tile_capacity_for(0, ws.T, eng.max_tile))):
             ws = RasterStepWorkspace(N, W, H, want, self.means.device, eng.max_tile)
             self._ws = ws
         return ws
@@ -276,7 +278,8 @@ class EdgeGaussianSplatting(torch.nn.Module):
         cfg = _lib.EgConfig(n=N, width=W, height=H, tile_size=TILE, eps2d=0.3, near_plane=0.01, far_plane=1e10,
                             radius_clip=0.0, antialiased=1 if self.config.rasterize_mode == "antialiased" else 0,
                             raw_params=1, isect_capacity=ws.capacity, tile_capacity=ws.tile_capacity,
-                            flags=_lib.EG_FLAG_LAZY_SORT if self._use_lazy(lazy_sort) else 0)
+                            flags=(_lib.EG_FLAG_LAZY_SORT if self._use_lazy(lazy_sort) else 0)
+                            | (_lib.EG_FLAG_COMPACT_KEYS if ws.compact_keys else 0))
         c = ctypes.byref(cfg)
         s = _stream()
         gt_kind = _lib.EG_GT_U8 if gt.dtype == torch.uint8 else _lib.EG_GT_F32
@@ -289,7 +292,8 @@ class EdgeGaussianSplatting(torch.nn.Module):
         chk(lib.eg_project_fwd(c, _p(means), _p(quats), _p(scales), _p(opac), None, _p(viewmat), _p(K), _p(ws.rec),
                                _p(ws.gint), _p(ws.tile_counts), _p(ws.keys), _p(ws.status), s), "eg_project_fwd")
         cb("project_fwd")
-        chk(lib.eg_bin(c, _p(ws.tile_counts), _p(ws.tile_offsets), _p(ws.status), s), "eg_bin")
+        chk(lib.eg_bin(c, _p(ws.tile_counts), _p(ws.tile_offsets), _p(ws.status), _p(ws.rec), _p(ws.gint),
+                       _p(ws.keys), s), "eg_bin")
         cb("bin")
         chk(lib.eg_raster_fwd(c, _p(ws.rec), _p(ws.tile_offsets), _p(ws.keys), _p(ws.flatten_ids), None,
                               _p(ws.render0) if want_render else None, None, None, _p(ws.cmask), _p(gt), gt_kind,

@@ -34,6 +34,15 @@ def tile_grid(width: int, height: int):
     return (width + TILE - 1) // TILE, (height + TILE - 1) // TILE
 
 
+KEY_BUCKET_BYTES_MAX = 1 << 30  # above this, tile buckets are replaced by compact per-tile segments
+
+
+def use_compact_keys(n_tiles: int, tile_capacity: int) -> bool:
+    """Fixed-capacity buckets cost T * tile_capacity * 8 B; a view where a few tiles hold most intersections
+    (camera far away) would blow that up, so such views use the two-pass compact layout instead."""
+    return n_tiles * tile_capacity * 8 > KEY_BUCKET_BYTES_MAX
+
+
 def tile_capacity_for(isect_capacity: int, n_tiles: int, max_tile: int = 0) -> int:
     """Keys per tile bucket: 4x the mean tile load implied by the intersection capacity, at least
     1.25x the largest tile seen so far, rounded up to a multiple of 64."""
@@ -83,10 +92,11 @@ class Engine:
 
     # ------------------------------------------------------------------ helpers
     def make_cfg(self, n, width, height, *, eps2d=0.3, near_plane=0.01, far_plane=1e10, radius_clip=0.0,
-                 antialiased=True, raw_params=False, capacity=0, tile_capacity=0) -> EgConfig:
+                 antialiased=True, raw_params=False, capacity=0, tile_capacity=0, flags=0) -> EgConfig:
         return EgConfig(n=n, width=width, height=height, tile_size=TILE, eps2d=eps2d, near_plane=near_plane,
                         far_plane=far_plane, radius_clip=radius_clip, antialiased=1 if antialiased else 0,
-                        raw_params=1 if raw_params else 0, isect_capacity=capacity, tile_capacity=tile_capacity)
+                        raw_params=1 if raw_params else 0, isect_capacity=capacity, tile_capacity=tile_capacity,
+                        flags=flags)
 
     def note_status(self, n_isects: int, max_tile: int) -> None:
         """Grow the capacity estimates after an overflow report."""
@@ -123,16 +133,17 @@ class Engine:
         status = torch.zeros(EG_ST_WORDS, dtype=torch.int32, device=dev)
         while True:
             tcap = tile_capacity_for(cap, T, self.max_tile)
+            compact = use_compact_keys(T, tcap)
             cfg = self.make_cfg(N, width, height, eps2d=eps2d, near_plane=near_plane, far_plane=far_plane,
                                 radius_clip=radius_clip, antialiased=antialiased, raw_params=raw_params,
-                                capacity=cap, tile_capacity=tcap)
-            keys = torch.empty(T * tcap, dtype=torch.int64, device=dev)
+                                capacity=cap, tile_capacity=tcap, flags=_lib.EG_FLAG_COMPACT_KEYS if compact else 0)
+            keys = torch.empty(cap if compact else T * tcap, dtype=torch.int64, device=dev)
             flatten_ids = torch.empty(cap, dtype=torch.int32, device=dev)
             _lib.check(self.lib.eg_project_fwd(ctypes.byref(cfg), _p(means), _p(quats), _p(scales), _p(opacities),
                                                _p(colors), _p(viewmat), _p(K), _p(rec), _p(gint),
                                                _p(tile_counts), _p(keys), _p(status), _stream()), "eg_project_fwd")
-            _lib.check(self.lib.eg_bin(ctypes.byref(cfg), _p(tile_counts), _p(tile_offsets), _p(status), _stream()),
-                       "eg_bin")
+            _lib.check(self.lib.eg_bin(ctypes.byref(cfg), _p(tile_counts), _p(tile_offsets), _p(status), _p(rec),
+                                       _p(gint), _p(keys), _stream()), "eg_bin")
             st = SplatState(cfg=cfg, N=N, width=width, height=height, tile_w=tw, tile_h=th, rec=rec, gint=gint,
                             tile_offsets=tile_offsets, keys=keys, flatten_ids=flatten_ids, status=status)
             if not sync:

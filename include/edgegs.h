@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define EG_ABI_VERSION 5
+#define EG_ABI_VERSION 6
 #define EG_CNT_STRIDE 32
 
 enum { EG_ST_NISECT = 0, EG_ST_OVERFLOW = 1, EG_ST_BADCOLOR = 2, EG_ST_MAXTILE = 3, EG_ST_REDO = 4, EG_ST_WORDS = 8 };
@@ -61,7 +61,11 @@ enum { EG_GT_NONE = 0, EG_GT_F32 = 1, EG_GT_U8 = 2 };
  * pixel came near gsplat's transmittance stop threshold -- when none does, the blend result cannot depend on
  * the order.  flatten_ids is then unordered inside such tiles (cmask stays aligned with it).
  * status[EG_ST_REDO] counts the tiles that had to be redone. */
-enum { EG_FLAG_LAZY_SORT = 1 };
+enum { EG_FLAG_LAZY_SORT = 1, EG_FLAG_COMPACT_KEYS = 2 };
+/* EG_FLAG_COMPACT_KEYS: keys is a compact [isect_capacity] array segmented by tile_offsets instead of T
+ * fixed-capacity buckets (for views where a few tiles hold most intersections and T * tile_capacity keys
+ * would not fit): eg_project_fwd then only counts, eg_bin scans AND emits (second pass over the Gaussians,
+ * needs rec / gint).  tile_capacity is ignored. */
 
 typedef struct eg_config {
     int32_t n;            /* number of Gaussians                                   */
@@ -98,8 +102,8 @@ int eg_project_fwd(const eg_config *cfg, const float *means, const float *quats,
  * the largest tile count, all kept on the device (status).  Replaces gsplat cumsum + the n_isects
  * D2H sync + isect_offset_encode (keys were already emitted into the tile buckets by eg_project_fwd;
  * the sort itself is per tile inside eg_raster_fwd). */
-int eg_bin(const eg_config *cfg, const int32_t *tile_counts, int32_t *tile_offsets, int32_t *status,
-           void *stream);
+int eg_bin(const eg_config *cfg, int32_t *tile_counts, int32_t *tile_offsets, int32_t *status,
+           const float *rec, const int32_t *gint, uint64_t *keys, void *stream);
 
 /* K3 + K5 (+ a8 "whole" L1): per-tile sort, front-to-back compositing, optional fused edge-map loss.
  * Replaces cub radix sort + gsplat rasterize_to_pixels fwd; with gt != NULL also

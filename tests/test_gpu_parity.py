@@ -244,3 +244,29 @@ def test_capacity_growth_is_transparent():
     l1 = float(model.raster_step(0, gt))
     l2 = float(model.raster_step(0, gt))
     assert l1 == pytest.approx(l2, rel=1e-6)
+
+
+def test_compact_key_layout_matches(monkeypatch):
+    """EG_FLAG_COMPACT_KEYS (two-pass binning into compact per-tile segments, used when a few tiles hold most
+    intersections) gives the same bit-exact integer pipeline and the same fused-step gradients."""
+    from edgegaussians_b200 import engine
+    monkeypatch.setattr(engine, "KEY_BUCKET_BYTES_MAX", 0)
+    name, N, W, H, regime, seed, bs, view = CASES[3]
+    m, q, s, o, sc, op, vm, K = _inputs(N, W, H, regime, seed, bs, view)
+    ref = oracle.rasterization(m, q, sc, op, vm, K, W, H)
+    _, render, alpha, meta = _gpu_forward(m, q, sc, op, vm, K, W, H)
+    assert meta["_state"].cfg.flags & 2
+    np.testing.assert_array_equal(meta["flatten_ids"].cpu().numpy(), ref["flatten_ids"])
+    np.testing.assert_array_equal(meta["isect_ids"].cpu().numpy(), ref["isect_ids"])
+    np.testing.assert_allclose(alpha[0, ..., 0].cpu().numpy(), ref["alpha"], atol=2e-5)
+    gt_f = synth.make_edge_map(W, H, seed)
+    refs = oracle.edge_step(m, q, s, o, vm, K, W, H, gt_f)
+    model = EdgeGaussianSplatting(device=DEV)
+    model.set_params(m, s, q, o, viewcams=[OpenCVCamera.from_matrices(H, W, K, vm).to(DEV)])
+    import edgegaussians_b200.edge_gs as eg_mod
+    monkeypatch.setattr(eg_mod, "use_compact_keys", lambda T, tcap: True)
+    loss = model.raster_step(0, _t(gt_f))
+    assert model._ws.compact_keys
+    assert abs(float(loss) - refs["loss"]) <= 2e-6 + 1e-5 * abs(refs["loss"])
+    _check_grad(name, "v_means", model.means.grad.cpu().numpy(), refs["v_means"])
+    _check_grad(name, "v_log_scales", model.scales.grad.cpu().numpy(), refs["v_log_scales"])
