@@ -62,6 +62,38 @@ def algorithmic_bytes(N, I, P):
     return stages, sum(stages.values())
 
 
+def workload_name(args):
+    return f"{args.n} Gaussians x {args.width}x{args.height}, 1 view/iter/GPU, regime={args.regime}"
+
+
+def ncu_traffic_bytes(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full
+    summary (profiles/r1_ncu_full_summary.txt, written by scripts/summarise_profiles.py); None if absent."""
+    path = os.path.join(ROOT, "profiles", "r1_ncu_full_summary.txt")
+    if not os.path.exists(path):
+        return None
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    cur, rd, wr, best = None, None, None, None
+    for line in open(path):
+        parts = line.split()
+        if not parts:
+            continue
+        if parts[0] == "Kernel" and len(parts) > 2:
+            cur, rd, wr = line, None, None
+        elif parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and cur and kernel in cur:
+            try:
+                val = float(parts[1].replace(",", "")) * mult.get(parts[2], 1.0)
+            except (ValueError, IndexError):
+                continue
+            if parts[0].startswith("dram__bytes_read"):
+                rd = val
+            else:
+                wr = val
+            if rd is not None and wr is not None:
+                best = rd + wr
+    return best
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -157,7 +189,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_step * scale, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic (synth-v1)",
-        "config": {"workload": f"{args.n} Gaussians x {args.width}x{args.height}, 1 view/iter, regime={args.regime}"},
+        "config": {"workload": workload_name(args)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{n_sample} of {args.n} Gaussians per step at full resolution, time scaled x{scale:.2f} (linear in N)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -329,14 +361,14 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic (synth-v1: uniform Gaussians in [-1,1]^3, Fibonacci-sphere cameras, random-segment edge maps)",
-            "config": {"workload": f"{N} Gaussians x {W}x{H}, 1 view/iter/GPU, regime={args.regime}, {V} views cycled per GPU",
+            "config": {"workload": workload_name(args), "views_cycled_per_gpu": V,
                        "n_isects": I_mean, "isect_per_gaussian": I_mean / N, "overflow": overflow,
                        "l2": "flushed between timed iterations (256 MiB fill)" if flush_buf is not None else "not flushed",
                        "tile_sort": "lazy (only tiles near the transmittance stop threshold)" if model._use_lazy() else "every tile",
                        "execution": "CUDA graph replay per iteration (1 memset + 5 kernels)" + ((", + NCCL all-reduce of the 11N fp32 gradient buffer " + ("captured in the graph" if step.allreduce_in_graph else "issued after the replay")) if world > 1 else ""),
                        "parallelism": f"view-sharded dp{world}" if world > 1 else "single GPU"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": ncu_traffic_bytes(dom + "_kernel"), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": stages[dom], "kernel_ms": kern_ms[dom]},
             "roofline_step": {"algorithmic_bytes": A, "achieved": A / (ms_per_step * 1e-3) / 1e9,
                               "frac": A / (ms_per_step * 1e-3) / 1e9 / peak, "formula": "228 N + 92 I + 20 P"},

@@ -270,3 +270,27 @@ def test_compact_key_layout_matches(monkeypatch):
     assert abs(float(loss) - refs["loss"]) <= 2e-6 + 1e-5 * abs(refs["loss"])
     _check_grad(name, "v_means", model.means.grad.cpu().numpy(), refs["v_means"])
     _check_grad(name, "v_log_scales", model.scales.grad.cpu().numpy(), refs["v_log_scales"])
+
+
+def test_real_abc_camera_and_edge_map(golden_dir):
+    """Shipped ABC-NEF scan 00004926 (fixtures made by the reference's own EMAP parser): real camera, real
+    DexiNed edge map (uint8, /255 fused), 800x800 -- fused step against the oracle."""
+    cams = np.load(os.path.join(golden_dir, "cameras_abc.npz"))
+    edge = np.load(os.path.join(golden_dir, "edge_abc_view0.npz"))["image_u8"]
+    W, H = (int(v) for v in cams["width_height"])
+    N = 30000
+    m, q, s, o = synth.make_gaussians(N, "trained", 9, base_scale=0.003)
+    m = (0.5 * m).astype(np.float32)                      # ABC objects live in [-0.5, 0.5]^3
+    vm, K = cams["viewmats"][0], cams["Ks"][0]
+    gt_f = edge.astype(np.float32) / np.float32(255.0)
+    ref = oracle.edge_step(m, q, s, o, vm, K, W, H, gt_f)
+    assert ref["state"]["n_isects"] > N                   # the object is in view
+    model = EdgeGaussianSplatting(device=DEV)
+    model.set_params(m, s, q, o, viewcams=[OpenCVCamera.from_matrices(H, W, K, vm).to(DEV)])
+    loss = model.raster_step(0, _t(edge))
+    assert abs(float(loss) - ref["loss"]) <= 2e-6 + 1e-5 * abs(ref["loss"])
+    floor = 1e-6 * np.abs(ref["v_means"]).max()
+    _check_grad("abc-real", "v_means", model.means.grad.cpu().numpy(), ref["v_means"])
+    _check_grad("abc-real", "v_quats", model.quats.grad.cpu().numpy(), ref["v_quats"], floor)
+    _check_grad("abc-real", "v_log_scales", model.scales.grad.cpu().numpy(), ref["v_log_scales"])
+    _check_grad("abc-real", "v_logit_opacities", model.opacities.grad.cpu().numpy()[:, 0], ref["v_logit_opacities"])
