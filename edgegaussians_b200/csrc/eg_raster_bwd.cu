@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
     __shared__ float s_w[EG_TILE * EG_TILE];           // seed * T_final per pixel (0 outside the image)
     __shared__ __align__(16) float4 sA[RB_THREADS];    // mean2d.x, mean2d.y, opacity, gaussian id
     __shared__ __align__(16) float4 sB[RB_THREADS];    // conic a, b, c, -
+    __shared__ __align__(16) float4 sC[RB_THREADS];    // folded conic fa, fb, fc, log2(opacity)  (eg_fold)
     __shared__ __align__(16) uint32_t s_cm[RB_THREADS * 8];  // contribution masks of the batch
     __shared__ int s_off[RB_THREADS + 1];              // exclusive prefix of the mask popcounts
     __shared__ unsigned char s_nz[RB_THREADS];         // which of the 8 mask words are non-zero
@@ -92,6 +93,8 @@ __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
             const float4 r0 = __ldg(rec + 2 * gid), r1 = __ldg(rec + 2 * gid + 1);
             sA[tid] = make_float4(r0.x, r0.y, r0.z, __int_as_float(gid));
             sB[tid] = r1;
+            const EgFold f0 = eg_fold(r1.x, r1.y, r1.z, r0.z);
+            sC[tid] = make_float4(f0.fa, f0.fb, f0.fc, f0.lo);
             reinterpret_cast<uint4 *>(s_cm)[2 * tid] = c0;
             reinterpret_cast<uint4 *>(s_cm)[2 * tid + 1] = c1;
             cnt = __popc(c0.x) + __popc(c0.y) + __popc(c0.z) + __popc(c0.w) + __popc(c1.x) + __popc(c1.y) +
@@ -148,10 +151,8 @@ __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
             }
             for (; skip > 0; --skip) mask &= mask - 1;
         }
-        float4 a = sA[g], cn = sB[g];
-        EgFold f = eg_fold(cn.x, cn.y, cn.z, a.z);
-        float bx = X0f + (float)(8 * (wv & 1)), by = Y0f + (float)(4 * (wv >> 1));
-        int ib = (4 * (wv >> 1)) * EG_TILE + 8 * (wv & 1);
+        float4 a = sA[g], cn = sB[g], f = sC[g];
+        int ib = ((wv >> 1) << 6) | ((wv & 1) << 3);  // tile-local index of the word's first pixel
         PairAcc acc;
         acc_zero(acc);
         while (remaining > 0) {
@@ -163,22 +164,20 @@ __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
                     nzleft = s_nz[g];
                     a = sA[g];
                     cn = sB[g];
-                    f = eg_fold(cn.x, cn.y, cn.z, a.z);
+                    f = sC[g];
                 }
                 wv = __ffs(nzleft) - 1;
                 nzleft &= nzleft - 1;
                 mask = s_cm[g * 8 + wv];
-                bx = X0f + (float)(8 * (wv & 1));
-                by = Y0f + (float)(4 * (wv >> 1));
-                ib = (4 * (wv >> 1)) * EG_TILE + 8 * (wv & 1);
+                ib = ((wv >> 1) << 6) | ((wv & 1) << 3);
             }
             const int l = __ffs(mask) - 1;
             mask &= mask - 1;
             --remaining;
-            const int lx = l & 7, ly = l >> 3;
-            const float w = s_w[ib + ly * EG_TILE + lx];
-            const float dx = a.x - (bx + (float)lx), dy = a.y - (by + (float)ly);
-            const float pw2 = eg_pow2arg(f.fa, f.fb, f.fc, f.lo, dx, dy);
+            const int idx = ib + ((l >> 3) << 4) + (l & 7);  // pixel (idx & 15, idx >> 4) of the tile
+            const float w = s_w[idx];
+            const float dx = a.x - (X0f + (float)(idx & 15)), dy = a.y - (Y0f + (float)(idx >> 4));
+            const float pw2 = eg_pow2arg(f.x, f.y, f.z, f.w, dx, dy);
             const float ov = eg_ex2(pw2);  // opacity * exp(-sigma), exactly as the forward computed it
             if (ov <= EG_ALPHA_MAX) {      // gsplat: no gradient through a clamped alpha
                 const float ra = __fdividef(1.0f, 1.0f - ov);
