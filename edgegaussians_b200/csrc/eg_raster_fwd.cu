@@ -280,9 +280,23 @@ __global__ void __launch_bounds__(RF_THREADS, 5) raster_fwd_kernel(
             int mask = 0;
             float hx, hy, tau;
             if (eg_extent(r0.z, r1.x, r1.y, r1.z, hx, hy, tau)) {
-                if (hx >= 1e29f) {
-                    mask = 0xff;  // degenerate conic: no culling
-                } else {
+                // bounding box of the footprint first ...
+                {
+                    const float xl = r0.x - hx, xh = r0.x + hx, yl = r0.y - hy, yh = r0.y + hy;
+                    int cx = 0, cy = 0;
+                    if (xh >= X0 + 0.5f && xl <= X0 + 7.5f) cx |= 1;
+                    if (xh >= X0 + 8.5f && xl <= X0 + 15.5f) cx |= 2;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+                        if (yh >= Y0 + 4.0f * r + 0.5f && yl <= Y0 + 4.0f * r + 3.5f) cy |= 1 << r;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+                        if (cy & (1 << r)) mask |= cx << (2 * r);
+                }
+                // ... refined only where the box is likely loose (it covers most of the tile: elongated or
+                // large Gaussians; small footprints gain nothing from the 16-row test)
+                if (hx < 1e29f && __popc(mask) >= 6) {
+                    mask = 0;
                     // exact footprint per pixel row: sigma(dx, dy) <= tau  <=>  |dx - c| <= hw with
                     // c = -B dy / A, hw = sqrt(2 A tau - det dy^2) / A  (conservative margins); a sub-tile is
                     // walked iff one of its four rows has a span that reaches its eight columns
