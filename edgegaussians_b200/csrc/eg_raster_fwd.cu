@@ -280,40 +280,16 @@ __global__ void __launch_bounds__(RF_THREADS, 5) raster_fwd_kernel(
             int mask = 0;
             float hx, hy, tau;
             if (eg_extent(r0.z, r1.x, r1.y, r1.z, hx, hy, tau)) {
-                // bounding box of the footprint first ...
-                {
-                    const float xl = r0.x - hx, xh = r0.x + hx, yl = r0.y - hy, yh = r0.y + hy;
-                    int cx = 0, cy = 0;
-                    if (xh >= X0 + 0.5f && xl <= X0 + 7.5f) cx |= 1;
-                    if (xh >= X0 + 8.5f && xl <= X0 + 15.5f) cx |= 2;
+                const float xl = r0.x - hx, xh = r0.x + hx, yl = r0.y - hy, yh = r0.y + hy;
+                int cx = 0, cy = 0;
+                if (xh >= X0 + 0.5f && xl <= X0 + 7.5f) cx |= 1;
+                if (xh >= X0 + 8.5f && xl <= X0 + 15.5f) cx |= 2;
 #pragma unroll
-                    for (int r = 0; r < 4; ++r)
-                        if (yh >= Y0 + 4.0f * r + 0.5f && yl <= Y0 + 4.0f * r + 3.5f) cy |= 1 << r;
+                for (int r = 0; r < 4; ++r)
+                    if (yh >= Y0 + 4.0f * r + 0.5f && yl <= Y0 + 4.0f * r + 3.5f) cy |= 1 << r;
 #pragma unroll
-                    for (int r = 0; r < 4; ++r)
-                        if (cy & (1 << r)) mask |= cx << (2 * r);
-                }
-                // ... refined only where the box is likely loose (it covers most of the tile: elongated or
-                // large Gaussians; small footprints gain nothing from the 16-row test)
-                if (hx < 1e29f && __popc(mask) >= 6) {
-                    mask = 0;
-                    // exact footprint per pixel row: sigma(dx, dy) <= tau  <=>  |dx - c| <= hw with
-                    // c = -B dy / A, hw = sqrt(2 A tau - det dy^2) / A  (conservative margins); a sub-tile is
-                    // walked iff one of its four rows has a span that reaches its eight columns
-                    const float inv_a = 1.0f / r1.x, det = r1.x * r1.z - r1.y * r1.y, tta = 2.0f * tau * r1.x;
-                    const float bia = r1.y * inv_a;
-#pragma unroll
-                    for (int y = 0; y < EG_TILE; ++y) {
-                        const float dy = r0.y - (Y0 + (float)y + 0.5f);
-                        const float D = fmaf(-det * dy, dy, tta);
-                        const float hw = sqrtf(fmaxf(D, 0.0f)) * inv_a * 1.0001f + 2e-3f;
-                        const float c = fmaf(bia, dy, r0.x);
-                        int cx = 0;
-                        if (c + hw >= X0 + 0.5f && c - hw <= X0 + 7.5f) cx |= 1;
-                        if (c + hw >= X0 + 8.5f && c - hw <= X0 + 15.5f) cx |= 2;
-                        if (D >= 0.0f) mask |= cx << (2 * (y >> 2));
-                    }
-                }
+                for (int r = 0; r < 4; ++r)
+                    if (cy & (1 << r)) mask |= cx << (2 * r);
             }
             const EgFold f = eg_fold(r1.x, r1.y, r1.z, r0.z);
             sAB[2 * tid] = make_float4(r0.x, r0.y, f.lo, __int_as_float(mask));
