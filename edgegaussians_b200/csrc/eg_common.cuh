@@ -51,6 +51,12 @@ __device__ __forceinline__ float eg_ex2(float x) {
     return y;
 }
 
+__device__ __forceinline__ float eg_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __device__ __forceinline__ void eg_red_add_v4(float *addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
                  : "memory");

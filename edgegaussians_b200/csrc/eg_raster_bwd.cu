@@ -35,7 +35,7 @@ __device__ __forceinline__ void acc_zero(PairAcc &a) { a.gx = a.gy = a.ax = a.ay
 __device__ __forceinline__ void acc_flush(const PairAcc &a, float *__restrict__ grad2d, int gid, float opac) {
     float *dst = grad2d + 8ll * gid;
     eg_red_add_v4(dst, a.gx, a.gy, a.ax, a.ay);
-    eg_red_add_v4(dst + 4, a.ca, a.cb, a.cc, __fdividef(-a.gs, opac));
+    eg_red_add_v4(dst + 4, a.ca, a.cb, a.cc, -a.gs * eg_rcp(opac));
 }
 
 __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
@@ -44,7 +44,8 @@ __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
     const float *__restrict__ v_render, int vr_ch, const float *__restrict__ v_alpha,
     const float *__restrict__ wpix, float seed_scale, float *__restrict__ grad2d,
     const int32_t *__restrict__ status) {
-    __shared__ float s_w[EG_TILE * EG_TILE];           // seed * T_final per pixel (0 outside the image)
+    __shared__ __align__(16) float4 s_px[EG_TILE * EG_TILE];  // per pixel: seed * T_final (0 outside the image),
+                                                              // pixel centre x, y, -
     __shared__ __align__(16) float4 sA[RB_THREADS];    // mean2d.x, mean2d.y, opacity, gaussian id
     __shared__ __align__(16) float4 sB[RB_THREADS];    // conic a, b, c, -
     __shared__ __align__(16) float4 sC[RB_THREADS];    // folded conic fa, fb, fc, log2(opacity)  (eg_fold)
@@ -78,33 +79,26 @@ __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
                 w = gsum * (1.0f - __ldg(alpha + pix));
             }
         }
-        s_w[tid] = w;
+        s_px[tid] = make_float4(w, (float)pxi + 0.5f, (float)pyi + 0.5f, 0.0f);
     }
-    const float X0f = (float)X0 + 0.5f, Y0f = (float)Y0 + 0.5f;  // centre of pixel (0,0) of the tile
 
     for (int b0 = 0; b0 < L; b0 += RB_THREADS) {
         __syncthreads();  // pixel seeds visible / previous batch fully consumed
         // ---- A. one Gaussian per thread: record + contribution mask; block scan of the pair counts ----
+        // Gaussians that composited nowhere in the tile are dropped here: the staged arrays are DENSE in the
+        // Gaussians that have pairs (one packed scan gives both the pair offset and the dense rank).
         const int k = b0 + tid;
-        int cnt = 0;
+        int cnt = 0, gid = 0;
+        uint4 c0 = make_uint4(0u, 0u, 0u, 0u), c1 = c0;
         if (k < L) {
-            const int gid = __ldg(flatten_ids + start + k);
-            const uint4 c0 = __ldg(cmask + 2 * (size_t)(start + k)), c1 = __ldg(cmask + 2 * (size_t)(start + k) + 1);
-            const float4 r0 = __ldg(rec + 2 * gid), r1 = __ldg(rec + 2 * gid + 1);
-            sA[tid] = make_float4(r0.x, r0.y, r0.z, __int_as_float(gid));
-            sB[tid] = r1;
-            const EgFold f0 = eg_fold(r1.x, r1.y, r1.z, r0.z);
-            sC[tid] = make_float4(f0.fa, f0.fb, f0.fc, f0.lo);
-            reinterpret_cast<uint4 *>(s_cm)[2 * tid] = c0;
-            reinterpret_cast<uint4 *>(s_cm)[2 * tid + 1] = c1;
+            gid = __ldg(flatten_ids + start + k);
+            c0 = __ldg(cmask + 2 * (size_t)(start + k));
+            c1 = __ldg(cmask + 2 * (size_t)(start + k) + 1);
             cnt = __popc(c0.x) + __popc(c0.y) + __popc(c0.z) + __popc(c0.w) + __popc(c1.x) + __popc(c1.y) +
                   __popc(c1.z) + __popc(c1.w);
-            s_nz[tid] = (unsigned char)((c0.x != 0) | ((c0.y != 0) << 1) | ((c0.z != 0) << 2) | ((c0.w != 0) << 3) |
-                                        ((c1.x != 0) << 4) | ((c1.y != 0) << 5) | ((c1.z != 0) << 6) | ((c1.w != 0) << 7));
-        } else {
-            s_nz[tid] = 0;
         }
-        int incl = cnt;
+        const int packed = cnt | ((cnt > 0) << 20);  // pairs (<= 2^16 per batch) | non-empty flag
+        int incl = packed;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const int v = __shfl_up_sync(0xffffffffu, incl, d);
@@ -112,15 +106,29 @@ __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
         }
         if (lane == 31) s_wsum[warp] = incl;
         __syncthreads();
-        int wbase = 0, n_pairs = 0;
+        int wbase = 0, total = 0;
 #pragma unroll
         for (int w = 0; w < RB_THREADS / 32; ++w) {
             const int v = s_wsum[w];
             if (w < warp) wbase += v;
-            n_pairs += v;
+            total += v;
         }
-        s_off[tid] = wbase + incl - cnt;
-        if (tid == 0) s_off[RB_THREADS] = n_pairs;
+        const int n_pairs = total & 0xfffff, n_live = total >> 20;
+        const int excl = wbase + incl - packed;
+        if (cnt > 0) {
+            const int d = excl >> 20;  // dense index of this Gaussian
+            const float4 r0 = __ldg(rec + 2 * gid), r1 = __ldg(rec + 2 * gid + 1);
+            sA[d] = make_float4(r0.x, r0.y, r0.z, __int_as_float(gid));
+            sB[d] = r1;
+            const EgFold f0 = eg_fold(r1.x, r1.y, r1.z, r0.z);
+            sC[d] = make_float4(f0.fa, f0.fb, f0.fc, f0.lo);
+            reinterpret_cast<uint4 *>(s_cm)[2 * d] = c0;
+            reinterpret_cast<uint4 *>(s_cm)[2 * d + 1] = c1;
+            s_nz[d] = (unsigned char)((c0.x != 0) | ((c0.y != 0) << 1) | ((c0.z != 0) << 2) | ((c0.w != 0) << 3) |
+                                      ((c1.x != 0) << 4) | ((c1.y != 0) << 5) | ((c1.z != 0) << 6) | ((c1.w != 0) << 7));
+            s_off[d] = excl & 0xfffff;
+        }
+        if (tid == 0) s_off[n_live] = n_pairs;
         __syncthreads();
         if (n_pairs == 0) continue;  // uniform over the CTA
 
@@ -130,7 +138,7 @@ __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
         int remaining = min(n_pairs, c0i + per) - c0i;
         if (remaining <= 0) continue;
         // Gaussian holding pair c0i: the g with s_off[g] <= c0i < s_off[g+1]
-        int lo = 0, hi = RB_THREADS;
+        int lo = 0, hi = n_live;
         while (hi - lo > 1) {
             const int mid = (lo + hi) >> 1;
             if (s_off[mid] <= c0i) lo = mid; else hi = mid;
@@ -160,7 +168,7 @@ __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
                 if (nzleft == 0) {  // ... of the next Gaussian that has pairs
                     acc_flush(acc, grad2d, __float_as_int(a.w), a.z);
                     acc_zero(acc);
-                    do { ++g; } while (s_nz[g] == 0);
+                    ++g;  // dense: the next staged Gaussian has pairs
                     nzleft = s_nz[g];
                     a = sA[g];
                     cn = sB[g];
@@ -174,13 +182,13 @@ __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
             const int l = __ffs(mask) - 1;
             mask &= mask - 1;
             --remaining;
-            const int idx = ib + ((l >> 3) << 4) + (l & 7);  // pixel (idx & 15, idx >> 4) of the tile
-            const float w = s_w[idx];
-            const float dx = a.x - (X0f + (float)(idx & 15)), dy = a.y - (Y0f + (float)(idx >> 4));
+            const float4 pxl = s_px[ib + l + (l & 24)];  // word bit l -> pixel (l & 7, l >> 3) of the 8x4 block
+            const float w = pxl.x;
+            const float dx = a.x - pxl.y, dy = a.y - pxl.z;
             const float pw2 = eg_pow2arg(f.x, f.y, f.z, f.w, dx, dy);
             const float ov = eg_ex2(pw2);  // opacity * exp(-sigma), exactly as the forward computed it
             if (ov <= EG_ALPHA_MAX) {      // gsplat: no gradient through a clamped alpha
-                const float ra = __fdividef(1.0f, 1.0f - ov);
+                const float ra = eg_rcp(1.0f - ov);
                 const float v_sigma = -ov * w * ra;
                 const float gx = v_sigma * fmaf(cn.x, dx, cn.y * dy);
                 const float gy = v_sigma * fmaf(cn.y, dx, cn.z * dy);
