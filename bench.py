@@ -273,6 +273,15 @@ def run_b200(args):
     t_wall = time.perf_counter() - t_wall0
     per_step_ms = [a.elapsed_time(b) for a, b in zip(ev0, ev1)]
     total_ms = sum(per_step_ms)
+    # informational: the same K steps back to back WITHOUT the L2 flush (parameters / records stay L2-resident,
+    # as they would between optimizer steps); not the headline
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        one_step(i)
+    e1.record()
+    barrier()
+    hot_ms = e0.elapsed_time(e1)
     n_isects = int(ws.status[0])
     overflow = int(ws.status[1])
 
@@ -375,6 +384,7 @@ def run_b200(args):
             "kernel_ms": kern_ms,
             "e2e": {"value": world * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "api": "GraphedRasterStep.set_view(pinned host) + replay + loss readback"},
+            "value_no_l2_flush": world * args.steps / (hot_ms * 1e-3),
             "gpu_launches": 5 * args.steps,
             "clocks": clocks,
             "wall_s_timed_region": t_wall,

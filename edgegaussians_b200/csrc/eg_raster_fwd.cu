@@ -193,7 +193,7 @@ __device__ void sort_large(u64 *__restrict__ gk, int L, u64 *s, int tid) {
     }
 }
 
-template <int GT_KIND>
+template <int GT_KIND, bool WANT_LAST>
 __global__ void __launch_bounds__(RF_THREADS, 5) raster_fwd_kernel(
     const eg_config cfg, int tw, const float4 *__restrict__ rec, const int32_t *__restrict__ tile_offsets,
     u64 *__restrict__ keys, int32_t *__restrict__ flatten_ids, long long *__restrict__ isect_ids,
@@ -268,7 +268,6 @@ __global__ void __launch_bounds__(RF_THREADS, 5) raster_fwd_kernel(
     int b_done = 0;  // Gaussians [0, b_done) of the segment have their contribution masks written
     last = -start;   // relative to the segment start; gsplat initialises the absolute index to 0
     bool done = !inside;
-    bool near_stop = false;
 
     for (int b0 = 0; b0 < L; b0 += RF_THREADS) {
         // barrier doubles as "sorted ids / previous batch visible" and the all-pixels-done early exit
@@ -317,12 +316,11 @@ __global__ void __launch_bounds__(RF_THREADS, 5) raster_fwd_kernel(
                 const bool valid = !done && pw2 <= a.z && al >= EG_ALPHA_MIN;  // sigma >= 0 and alpha >= 1/255
                 const float nT = T * (1.0f - al);
                 const bool stop = valid && nT <= t_stop;
-                near_stop = near_stop || stop;
                 const bool take = valid && !stop;
                 done = done || stop;
                 out = take ? fmaf(al, T, out) : out;
                 T = take ? nT : T;
-                last = take ? (b0 + t) : last;
+                if (WANT_LAST) last = take ? (b0 + t) : last;
                 const unsigned bal = __ballot_sync(0xffffffffu, take);
                 myword = (lane == j) ? bal : myword;
             }
@@ -344,7 +342,8 @@ __global__ void __launch_bounds__(RF_THREADS, 5) raster_fwd_kernel(
             cmask[2 * (size_t)(start + k)] = make_uint4(0u, 0u, 0u, 0u);
             cmask[2 * (size_t)(start + k) + 1] = make_uint4(0u, 0u, 0u, 0u);
         }
-    if (sorted || !__syncthreads_or(near_stop)) break;
+    // `done` of an in-image pixel can only have been set by the stop rule
+    if (sorted || !__syncthreads_or(done && inside)) break;
     if (tid == 0) atomicAdd(status + EG_ST_REDO, 1);  // lets the host switch lazy sorting off when it stops paying
     }  // pass
 
@@ -354,7 +353,7 @@ __global__ void __launch_bounds__(RF_THREADS, 5) raster_fwd_kernel(
         const long long pix = (long long)pyi * cfg.width + pxi;
         if (alpha_out) alpha_out[pix] = 1.0f - T;
         if (render0) render0[pix] = out;
-        if (last_ids) last_ids[pix] = start + last;
+        if (WANT_LAST && last_ids) last_ids[pix] = start + last;
         if (GT_KIND != EG_GT_NONE) {
             float g;
             if (GT_KIND == EG_GT_F32) g = __ldg(reinterpret_cast<const float *>(gt) + pix);
@@ -400,10 +399,16 @@ extern "C" int eg_raster_fwd(const eg_config *cfg, const float *rec, const int32
     eg_tile_grid(cfg->width, cfg->height, cfg->tile_size, &tw, &th);
     cudaStream_t s = (cudaStream_t)stream;
     const int grid = tw * th;
-#define EG_LAUNCH(KIND)                                                                                          \
-    raster_fwd_kernel<KIND><<<grid, RF_THREADS, 0, s>>>(*cfg, tw, (const float4 *)rec, tile_offsets, (u64 *)keys, \
-                                                        flatten_ids, (long long *)isect_ids, render0, alpha,      \
-                                                        last_ids, (uint4 *)cmask, gt, loss_sum, wpix, status)
+#define EG_LAUNCH2(KIND, WL)                                                                                     \
+    raster_fwd_kernel<KIND, WL><<<grid, RF_THREADS, 0, s>>>(*cfg, tw, (const float4 *)rec, tile_offsets,         \
+                                                            (u64 *)keys, flatten_ids, (long long *)isect_ids,    \
+                                                            render0, alpha, last_ids, (uint4 *)cmask, gt,        \
+                                                            loss_sum, wpix, status)
+#define EG_LAUNCH(KIND)                       \
+    do {                                      \
+        if (last_ids != nullptr) EG_LAUNCH2(KIND, true); \
+        else EG_LAUNCH2(KIND, false);         \
+    } while (0)
     switch (gt_kind) {
         case EG_GT_NONE: EG_LAUNCH(EG_GT_NONE); break;
         case EG_GT_F32: EG_LAUNCH(EG_GT_F32); break;
@@ -411,5 +416,6 @@ extern "C" int eg_raster_fwd(const eg_config *cfg, const float *rec, const int32
         default: eg_set_error("eg_raster_fwd: bad gt_kind %d", gt_kind); return 1;
     }
 #undef EG_LAUNCH
+#undef EG_LAUNCH2
     return eg_check_launch("eg_raster_fwd");
 }
