@@ -45,7 +45,9 @@ def parse_args():
     ap.add_argument("--views", type=int, default=8, help="distinct synthetic views cycled per rank")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed iterations")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-lazy-sort", action="store_true", help="always sort every tile (gsplat order) in the fused step")
+    ap.add_argument("--no-lazy-sort", action="store_true", help="always sort every tile (gsplat order) in the tile pipelines")
+    ap.add_argument("--pipeline", default="auto", choices=["auto", "splat", "tiles+splat", "tiles"],
+                    help="fused-step pipeline (edge_gs.enqueue_raster_step); auto = what training would run")
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
     return ap.parse_args()
 
@@ -59,7 +61,12 @@ def algorithmic_bytes(N, I, P):
         "raster_bwd": 28 * I + 12 * P + 32 * N,
         "project_bwd": 120 * N,
     }
-    return stages, sum(stages.values())
+    total = sum(stages.values())
+    # fused kernels carry the algorithmic bytes of the stages they replace
+    stages["splat_bwd"] = stages["raster_bwd"] + stages["project_bwd"]
+    stages["splat_fwd"] = stages["bin"] + stages["raster_fwd"]
+    stages["memset"] = 0
+    return stages, total
 
 
 def workload_name(args):
@@ -226,6 +233,7 @@ def run_b200(args):
     cams = [OpenCVCamera.from_matrices(H, W, Ks[v], vms[v]).to(dev) for v in my_views]
     model.set_params(m, s, q, o, viewcams=cams)
     model.lazy_sort = False if args.no_lazy_sort else "auto"
+    model.pipeline = args.pipeline
 
     step = GraphedRasterStep(model, W, H, n_slots=V, gt_dtype=torch.uint8, allreduce=world > 1)
     host_vm = [torch.from_numpy(vms[v]).pin_memory() for v in my_views]
@@ -296,8 +304,7 @@ def run_b200(args):
     overflow = int(ws.status[1])
 
     # ---------------- per-kernel breakdown (events between stages, eager launches) ----------------
-    names = ["memset", "project_fwd", "bin", "raster_fwd", "raster_bwd", "project_bwd"]
-    acc = {k: 0.0 for k in names}
+    names, acc = None, {}
     isect_sum = 0
     reps = min(args.steps, 16)
     for i in range(reps):
@@ -310,6 +317,9 @@ def run_b200(args):
         flush()  # also lets the host run ahead of the device so events see no launch gaps
         step._enqueue(i % V, stage_cb=cb)
         torch.cuda.synchronize()
+        if names is None:
+            names = [k for k in evs if k != "begin"]   # stage order as enqueued (dicts keep insertion order)
+            acc = {k: 0.0 for k in names}
         prev = "begin"
         for k in names:
             acc[k] += evs[prev].elapsed_time(evs[k])
@@ -373,7 +383,8 @@ def run_b200(args):
         stages, A = algorithmic_bytes(N, I_mean, P)
         ms_per_step = total_ms / args.steps
         value = world * args.steps / (total_ms * 1e-3)
-        dom = max(("project_fwd", "bin", "raster_fwd", "raster_bwd", "project_bwd"), key=lambda k: kern_ms[k])
+        kernels = [k for k in names if k != "memset"]
+        dom = max(kernels, key=lambda k: kern_ms[k])
         achieved = stages[dom] / (kern_ms[dom] * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -382,8 +393,12 @@ def run_b200(args):
             "config": {"workload": workload_name(args), "views_cycled_per_gpu": V,
                        "n_isects": I_mean, "isect_per_gaussian": I_mean / N, "overflow": overflow,
                        "l2": "flushed between timed iterations (256 MiB fill)" if flush_buf is not None else "not flushed",
-                       "tile_sort": "lazy (only tiles near the transmittance stop threshold)" if model._use_lazy() else "every tile",
-                       "execution": "CUDA graph replay per iteration (1 memset + 5 kernels)" + ((", + NCCL all-reduce of the 11N fp32 gradient buffer " + ("captured in the graph" if step.allreduce_in_graph else "issued after the replay")) if world > 1 else ""),
+                       "pipeline": ws.pipeline + {"splat": " (Gaussian-major forward + backward; tiles near the transmittance stop threshold redone sorted)",
+                                                  "tiles+splat": " (tile binning + per-tile sort/compositing, Gaussian-major backward)",
+                                                  "tiles": " (tile binning + per-tile sort/compositing, tile-major backward)"}[ws.pipeline],
+                       "stopped_tiles": int(ws.status[5]),
+                       "tile_sort": ("n/a" if ws.pipeline == "splat" else "lazy (only tiles near the transmittance stop threshold)" if model._use_lazy() else "every tile"),
+                       "execution": f"CUDA graph replay per iteration (1 memset + {len(kernels)} kernels: {', '.join(kernels)})" + ((", + NCCL all-reduce of the 11N fp32 gradient buffer " + ("captured in the graph" if step.allreduce_in_graph else "issued after the replay")) if world > 1 else ""),
                        "parallelism": f"view-sharded dp{world}" if world > 1 else "single GPU"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic_bytes(dom + "_kernel"), "peak_source": peak_src,
@@ -394,7 +409,7 @@ def run_b200(args):
             "e2e": {"value": world * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "api": "GraphedRasterStep.set_view(pinned host) + replay + loss readback"},
             "value_no_l2_flush": world * args.steps / (hot_ms * 1e-3),
-            "gpu_launches": 5 * args.steps,
+            "gpu_launches": len(kernels) * args.steps,
             "clocks": clocks,
             "wall_s_timed_region": t_wall,
         }

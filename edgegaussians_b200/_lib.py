@@ -12,14 +12,15 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_C", "libedgegs.so")
 
-EG_ST_NISECT, EG_ST_OVERFLOW, EG_ST_BADCOLOR, EG_ST_MAXTILE, EG_ST_REDO, EG_ST_WORDS = 0, 1, 2, 3, 4, 8
+EG_ST_NISECT, EG_ST_OVERFLOW, EG_ST_BADCOLOR, EG_ST_MAXTILE, EG_ST_REDO, EG_ST_STOPPED, EG_ST_WORDS = 0, 1, 2, 3, 4, 5, 8
 EG_GT_NONE, EG_GT_F32, EG_GT_U8 = 0, 1, 2
 EG_CNT_STRIDE = 32
 EG_FLAG_LAZY_SORT = 1
 EG_FLAG_COMPACT_KEYS = 2
+EG_FLAG_NO_EMIT = 4
 
 EXPORTS = ["eg_last_error", "eg_abi_version", "eg_tile_grid", "eg_project_fwd", "eg_bin", "eg_raster_fwd",
-           "eg_raster_bwd", "eg_project_bwd", "eg_reg_fwd_bwd", "eg_knn_workspace_bytes", "eg_knn", "eg_adam_step"]
+           "eg_raster_bwd", "eg_project_bwd", "eg_splat_bwd", "eg_make_seed", "eg_splat_fwd", "eg_splat_resolve", "eg_emit_flagged", "eg_reg_fwd_bwd", "eg_knn_workspace_bytes", "eg_knn", "eg_adam_step"]
 
 
 class EgConfig(Structure):
@@ -53,9 +54,14 @@ def load(build_if_missing: bool = True):
     lib.eg_tile_grid.argtypes = [c_int, c_int, c_int, POINTER(c_int), POINTER(c_int)]
     lib.eg_project_fwd.argtypes = [cfgp] + [P] * 13
     lib.eg_bin.argtypes = [cfgp] + [P] * 7
-    lib.eg_raster_fwd.argtypes = [cfgp] + [P] * 10 + [c_int, P, P, P, P]
+    lib.eg_raster_fwd.argtypes = [cfgp] + [P] * 10 + [c_int] + [P] * 8
     lib.eg_raster_bwd.argtypes = [cfgp] + [P] * 6 + [c_int, P, P, c_float, P, P, P]
     lib.eg_project_bwd.argtypes = [cfgp] + [P] * 9 + [c_int] + [P] * 7
+    lib.eg_splat_bwd.argtypes = [cfgp] + [P] * 9 + [c_float] + [P] * 11
+    lib.eg_splat_fwd.argtypes = [cfgp] + [P] * 5
+    lib.eg_splat_resolve.argtypes = [cfgp, P, P, c_int] + [P] * 7
+    lib.eg_emit_flagged.argtypes = [cfgp] + [P] * 7
+    lib.eg_make_seed.argtypes = [c_int64, P, P, c_int, P, P, P]
     lib.eg_reg_fwd_bwd.argtypes = [c_int, P, P, P, P, c_int, c_int, c_int, c_float, c_float, P, P, P, P, P]
     lib.eg_knn_workspace_bytes.argtypes = [c_int]
     lib.eg_knn.argtypes = [c_int, P, c_int, c_int, P, P, ctypes.c_size_t, P]

@@ -87,8 +87,15 @@ __device__ __forceinline__ EgFold eg_fold(float A, float B, float C, float o) {
     f.lo = __log2f(o);
     return f;
 }
+// Horner form in dx: both roundings of the per-row terms  b1 = fb*dy  and  c0 = fc*dy*dy + lo  are explicit, so a
+// kernel that walks a pixel ROW (dy fixed) hoists them and still reproduces this value bit for bit.
+__device__ __forceinline__ float eg_pow2row_b1(float fb, float dy) { return __fmul_rn(fb, dy); }
+__device__ __forceinline__ float eg_pow2row_c0(float fc, float lo, float dy) { return __fmaf_rn(__fmul_rn(fc, dy), dy, lo); }
+__device__ __forceinline__ float eg_pow2row(float fa, float b1, float c0, float dx) {
+    return __fmaf_rn(__fmaf_rn(fa, dx, b1), dx, c0);
+}
 __device__ __forceinline__ float eg_pow2arg(float fa, float fb, float fc, float lo, float dx, float dy) {
-    return __fmaf_rn(__fmul_rn(fa, dx), dx, __fmaf_rn(__fmul_rn(fc, dy), dy, __fmaf_rn(__fmul_rn(fb, dx), dy, lo)));
+    return eg_pow2row(fa, eg_pow2row_b1(fb, dy), eg_pow2row_c0(fc, lo, dy), dx);
 }
 
 // Conservative half-extents (pixels) of the region where a Gaussian can reach alpha >= 1/255:

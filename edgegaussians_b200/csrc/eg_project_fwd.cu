@@ -141,7 +141,12 @@ __global__ void __launch_bounds__(256) project_fwd_kernel(
     // K2 emission: append (depth_bits << 32 | id) to the bucket of every tile of the rectangle
     const unsigned long long key = ((unsigned long long)__float_as_uint(r0.w) << 32) | (unsigned int)g;
     const uint32_t w = x1 - x0;
-    if (cfg.flags & EG_FLAG_COMPACT_KEYS) {  // count only; eg_bin emits after the scan
+    if (cfg.flags & EG_FLAG_NO_EMIT) {
+        // Gaussian-major forward: no tile lists at all; only the intersection count is kept (one atomic per warp)
+        const unsigned am = __activemask();
+        const int nt = __reduce_add_sync(am, ntiles);
+        if ((int)(threadIdx.x & 31) == __ffs(am) - 1 && nt > 0) atomicAdd(status + EG_ST_NISECT, nt);
+    } else if (cfg.flags & EG_FLAG_COMPACT_KEYS) {  // count only; eg_bin emits after the scan
         for (uint32_t i = y0; i < y1; ++i)
             for (uint32_t j = x0; j < x1; ++j) atomicAdd(tile_counts + (size_t)(i * tw + j) * EG_CNT_STRIDE, 1);
     } else if (ntiles > 0 && ntiles <= 12) {

@@ -199,7 +199,8 @@ __global__ void __launch_bounds__(RF_THREADS, 5) raster_fwd_kernel(
     u64 *__restrict__ keys, int32_t *__restrict__ flatten_ids, long long *__restrict__ isect_ids,
     float *__restrict__ render0, float *__restrict__ alpha_out, int32_t *__restrict__ last_ids,
     uint4 *__restrict__ cmask, const void *__restrict__ gt, double *__restrict__ loss_sum,
-    float *__restrict__ wpix, int32_t *__restrict__ status) {
+    float *__restrict__ wpix, uint32_t *__restrict__ last_depth, int32_t *__restrict__ last_gid,
+    const int32_t *__restrict__ tile_stop, const int32_t *__restrict__ tile_cnt, int32_t *__restrict__ status) {
     __shared__ __align__(16) u64 sbuf[2 * SORT_CAP];  // sort exchange buffers, then the sorted ids
     __shared__ __align__(16) float4 sAB[2 * RF_THREADS];  // per Gaussian: (mean2d.x, mean2d.y, log2 opacity,
                                                           // sub-tile mask bits) , (folded conic fa, fb, fc, -)
@@ -211,8 +212,12 @@ __global__ void __launch_bounds__(RF_THREADS, 5) raster_fwd_kernel(
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x;
     const int tile_y = tile / tw, tile_x = tile - tile_y * tw;
-    const int start = tile_offsets[tile];
-    const int L = tile_offsets[tile + 1] - start;
+    // fallback of the Gaussian-major forward (eg_splat_fwd.cu): only the tiles eg_splat_resolve flagged, whose
+    // keys eg_emit_flagged appended to fixed-capacity buckets (count in tile_cnt, no scan)
+    const bool flagged_only = tile_stop != nullptr;
+    if (flagged_only && tile_stop[tile] == 0) return;
+    const int start = flagged_only ? tile * cfg.tile_capacity : tile_offsets[tile];
+    const int L = flagged_only ? min(tile_cnt[tile], cfg.tile_capacity) : tile_offsets[tile + 1] - start;
 
     const int sub_x = tile_x * EG_TILE + 8 * (warp & 1), sub_y = tile_y * EG_TILE + 4 * (warp >> 1);
     const int pxi = sub_x + (lane & 7), pyi = sub_y + (lane >> 3);
@@ -220,15 +225,17 @@ __global__ void __launch_bounds__(RF_THREADS, 5) raster_fwd_kernel(
     const float px = (float)pxi + 0.5f, py = (float)pyi + 0.5f;
     const float X0 = (float)(tile_x * EG_TILE), Y0 = (float)(tile_y * EG_TILE);
     const bool on_chip = L <= SORT_CAP;
-    u64 *bucket = (cfg.flags & EG_FLAG_COMPACT_KEYS) ? keys + start : keys + (size_t)tile * (size_t)cfg.tile_capacity;
+    u64 *bucket = ((cfg.flags & EG_FLAG_COMPACT_KEYS) && !flagged_only) ? keys + start
+                                                                       : keys + (size_t)tile * (size_t)cfg.tile_capacity;
 
     // EG_FLAG_LAZY_SORT: composite once in bucket (arbitrary) order.  If no pixel of the tile comes near the
     // transmittance stop threshold, no prefix product in ANY order can cross it, so gsplat's result is the
     // order-free product and the sort is skipped (flatten_ids then holds the tile's ids unsorted).  Otherwise
     // the tile is redone in sorted order (pass 1), which is always exact.
-    const bool lazy = (cfg.flags & EG_FLAG_LAZY_SORT) != 0 && isect_ids == nullptr && last_ids == nullptr;
+    const bool lazy = (cfg.flags & EG_FLAG_LAZY_SORT) != 0 && isect_ids == nullptr && last_ids == nullptr && !flagged_only;
     float T = 1.0f, out = 0.0f;
     int last = -start;
+    bool done = !inside;
     for (int pass = lazy ? 0 : 1; pass < 2; ++pass) {
     const bool sorted = pass == 1;
     const float t_stop = sorted ? EG_T_MIN : EG_T_MIN * 1.0002f;
@@ -267,7 +274,7 @@ __global__ void __launch_bounds__(RF_THREADS, 5) raster_fwd_kernel(
     out = 0.0f;
     int b_done = 0;  // Gaussians [0, b_done) of the segment have their contribution masks written
     last = -start;   // relative to the segment start; gsplat initialises the absolute index to 0
-    bool done = !inside;
+    done = !inside;
 
     for (int b0 = 0; b0 < L; b0 += RF_THREADS) {
         // barrier doubles as "sorted ids / previous batch visible" and the all-pixels-done early exit
@@ -348,9 +355,22 @@ __global__ void __launch_bounds__(RF_THREADS, 5) raster_fwd_kernel(
     }  // pass
 
     // ---------------- epilogue ----------------
+    if (__syncthreads_or(done && inside) && tid == 0 && !flagged_only) atomicAdd(status + EG_ST_STOPPED, 1);
     float absd = 0.0f;
     if (inside) {
         const long long pix = (long long)pyi * cfg.width + pxi;
+        if (WANT_LAST && last_depth != nullptr) {
+            // sort key of the last Gaussian a STOPPED pixel composited (what eg_splat_bwd compares against);
+            // a pixel that never stopped composited every Gaussian that passed the alpha test
+            uint32_t ld = 0xffffffffu;
+            int lg = -1;
+            if (done) {
+                lg = on_chip ? (int)sids[last] : flatten_ids[start + last];
+                ld = __float_as_uint(__ldg(rec + 2 * lg).w);
+            }
+            last_depth[pix] = ld;
+            last_gid[pix] = lg;
+        }
         if (alpha_out) alpha_out[pix] = 1.0f - T;
         if (render0) render0[pix] = out;
         if (WANT_LAST && last_ids) last_ids[pix] = start + last;
@@ -385,13 +405,26 @@ __global__ void __launch_bounds__(RF_THREADS, 5) raster_fwd_kernel(
 extern "C" int eg_raster_fwd(const eg_config *cfg, const float *rec, const int32_t *tile_offsets, uint64_t *keys,
                              int32_t *flatten_ids, int64_t *isect_ids, float *render0, float *alpha,
                              int32_t *last_ids, uint32_t *cmask, const void *gt, int gt_kind, double *loss_sum,
-                             float *wpix, int32_t *status, void *stream) {
+                             float *wpix, uint32_t *last_depth, int32_t *last_gid, const int32_t *tile_stop,
+                             const int32_t *tile_cnt, int32_t *status, void *stream) {
     if (cfg == nullptr || cfg->tile_size != EG_TILE) {
         eg_set_error("eg_raster_fwd: tile_size must be %d", EG_TILE);
         return 1;
     }
     if (flatten_ids == nullptr) {
         eg_set_error("eg_raster_fwd: flatten_ids is required");
+        return 1;
+    }
+    if ((last_depth == nullptr) != (last_gid == nullptr)) {
+        eg_set_error("eg_raster_fwd: last_depth and last_gid go together");
+        return 1;
+    }
+    if ((tile_stop == nullptr) != (tile_cnt == nullptr)) {
+        eg_set_error("eg_raster_fwd: tile_stop and tile_cnt go together");
+        return 1;
+    }
+    if (tile_stop == nullptr && tile_offsets == nullptr) {
+        eg_set_error("eg_raster_fwd: tile_offsets is required");
         return 1;
     }
     if (gt == nullptr) gt_kind = EG_GT_NONE;
@@ -403,10 +436,11 @@ extern "C" int eg_raster_fwd(const eg_config *cfg, const float *rec, const int32
     raster_fwd_kernel<KIND, WL><<<grid, RF_THREADS, 0, s>>>(*cfg, tw, (const float4 *)rec, tile_offsets,         \
                                                             (u64 *)keys, flatten_ids, (long long *)isect_ids,    \
                                                             render0, alpha, last_ids, (uint4 *)cmask, gt,        \
-                                                            loss_sum, wpix, status)
+                                                            loss_sum, wpix, last_depth, last_gid, tile_stop,     \
+                                                            tile_cnt, status)
 #define EG_LAUNCH(KIND)                       \
     do {                                      \
-        if (last_ids != nullptr) EG_LAUNCH2(KIND, true); \
+        if (last_ids != nullptr || last_depth != nullptr) EG_LAUNCH2(KIND, true); \
         else EG_LAUNCH2(KIND, false);         \
     } while (0)
     switch (gt_kind) {

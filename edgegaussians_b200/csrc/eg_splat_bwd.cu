@@ -1,0 +1,311 @@
+// eg_splat_bwd.cu -- K6 + K7 in one kernel: Gaussian-major compositing backward (with abs-grad) fused with the
+// projection backward, the activation VJPs and update_absgrads.  No tile lists, no atomics, no 2D-gradient
+// round trip through HBM.
+//
+// Semantics: SURVEY.md Appendix A.5 + A.6 (gsplat==1.0.0 rasterize_to_pixels bwd + fully_fused_projection bwd
+// behind /root/reference/edgegaussians/models/edge_gs.py:250-268, absgrad=True edge_gs.py:266, update_absgrads
+// edge_gs.py:603-613).
+//
+// With colors == 1 (edge_gs.py:247) every render channel is 1 - prod_i (1 - alpha_i), so
+//     d out(p) / d alpha_k = T_final(p) / (1 - alpha_k)      for every k that pixel p composited,
+// a plain sum over composited (pixel, Gaussian) pairs with no ordering dependence (see eg_raster_bwd.cu).
+// Which pairs were composited is decidable from the Gaussian's side (eg_splat.cuh): tile rectangle, sigma >= 0,
+// alpha >= 1/255 -- and, for the pixels that hit gsplat's transmittance stop, "sort key of g <= key of the last
+// Gaussian the pixel composited", which the forward kernels leave in two per-pixel planes (last_depth,
+// last_gid; last_depth = 0xffffffff where the pixel never stopped).  So:
+//   phase 1  lane = Gaussian : record -> tile rectangle, folded conic, row range (eg_splat_setup);
+//   phase 2  lane = (Gaussian, row) : walk the row's span in aligned 4-pixel chunks (one LDG.128 of the
+//            per-pixel seed  w_p = seed * T_final(p)  per chunk), accumulate the row's moments
+//            S0 = sum v_sigma, S1 = sum v_sigma dx, S2 = sum v_sigma dx^2 and the two abs-sums in registers,
+//            turn them into the 8 per-Gaussian 2D gradients, segmented-reduce over the lanes of the same
+//            Gaussian (shuffles) and add into the warp's private shared-memory accumulators;
+//   phase 3  lane = Gaussian : projection VJP + exp/sigmoid VJP + abs-grad norm, gradients written with plain
+//            stores (each Gaussian has exactly one owner).
+#include "eg_project_vjp.cuh"
+#include "eg_splat.cuh"
+
+namespace {
+
+constexpr int SB_WARPS = 4;
+
+template <bool ALIGNED>
+__device__ __forceinline__ float4 ld_f4(const float *__restrict__ row, int c, int xlim) {
+    if (ALIGNED) return __ldg(reinterpret_cast<const float4 *>(row) + c);
+    float4 v;
+    const int x = 4 * c;
+    v.x = (x < xlim) ? __ldg(row + x) : 0.0f;
+    v.y = (x + 1 < xlim) ? __ldg(row + x + 1) : 0.0f;
+    v.z = (x + 2 < xlim) ? __ldg(row + x + 2) : 0.0f;
+    v.w = (x + 3 < xlim) ? __ldg(row + x + 3) : 0.0f;
+    return v;
+}
+template <bool ALIGNED>
+__device__ __forceinline__ uint4 ld_u4(const unsigned *__restrict__ row, int c, int xlim) {
+    if (ALIGNED) return __ldg(reinterpret_cast<const uint4 *>(row) + c);
+    uint4 v;
+    const int x = 4 * c;
+    v.x = (x < xlim) ? __ldg(row + x) : 0u;
+    v.y = (x + 1 < xlim) ? __ldg(row + x + 1) : 0u;
+    v.z = (x + 2 < xlim) ? __ldg(row + x + 2) : 0u;
+    v.w = (x + 3 < xlim) ? __ldg(row + x + 3) : 0u;
+    return v;
+}
+
+struct RowAcc {
+    float S0, S1, S2, ax, ay;
+};
+
+template <bool HAS_LAST>
+__device__ __forceinline__ void pair_bwd(const EgSplatG &G, const float b1, const float c0, const float Bdy,
+                                         const float Cdy, const float px, const bool in_span, const float w,
+                                         const unsigned dl, const int *__restrict__ gid_px, RowAcc &r) {
+    const float dx = G.mx - px;
+    const float p = eg_pow2row(G.fa, b1, c0, dx);  // log2(opacity * exp(-sigma)), bit-identical to the forward's
+    const float ov = eg_ex2(p);
+    // composited (sigma >= 0, alpha >= 1/255) and alpha not clamped (gsplat: no gradient through the clamp)
+    bool valid = eg_pair_valid_grad(ov, p, G.lo, in_span);
+    if (HAS_LAST) {
+        if (valid && G.depth_bits >= dl)  // rare: at or behind the pixel's last composited Gaussian
+            valid = G.depth_bits == dl && G.gid <= __ldg(gid_px);
+    }
+    const float ra = eg_rcp(1.0f - ov);
+    float vs = (ov * w) * ra;  // -v_sigma = alpha * T_final * seed / (1 - alpha); the sign is applied per row
+    vs = valid ? vs : 0.0f;
+    const float vd = vs * dx;
+    r.S0 += vs;
+    r.S1 += vd;
+    r.S2 = fmaf(vd, dx, r.S2);
+    r.ax += fabsf(vs * fmaf(G.A, dx, Bdy));
+    r.ay += fabsf(vs * fmaf(G.B, dx, Cdy));
+}
+
+template <bool HAS_LAST, bool ALIGNED>
+__device__ __forceinline__ void walk_row_bwd(const EgSplatG &G, const int y, const int W, const int tw,
+                                             const float *__restrict__ wpix, const unsigned *__restrict__ last_depth,
+                                             const int *__restrict__ last_gid, const int *__restrict__ tile_stop,
+                                             float (&v)[8]) {
+    const float dy = G.my - ((float)y + 0.5f);
+    const float b1 = eg_pow2row_b1(G.fb, dy), c0 = eg_pow2row_c0(G.fc, G.lo, dy);
+    int xa, xb;
+    RowAcc r = {0.f, 0.f, 0.f, 0.f, 0.f};
+    const float Bdy = G.B * dy, Cdy = G.C * dy;
+    if (eg_row_span(G, b1, c0, xa, xb)) {
+        const size_t off = (size_t)y * (size_t)W;
+        const float *wrow = wpix + off;
+        const unsigned *drow = HAS_LAST ? last_depth + off : nullptr;
+        const int *grow = HAS_LAST ? last_gid + off : nullptr;
+        const int *srow = (HAS_LAST && tile_stop != nullptr) ? tile_stop + (y >> 4) * tw : nullptr;
+        int c = xa >> 2;
+        const int cend = xb >> 2;
+        float4 w4 = ld_f4<ALIGNED>(wrow, c, W);
+        for (; c <= cend; ++c) {
+            float4 wn = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < cend) wn = ld_f4<ALIGNED>(wrow, c + 1, W);  // next chunk in flight while this one is evaluated
+            const int x = 4 * c;
+            uint4 d4 = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+            if (HAS_LAST) {  // the planes are only defined in tiles where some pixel stopped (a chunk never straddles tiles)
+                if (srow == nullptr || __ldg(srow + (x >> 4)) != 0) d4 = ld_u4<ALIGNED>(drow, c, W);
+            }
+            const float px = (float)x + 0.5f;  // pixel centres x + 0.5 .. x + 3.5 are exact in fp32
+            // ALIGNED: an aligned chunk that overlaps the span lies inside the tile rectangle (see eg_splat_fwd.cu)
+            pair_bwd<HAS_LAST>(G, b1, c0, Bdy, Cdy, px, ALIGNED || (x >= xa && x <= xb), w4.x, d4.x, grow + x, r);
+            pair_bwd<HAS_LAST>(G, b1, c0, Bdy, Cdy, px + 1.0f, ALIGNED || (x + 1 >= xa && x + 1 <= xb), w4.y, d4.y,
+                               grow + x + 1, r);
+            pair_bwd<HAS_LAST>(G, b1, c0, Bdy, Cdy, px + 2.0f, ALIGNED || (x + 2 >= xa && x + 2 <= xb), w4.z, d4.z,
+                               grow + x + 2, r);
+            pair_bwd<HAS_LAST>(G, b1, c0, Bdy, Cdy, px + 3.0f, ALIGNED || (x + 3 >= xa && x + 3 <= xb), w4.w, d4.w,
+                               grow + x + 3, r);
+            w4 = wn;
+        }
+    }
+    // row moments (of -v_sigma) -> (v_mean2d.x, .y, absgrad.x, .y, v_conic.a, .b, .c, sum v_sigma)
+    v[0] = -fmaf(G.A, r.S1, Bdy * r.S0);
+    v[1] = -fmaf(G.B, r.S1, Cdy * r.S0);
+    v[2] = r.ax;
+    v[3] = r.ay;
+    v[4] = -0.5f * r.S2;
+    v[5] = -dy * r.S1;
+    v[6] = -0.5f * dy * dy * r.S0;
+    v[7] = -r.S0;
+}
+
+template <bool RAW, bool ALIGNED>
+__global__ void __launch_bounds__(SB_WARPS * 32) splat_bwd_kernel(
+    const eg_config cfg, const int tw, const int th, const float *__restrict__ means, const float *__restrict__ quats,
+    const float *__restrict__ scales, const float *__restrict__ opacities, const float *__restrict__ viewmat,
+    const float *__restrict__ Kmat, const float4 *__restrict__ rec, const int2 *__restrict__ gint,
+    const float *__restrict__ wpix, const float seed_scale, const unsigned *__restrict__ last_depth,
+    const int *__restrict__ last_gid, const int *__restrict__ tile_stop, const int32_t *__restrict__ status,
+    float4 *__restrict__ grad2d_out,
+    float *__restrict__ v_means, float *__restrict__ v_quats, float *__restrict__ v_scales,
+    float *__restrict__ v_opacities, float *__restrict__ absgrad_accum) {
+    __shared__ EgSplatG s_g[SB_WARPS][32];
+    __shared__ int s_end[SB_WARPS][32];
+    __shared__ __align__(16) float s_acc[SB_WARPS][32][8];
+
+    if (status[EG_ST_OVERFLOW]) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = (blockIdx.x * SB_WARPS + warp) * 32 + lane;
+    const bool live = g < cfg.n;
+    const bool use_last = last_depth != nullptr && last_gid != nullptr && status[EG_ST_STOPPED] != 0;
+
+    // ---------------- phase 1: lane = Gaussian ----------------
+    EgSplatG G;
+    float4 r1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float opac_eff = 0.0f;
+    int nrows = 0, radius = 0;
+    if (live) {
+        const int2 gi = __ldg(gint + g);
+        radius = gi.x;
+        const float4 r0 = __ldg(rec + 2 * g);
+        r1 = __ldg(rec + 2 * g + 1);
+        opac_eff = r0.z;
+        nrows = eg_splat_setup(cfg, tw, th, g, r0, r1, radius, G);
+    } else {
+        G.nrows = 0;
+    }
+    int incl = nrows;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    G.start = incl - nrows;
+    s_g[warp][lane] = G;
+    s_end[warp][lane] = incl;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s_acc[warp][lane][k] = 0.0f;
+    const int R = __shfl_sync(0xffffffffu, incl, 31);
+    __syncwarp();
+
+    // ---------------- phase 2: lane = (Gaussian, row) ----------------
+    for (int base = 0; base < R; base += 32) {
+        const int item = base + lane;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        int owner = 32;
+        if (item < R) {
+            owner = eg_find_owner(s_end[warp], item);
+            const EgSplatG Go = s_g[warp][owner];
+            const int y = Go.ylo + (item - Go.start);
+            if (use_last) walk_row_bwd<true, ALIGNED>(Go, y, cfg.width, tw, wpix, last_depth, last_gid, tile_stop, v);
+            else walk_row_bwd<false, ALIGNED>(Go, y, cfg.width, tw, wpix, nullptr, nullptr, nullptr, v);
+        }
+        // segmented sum over the (contiguous) lanes that share an owner
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o2 = __shfl_down_sync(0xffffffffu, owner, d);
+            const bool add = (lane + d < 32) && (o2 == owner);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float t = __shfl_down_sync(0xffffffffu, v[k], d);
+                v[k] += add ? t : 0.0f;
+            }
+        }
+        const int prev = __shfl_up_sync(0xffffffffu, owner, 1);
+        if (item < R && (lane == 0 || prev != owner)) {  // one head lane per Gaussian of this batch
+            float4 *dst = reinterpret_cast<float4 *>(&s_acc[warp][owner][0]);
+            float4 a0 = dst[0], a1 = dst[1];
+            a0.x += v[0]; a0.y += v[1]; a0.z += v[2]; a0.w += v[3];
+            a1.x += v[4]; a1.y += v[5]; a1.z += v[6]; a1.w += v[7];
+            dst[0] = a0;
+            dst[1] = a1;
+        }
+        __syncwarp();
+    }
+
+    // ---------------- phase 3: lane = Gaussian ----------------
+    if (!live) return;
+    float vm[3] = {0.f, 0.f, 0.f}, vs[3] = {0.f, 0.f, 0.f}, vq[4] = {0.f, 0.f, 0.f, 0.f}, vo = 0.f;
+    float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
+    if (nrows > 0) {
+        const float4 a0 = *reinterpret_cast<const float4 *>(&s_acc[warp][lane][0]);
+        const float4 a1 = *reinterpret_cast<const float4 *>(&s_acc[warp][lane][4]);
+        const float sc = seed_scale, asc = fabsf(seed_scale);
+        g0 = make_float4(a0.x * sc, a0.y * sc, a0.z * asc, a0.w * asc);
+        // v_opacity' = sum vis * v_alpha = -(sum v_sigma) / opacity'
+        g1 = make_float4(a1.x * sc, a1.y * sc, a1.z * sc, -(a1.w * sc) * eg_rcp(opac_eff));
+        const float4 q4 = __ldg(reinterpret_cast<const float4 *>(quats) + g);
+        const float mx = __ldg(means + 3 * g), my = __ldg(means + 3 * g + 1), mz = __ldg(means + 3 * g + 2);
+        float s[3];
+        s[0] = __ldg(scales + 3 * g); s[1] = __ldg(scales + 3 * g + 1); s[2] = __ldg(scales + 3 * g + 2);
+        const float o = __ldg(opacities + g);
+        const EgCam cam = eg_load_cam(viewmat, Kmat);
+        if (absgrad_accum != nullptr) absgrad_accum[g] += sqrtf(g0.z * g0.z + g0.w * g0.w);
+        eg_project_vjp<RAW>(cfg, cam, r1, g0, g1, mx, my, mz, q4, s, o, 0.0f, vm, vs, vq, vo);
+    }
+    if (grad2d_out != nullptr) {
+        grad2d_out[2 * g] = g0;
+        grad2d_out[2 * g + 1] = g1;
+    }
+    v_means[3 * g] = vm[0]; v_means[3 * g + 1] = vm[1]; v_means[3 * g + 2] = vm[2];
+    v_scales[3 * g] = vs[0]; v_scales[3 * g + 1] = vs[1]; v_scales[3 * g + 2] = vs[2];
+    reinterpret_cast<float4 *>(v_quats)[g] = make_float4(vq[0], vq[1], vq[2], vq[3]);
+    v_opacities[g] = vo;
+}
+
+// per-pixel backward seed of the gsplat-shaped autograd path:  w_p = (sum_ch v_render[p,ch] + v_alpha[p]) * (1 - alpha[p])
+__global__ void __launch_bounds__(256) seed_kernel(long long P, const float *__restrict__ alpha,
+                                                   const float *__restrict__ v_render, int ch,
+                                                   const float *__restrict__ v_alpha, float *__restrict__ wpix) {
+    const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    float gsum = 0.0f;
+    if (v_render != nullptr)
+        for (int c = 0; c < ch; ++c) gsum += __ldg(v_render + p * ch + c);
+    if (v_alpha != nullptr) gsum += __ldg(v_alpha + p);
+    wpix[p] = gsum * (1.0f - __ldg(alpha + p));
+}
+
+}  // namespace
+
+extern "C" int eg_splat_bwd(const eg_config *cfg, const float *means, const float *quats, const float *scales,
+                            const float *opacities, const float *viewmat, const float *K, const float *rec,
+                            const int32_t *gint, const float *wpix, float seed_scale, const uint32_t *last_depth,
+                            const int32_t *last_gid, const int32_t *tile_stop, const int32_t *status,
+                            float *grad2d_out, float *v_means,
+                            float *v_quats, float *v_scales, float *v_opacities, float *absgrad_accum, void *stream) {
+    if (cfg == nullptr || cfg->tile_size != EG_TILE) {
+        eg_set_error("eg_splat_bwd: tile_size must be %d", EG_TILE);
+        return 1;
+    }
+    if (wpix == nullptr || rec == nullptr || gint == nullptr || status == nullptr) {
+        eg_set_error("eg_splat_bwd: rec, gint, wpix and status are required");
+        return 1;
+    }
+    if ((last_depth == nullptr) != (last_gid == nullptr)) {
+        eg_set_error("eg_splat_bwd: last_depth and last_gid go together");
+        return 1;
+    }
+    if (cfg->n <= 0) return 0;
+    int tw, th;
+    eg_tile_grid(cfg->width, cfg->height, cfg->tile_size, &tw, &th);
+    const int block = SB_WARPS * 32, grid = (cfg->n + block - 1) / block;
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool aligned = (cfg->width % 4 == 0) && (((uintptr_t)wpix & 15) == 0) &&
+                         (last_depth == nullptr || ((uintptr_t)last_depth & 15) == 0);
+#define EG_SB_LAUNCH(RAWP, AL)                                                                                       \
+    splat_bwd_kernel<RAWP, AL><<<grid, block, 0, s>>>(*cfg, tw, th, means, quats, scales, opacities, viewmat, K,    \
+                                                      (const float4 *)rec, (const int2 *)gint, wpix, seed_scale,    \
+                                                      last_depth, last_gid, tile_stop, status,                      \
+                                                      (float4 *)grad2d_out, v_means,                                \
+                                                      v_quats, v_scales, v_opacities, absgrad_accum)
+    if (cfg->raw_params) {
+        if (aligned) EG_SB_LAUNCH(true, true); else EG_SB_LAUNCH(true, false);
+    } else {
+        if (aligned) EG_SB_LAUNCH(false, true); else EG_SB_LAUNCH(false, false);
+    }
+#undef EG_SB_LAUNCH
+    return eg_check_launch("eg_splat_bwd");
+}
+
+extern "C" int eg_make_seed(int64_t n_pixels, const float *alpha, const float *v_render, int v_render_channels,
+                            const float *v_alpha, float *wpix, void *stream) {
+    if (alpha == nullptr || wpix == nullptr) {
+        eg_set_error("eg_make_seed: alpha and wpix are required");
+        return 1;
+    }
+    if (n_pixels <= 0) return 0;
+    seed_kernel<<<(unsigned)((n_pixels + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (long long)n_pixels, alpha, v_render, v_render_channels, v_alpha, wpix);
+    return eg_check_launch("eg_make_seed");
+}

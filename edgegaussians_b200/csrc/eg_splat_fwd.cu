@@ -1,0 +1,269 @@
+// eg_splat_fwd.cu -- Gaussian-major forward of the fused training step (no tile lists, no sort):
+//
+//   eg_splat_fwd     every warp owns 32 Gaussians, walks the pixel rows of their alpha >= 1/255 footprints
+//                    (eg_splat.cuh) and adds  log2(1 - alpha)  of every pair gsplat would composite into a
+//                    per-pixel accumulator with 128-bit vector reductions (red.global.add.v4.f32, one per
+//                    aligned 4-pixel chunk; the image is L2-resident).
+//   eg_splat_resolve one CTA per 16x16 tile: T = 2^(sum) = prod (1 - alpha), render = alpha = 1 - T, the
+//                    reference's clamp -> channel 0 -> mean |render - gt| (edge_gs.py:279,290-296;
+//                    train_gaussians.py:84-94) and the per-pixel backward seed; re-zeroes the accumulator.
+//   eg_emit_flagged  exactness fallback, see below.
+//
+// Why this is gsplat's result (colors == 1 as at edge_gs.py:247): a pixel's render
+// is  sum_i alpha_i T_i = 1 - prod_i (1 - alpha_i)  over the Gaussians it composites, and it composites every
+// Gaussian of its tile list that passes the alpha test UNLESS the running transmittance crosses the stop
+// threshold (T (1 - alpha) <= 1e-4).  Prefix products only decrease, so if the order-free product over ALL
+// passing Gaussians stays above the threshold no prefix in any order crossed it, gsplat never stopped and
+// the order-free product IS its result (up to fp32 rounding of the product, ~1e-6 relative).  Tiles in which
+// some pixel's product comes within 0.1 % of the threshold are flagged (tile_stop) and redone exactly:
+// eg_emit_flagged appends the (depth, id) keys of the Gaussians that touch flagged tiles to per-tile buckets
+// and eg_raster_fwd sorts and composites just those tiles front to back with the stop rule.  With the
+// reference's translucent Gaussians (opacity 0.08 at init, configs/*.json:35) no tile is flagged and both
+// fallback kernels return immediately.
+#include "eg_splat.cuh"
+
+namespace {
+
+constexpr int SF_WARPS = 4;
+
+__device__ __forceinline__ float eg_lg2(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void red_add_f32(float *addr, float v) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+
+// log2(1 - alpha) of one pair, 0 when gsplat skips it (sigma < 0 or alpha < 1/255)
+__device__ __forceinline__ float pair_fwd(const EgSplatG &G, const float b1, const float c0, const float px,
+                                          const bool in_span) {
+    const float dx = G.mx - px;
+    const float p = eg_pow2row(G.fa, b1, c0, dx);
+    const float ov = eg_ex2(p);
+    const float l = eg_lg2(1.0f - fminf(EG_ALPHA_MAX, ov));
+    return eg_pair_valid(ov, p, G.lo, in_span) ? l : 0.0f;
+}
+
+template <bool ALIGNED>
+__device__ __forceinline__ void walk_row_fwd(const EgSplatG &G, const int y, const int W, float *__restrict__ logT) {
+    const float dy = G.my - ((float)y + 0.5f);
+    const float b1 = eg_pow2row_b1(G.fb, dy), c0 = eg_pow2row_c0(G.fc, G.lo, dy);
+    int xa, xb;
+    if (!eg_row_span(G, b1, c0, xa, xb)) return;
+    float *row = logT + (size_t)y * (size_t)W;
+    const int cend = xb >> 2;
+    for (int c = xa >> 2; c <= cend; ++c) {
+        const int x = 4 * c;
+        const float px = (float)x + 0.5f;  // pixel centres x + 0.5 .. x + 3.5 are exact in fp32
+        // ALIGNED: W % 4 == 0 and the tile rectangle's columns are multiples of 16, so an aligned chunk that
+        // overlaps the span lies entirely inside the rectangle -- no per-pixel clipping needed
+        const float v0 = pair_fwd(G, b1, c0, px, ALIGNED || (x >= xa && x <= xb));
+        const float v1 = pair_fwd(G, b1, c0, px + 1.0f, ALIGNED || (x + 1 >= xa && x + 1 <= xb));
+        const float v2 = pair_fwd(G, b1, c0, px + 2.0f, ALIGNED || (x + 2 >= xa && x + 2 <= xb));
+        const float v3 = pair_fwd(G, b1, c0, px + 3.0f, ALIGNED || (x + 3 >= xa && x + 3 <= xb));
+        if (ALIGNED) {
+            if ((__float_as_uint(v0) | __float_as_uint(v1) | __float_as_uint(v2) | __float_as_uint(v3)) << 1)
+                eg_red_add_v4(row + x, v0, v1, v2, v3);
+        } else {
+            if (v0 != 0.0f) red_add_f32(row + x, v0);
+            if (v1 != 0.0f) red_add_f32(row + x + 1, v1);
+            if (v2 != 0.0f) red_add_f32(row + x + 2, v2);
+            if (v3 != 0.0f) red_add_f32(row + x + 3, v3);
+        }
+    }
+}
+
+template <bool ALIGNED>
+__global__ void __launch_bounds__(SF_WARPS * 32) splat_fwd_kernel(const eg_config cfg, const int tw, const int th,
+                                                                  const float4 *__restrict__ rec,
+                                                                  const int2 *__restrict__ gint,
+                                                                  float *__restrict__ logT,
+                                                                  const int32_t *__restrict__ status) {
+    __shared__ EgSplatG s_g[SF_WARPS][32];
+    __shared__ int s_end[SF_WARPS][32];
+    if (status[EG_ST_OVERFLOW]) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = (blockIdx.x * SF_WARPS + warp) * 32 + lane;
+    EgSplatG G;
+    int nrows = 0;
+    if (g < cfg.n) {
+        const int2 gi = __ldg(gint + g);
+        nrows = eg_splat_setup(cfg, tw, th, g, __ldg(rec + 2 * g), __ldg(rec + 2 * g + 1), gi.x, G);
+    } else {
+        G.nrows = 0;
+    }
+    int incl = nrows;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    G.start = incl - nrows;
+    s_g[warp][lane] = G;
+    s_end[warp][lane] = incl;
+    const int R = __shfl_sync(0xffffffffu, incl, 31);
+    __syncwarp();
+    for (int base = 0; base < R; base += 32) {
+        const int item = base + lane;
+        if (item < R) {
+            const int owner = eg_find_owner(s_end[warp], item);
+            const EgSplatG Go = s_g[warp][owner];
+            walk_row_fwd<ALIGNED>(Go, Go.ylo + (item - Go.start), cfg.width, logT);
+        }
+    }
+}
+
+template <int GT_KIND>
+__global__ void __launch_bounds__(256) splat_resolve_kernel(const eg_config cfg, const int tw,
+                                                            float *__restrict__ logT, const void *__restrict__ gt,
+                                                            double *__restrict__ loss_sum, float *__restrict__ wpix,
+                                                            float *__restrict__ render0, float *__restrict__ alpha_out,
+                                                            int32_t *__restrict__ tile_stop,
+                                                            int32_t *__restrict__ status) {
+    __shared__ float s_red[8];
+    if (status[EG_ST_OVERFLOW]) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x;
+    const int tile_y = tile / tw, tile_x = tile - tile_y * tw;
+    // a warp covers 2 rows x 16 pixels: each row segment is one 64-byte run
+    const int pxi = tile_x * EG_TILE + (tid & 15), pyi = tile_y * EG_TILE + (tid >> 4);
+    const bool inside = pxi < cfg.width && pyi < cfg.height;
+    const long long pix = (long long)pyi * cfg.width + pxi;
+    float T = 1.0f;
+    if (inside) {
+        T = eg_ex2(logT[pix]);
+        logT[pix] = 0.0f;  // clean for the next iteration's reductions
+    }
+    // some pixel of the tile may have hit gsplat's stop rule: the tile is redone exactly by eg_raster_fwd
+    if (__syncthreads_or(inside && !(T > EG_T_MIN * 1.001f))) {
+        if (tid == 0) {
+            tile_stop[tile] = 1;
+            atomicAdd(status + EG_ST_STOPPED, 1);
+        }
+        return;
+    }
+    float absd = 0.0f;
+    if (inside) {
+        const float out = 1.0f - T;
+        if (alpha_out) alpha_out[pix] = out;
+        if (render0) render0[pix] = out;
+        if (GT_KIND != EG_GT_NONE) {
+            float gv;
+            if (GT_KIND == EG_GT_F32) gv = __ldg(reinterpret_cast<const float *>(gt) + pix);
+            else gv = __fdiv_rn((float)__ldg(reinterpret_cast<const unsigned char *>(gt) + pix), 255.0f);
+            const float d = fminf(fmaxf(out, 0.0f), 1.0f) - gv;
+            absd = fabsf(d);
+            const float sgn = (d > 0.0f) ? 1.0f : ((d < 0.0f) ? -1.0f : 0.0f);
+            const float pass = (out >= 0.0f && out <= 1.0f) ? 1.0f : 0.0f;
+            if (wpix) wpix[pix] = sgn * pass * T;
+        }
+    }
+    if (GT_KIND != EG_GT_NONE && loss_sum != nullptr) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) absd += __shfl_xor_sync(0xffffffffu, absd, d);
+        if (lane == 0) s_red[warp] = absd;
+        __syncthreads();
+        if (tid == 0) {
+            float tsum = 0.0f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) tsum += s_red[w];
+            if (tsum != 0.0f) atomicAdd(loss_sum, (double)tsum);
+        }
+    }
+}
+
+// keys of the Gaussians that touch FLAGGED tiles -> per-tile buckets (only runs when a tile was flagged)
+__global__ void __launch_bounds__(256) emit_flagged_kernel(const eg_config cfg, const int tw, const int th,
+                                                           const float4 *__restrict__ rec,
+                                                           const int2 *__restrict__ gint,
+                                                           const int32_t *__restrict__ tile_stop,
+                                                           int32_t *__restrict__ tile_cnt,
+                                                           unsigned long long *__restrict__ keys,
+                                                           int32_t *__restrict__ status) {
+    if (status[EG_ST_STOPPED] == 0 || status[EG_ST_OVERFLOW]) return;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= cfg.n) return;
+    const int2 gi = __ldg(gint + g);
+    if (gi.x <= 0 || gi.y <= 0) return;
+    const float4 r0 = __ldg(rec + 2 * g);
+    uint32_t x0, y0, x1, y1;
+    eg_tile_rect(r0.x, r0.y, gi.x, tw, th, x0, y0, x1, y1);
+    const unsigned long long key = ((unsigned long long)__float_as_uint(r0.w) << 32) | (unsigned int)g;
+    for (uint32_t i = y0; i < y1; ++i)
+        for (uint32_t j = x0; j < x1; ++j) {
+            const size_t t = (size_t)i * tw + j;
+            if (__ldg(tile_stop + t) == 0) continue;
+            const int pos = atomicAdd(tile_cnt + t, 1);
+            if (pos < cfg.tile_capacity) keys[t * (size_t)cfg.tile_capacity + pos] = key;
+            else {  // bucket too small: the caller re-runs with tile_capacity >= status[EG_ST_MAXTILE]
+                status[EG_ST_OVERFLOW] = 1;
+                atomicMax(status + EG_ST_MAXTILE, pos + 1);
+            }
+        }
+}
+
+}  // namespace
+
+extern "C" int eg_splat_fwd(const eg_config *cfg, const float *rec, const int32_t *gint, float *logT,
+                            const int32_t *status, void *stream) {
+    if (cfg == nullptr || cfg->tile_size != EG_TILE) {
+        eg_set_error("eg_splat_fwd: tile_size must be %d", EG_TILE);
+        return 1;
+    }
+    if (rec == nullptr || gint == nullptr || logT == nullptr || status == nullptr) {
+        eg_set_error("eg_splat_fwd: rec, gint, logT and status are required");
+        return 1;
+    }
+    if (cfg->n <= 0) return 0;
+    int tw, th;
+    eg_tile_grid(cfg->width, cfg->height, cfg->tile_size, &tw, &th);
+    const int block = SF_WARPS * 32, grid = (cfg->n + block - 1) / block;
+    cudaStream_t s = (cudaStream_t)stream;
+    if ((cfg->width % 4 == 0) && (((uintptr_t)logT & 15) == 0))
+        splat_fwd_kernel<true><<<grid, block, 0, s>>>(*cfg, tw, th, (const float4 *)rec, (const int2 *)gint, logT, status);
+    else
+        splat_fwd_kernel<false><<<grid, block, 0, s>>>(*cfg, tw, th, (const float4 *)rec, (const int2 *)gint, logT, status);
+    return eg_check_launch("eg_splat_fwd");
+}
+
+extern "C" int eg_splat_resolve(const eg_config *cfg, float *logT, const void *gt, int gt_kind, double *loss_sum,
+                                float *wpix, float *render0, float *alpha, int32_t *tile_stop, int32_t *status,
+                                void *stream) {
+    if (cfg == nullptr || cfg->tile_size != EG_TILE) {
+        eg_set_error("eg_splat_resolve: tile_size must be %d", EG_TILE);
+        return 1;
+    }
+    if (logT == nullptr || tile_stop == nullptr || status == nullptr) {
+        eg_set_error("eg_splat_resolve: logT, tile_stop and status are required");
+        return 1;
+    }
+    if (gt == nullptr) gt_kind = EG_GT_NONE;
+    int tw, th;
+    eg_tile_grid(cfg->width, cfg->height, cfg->tile_size, &tw, &th);
+    cudaStream_t s = (cudaStream_t)stream;
+#define EG_RS_LAUNCH(KIND) \
+    splat_resolve_kernel<KIND><<<tw * th, 256, 0, s>>>(*cfg, tw, logT, gt, loss_sum, wpix, render0, alpha, tile_stop, status)
+    switch (gt_kind) {
+        case EG_GT_NONE: EG_RS_LAUNCH(EG_GT_NONE); break;
+        case EG_GT_F32: EG_RS_LAUNCH(EG_GT_F32); break;
+        case EG_GT_U8: EG_RS_LAUNCH(EG_GT_U8); break;
+        default: eg_set_error("eg_splat_resolve: bad gt_kind %d", gt_kind); return 1;
+    }
+#undef EG_RS_LAUNCH
+    return eg_check_launch("eg_splat_resolve");
+}
+
+extern "C" int eg_emit_flagged(const eg_config *cfg, const float *rec, const int32_t *gint, const int32_t *tile_stop,
+                               int32_t *tile_cnt, uint64_t *keys, int32_t *status, void *stream) {
+    if (cfg == nullptr || cfg->tile_size != EG_TILE) {
+        eg_set_error("eg_emit_flagged: tile_size must be %d", EG_TILE);
+        return 1;
+    }
+    if (cfg->n <= 0) return 0;
+    int tw, th;
+    eg_tile_grid(cfg->width, cfg->height, cfg->tile_size, &tw, &th);
+    emit_flagged_kernel<<<(cfg->n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        *cfg, tw, th, (const float4 *)rec, (const int2 *)gint, tile_stop, tile_cnt, (unsigned long long *)keys, status);
+    return eg_check_launch("eg_emit_flagged");
+}

@@ -63,24 +63,57 @@ class RasterStepWorkspace:
         T = tw * th
         f32, i32 = torch.float32, torch.int32
         self.N, self.W, self.H, self.T, self.capacity = N, W, H, T, int(capacity)
+        self.device = device
         self.tile_capacity = tile_capacity_for(self.capacity, T, max_tile)
         self.rec = torch.empty((N, 8), dtype=f32, device=device)
         self.gint = torch.empty((N, 2), dtype=i32, device=device)
-        # tile_counts | status share one allocation so a single memset clears both
-        self.zero_block = torch.zeros(T * _lib.EG_CNT_STRIDE + _lib.EG_ST_WORDS + 2, dtype=i32, device=device)
-        self.tile_counts = self.zero_block[:T * _lib.EG_CNT_STRIDE]
-        self.status = self.zero_block[T * _lib.EG_CNT_STRIDE:T * _lib.EG_CNT_STRIDE + _lib.EG_ST_WORDS]
-        self.loss_sum = self.zero_block[T * _lib.EG_CNT_STRIDE + _lib.EG_ST_WORDS:].view(torch.float64)
+        # status | loss accumulator | tile_stop | tile_cnt | padded tile counters share one allocation: the
+        # Gaussian-major pipeline clears only the small head, the tile pipeline all of it, with one memset each
+        head = _lib.EG_ST_WORDS + 2 + 2 * T
+        self.zero_block = torch.zeros(head + T * _lib.EG_CNT_STRIDE, dtype=i32, device=device)
+        self.zero_head = self.zero_block[:head]
+        self.status = self.zero_block[:_lib.EG_ST_WORDS]
+        self.loss_sum = self.zero_block[_lib.EG_ST_WORDS:_lib.EG_ST_WORDS + 2].view(torch.float64)
+        self.tile_stop = self.zero_block[_lib.EG_ST_WORDS + 2:_lib.EG_ST_WORDS + 2 + T]
+        self.tile_cnt = self.zero_block[_lib.EG_ST_WORDS + 2 + T:head]
+        self.tile_counts = self.zero_block[head:]
         self.tile_offsets = torch.empty(T + 1, dtype=i32, device=device)
         self.compact_keys = use_compact_keys(T, self.tile_capacity)
-        self.keys = torch.empty(self.capacity if self.compact_keys else T * self.tile_capacity, dtype=torch.int64,
-                                device=device)
-        self.flatten_ids = torch.empty(self.capacity, dtype=i32, device=device)
-        self.cmask = torch.empty((self.capacity, 8), dtype=i32, device=device)
         self.wpix = torch.empty((H, W), dtype=f32, device=device)
         self.render0 = torch.empty((H, W), dtype=f32, device=device)
-        self.grad2d = torch.zeros((N, 8), dtype=f32, device=device)
+        # per-pixel cut-off of the backward for pixels that hit the transmittance stop (eg_splat_bwd)
+        self.last_depth = torch.empty((H, W), dtype=i32, device=device)
+        self.last_gid = torch.empty((H, W), dtype=i32, device=device)
         self.grads = torch.zeros(11 * N, dtype=f32, device=device)  # means | scales | quats | opacities
+        self._lazy = {}
+
+    def _get(self, name, make):
+        if name not in self._lazy:
+            self._lazy[name] = make()
+        return self._lazy[name]
+
+    # buffers only some pipelines need (allocated on first use, then persistent)
+    @property
+    def logT(self):  # Gaussian-major forward: per-pixel sum of log2(1 - alpha), kept zero between iterations
+        return self._get("logT", lambda: torch.zeros((self.H, self.W), dtype=torch.float32, device=self.device))
+
+    @property
+    def keys(self):  # tile pipeline: all buckets (or the compact array); splat fallback: buckets of flagged tiles
+        n = self.capacity if self.compact_keys else self.T * self.tile_capacity
+        return self._get("keys", lambda: torch.empty(n, dtype=torch.int64, device=self.device))
+
+    @property
+    def flatten_ids(self):
+        n = max(self.capacity, 0 if self.compact_keys else self.T * self.tile_capacity)
+        return self._get("flatten_ids", lambda: torch.empty(n, dtype=torch.int32, device=self.device))
+
+    @property
+    def cmask(self):
+        return self._get("cmask", lambda: torch.empty((self.capacity, 8), dtype=torch.int32, device=self.device))
+
+    @property
+    def grad2d(self):
+        return self._get("grad2d", lambda: torch.zeros((self.N, 8), dtype=torch.float32, device=self.device))
 
 
 class EdgeGaussianSplatting(torch.nn.Module):
@@ -94,6 +127,8 @@ class EdgeGaussianSplatting(torch.nn.Module):
         # (opaque, saturating scenes late in training), as reported by status[EG_ST_REDO].
         self.lazy_sort = "auto"
         self._lazy_on = True
+        self.pipeline = "auto"          # "auto" | "splat" | "tiles+splat" | "tiles"  (see enqueue_raster_step)
+        self._auto_pipeline = "splat"
         self.crop_box = None
         self._ws: Optional[RasterStepWorkspace] = None
         self.config = EdgeGaussianSplattingConfig()
@@ -264,52 +299,112 @@ class EdgeGaussianSplatting(torch.nn.Module):
         return ws
 
     def enqueue_raster_step(self, viewmat, K, W, H, gt, *, loss_weight=1.0, accumulate_absgrad=True, capacity=None,
-                            want_render=False, stage_cb=None, lazy_sort=None) -> RasterStepWorkspace:
+                            want_render=False, stage_cb=None, lazy_sort=None, pipeline=None) -> RasterStepWorkspace:
         """Enqueue one fused forward+backward iteration on the current stream. No host sync, no
         allocation after the first call for a given (N, W, H): CUDA-graph capturable.
 
         Results (device): ws.loss_sum[0] / (W*H) = "whole" L1 loss; ws.grads = gradients of
         loss_weight * loss w.r.t. (means | log-scales | quats | logit-opacities), also installed as
         ``.grad`` views on the parameters; self.absgrads += ||means2d.absgrad|| when
-        ``accumulate_absgrad``; ws.status = (n_isects, overflow, ...)."""
+        ``accumulate_absgrad``; ws.status = (n_isects, overflow, ...).
+
+        ``pipeline`` (default: :meth:`current_pipeline`), all three give gsplat's result:
+          "splat"        Gaussian-major forward (eg_splat_fwd/resolve, exact per-tile fallback) + eg_splat_bwd;
+          "tiles+splat"  tile binning + per-tile sort/compositing (eg_raster_fwd) + eg_splat_bwd;
+          "tiles"        eg_raster_fwd with contribution masks + eg_raster_bwd + eg_project_bwd."""
         lib = get_engine(self.means.device).lib
         ws = self._workspace(W, H, capacity)
         N = ws.N
+        pipeline = pipeline or self.current_pipeline()
+        if pipeline not in ("splat", "tiles+splat", "tiles"):
+            raise ValueError(f"unknown pipeline {pipeline!r}")
+        if pipeline == "splat" and ws.compact_keys:
+            pipeline = "tiles+splat"  # the fallback of the Gaussian-major forward needs per-tile buckets
+        flags = (_lib.EG_FLAG_COMPACT_KEYS if ws.compact_keys else 0)
+        if pipeline == "splat":
+            flags |= _lib.EG_FLAG_NO_EMIT
+        elif self._use_lazy(lazy_sort):
+            flags |= _lib.EG_FLAG_LAZY_SORT
         cfg = _lib.EgConfig(n=N, width=W, height=H, tile_size=TILE, eps2d=0.3, near_plane=0.01, far_plane=1e10,
                             radius_clip=0.0, antialiased=1 if self.config.rasterize_mode == "antialiased" else 0,
-                            raw_params=1, isect_capacity=ws.capacity, tile_capacity=ws.tile_capacity,
-                            flags=(_lib.EG_FLAG_LAZY_SORT if self._use_lazy(lazy_sort) else 0)
-                            | (_lib.EG_FLAG_COMPACT_KEYS if ws.compact_keys else 0))
+                            raw_params=1, isect_capacity=ws.capacity, tile_capacity=ws.tile_capacity, flags=flags)
         c = ctypes.byref(cfg)
         s = _stream()
         gt_kind = _lib.EG_GT_U8 if gt.dtype == torch.uint8 else _lib.EG_GT_F32
         means, quats, scales, opac = self.means.data, self.quats.data, self.scales.data, self.opacities.data
         cb = stage_cb if stage_cb is not None else (lambda name: None)
-        cb("begin")
-        ws.zero_block.zero_()   # tile counters + status + loss accumulator (grad2d is re-zeroed by eg_project_bwd)
-        cb("memset")
         chk = _lib.check
-        chk(lib.eg_project_fwd(c, _p(means), _p(quats), _p(scales), _p(opac), None, _p(viewmat), _p(K), _p(ws.rec),
-                               _p(ws.gint), _p(ws.tile_counts), _p(ws.keys), _p(ws.status), s), "eg_project_fwd")
-        cb("project_fwd")
-        chk(lib.eg_bin(c, _p(ws.tile_counts), _p(ws.tile_offsets), _p(ws.status), _p(ws.rec), _p(ws.gint),
-                       _p(ws.keys), s), "eg_bin")
-        cb("bin")
-        chk(lib.eg_raster_fwd(c, _p(ws.rec), _p(ws.tile_offsets), _p(ws.keys), _p(ws.flatten_ids), None,
-                              _p(ws.render0) if want_render else None, None, None, _p(ws.cmask), _p(gt), gt_kind,
-                              _p(ws.loss_sum), _p(ws.wpix), _p(ws.status), s), "eg_raster_fwd")
-        cb("raster_fwd")
-        chk(lib.eg_raster_bwd(c, _p(ws.rec), _p(ws.tile_offsets), _p(ws.flatten_ids), _p(ws.cmask), None, None, 0,
-                              None, _p(ws.wpix), float(loss_weight) / float(W * H), _p(ws.grad2d), _p(ws.status), s),
-            "eg_raster_bwd")
-        cb("raster_bwd")
+        seed = float(loss_weight) / float(W * H)
         g = ws.grads
-        chk(lib.eg_project_bwd(c, _p(means), _p(quats), _p(scales), _p(opac), _p(viewmat), _p(K), _p(ws.rec),
-                               _p(ws.gint), _p(ws.grad2d), 1, None, _p(g[0:3 * N]), _p(g[6 * N:10 * N]),
-                               _p(g[3 * N:6 * N]), _p(g[10 * N:11 * N]),
-                               _p(self.absgrads) if accumulate_absgrad else None, s), "eg_project_bwd")
-        cb("project_bwd")
+        absg = _p(self.absgrads) if accumulate_absgrad else None
+        render0 = _p(ws.render0) if want_render else None
+        cb("begin")
+        if pipeline == "splat":
+            ws.zero_head.zero_()    # status + loss accumulator + tile_stop + tile_cnt (logT is re-zeroed by the resolve)
+            cb("memset")
+            chk(lib.eg_project_fwd(c, _p(means), _p(quats), _p(scales), _p(opac), None, _p(viewmat), _p(K), _p(ws.rec),
+                                   _p(ws.gint), None, None, _p(ws.status), s), "eg_project_fwd")
+            cb("project_fwd")
+            chk(lib.eg_splat_fwd(c, _p(ws.rec), _p(ws.gint), _p(ws.logT), _p(ws.status), s), "eg_splat_fwd")
+            cb("splat_fwd")
+            chk(lib.eg_splat_resolve(c, _p(ws.logT), _p(gt), gt_kind, _p(ws.loss_sum), _p(ws.wpix), render0, None,
+                                     _p(ws.tile_stop), _p(ws.status), s), "eg_splat_resolve")
+            cb("splat_resolve")
+            # exact redo of the tiles in which a pixel may have hit gsplat's stop rule (both return at once if none)
+            chk(lib.eg_emit_flagged(c, _p(ws.rec), _p(ws.gint), _p(ws.tile_stop), _p(ws.tile_cnt), _p(ws.keys),
+                                    _p(ws.status), s), "eg_emit_flagged")
+            chk(lib.eg_raster_fwd(c, _p(ws.rec), None, _p(ws.keys), _p(ws.flatten_ids), None, render0, None, None, None,
+                                  _p(gt), gt_kind, _p(ws.loss_sum), _p(ws.wpix), _p(ws.last_depth), _p(ws.last_gid),
+                                  _p(ws.tile_stop), _p(ws.tile_cnt), _p(ws.status), s), "eg_raster_fwd")
+            cb("stop_fallback")
+            tile_stop = _p(ws.tile_stop)
+        else:
+            ws.zero_block.zero_()   # + the padded tile counters
+            cb("memset")
+            chk(lib.eg_project_fwd(c, _p(means), _p(quats), _p(scales), _p(opac), None, _p(viewmat), _p(K), _p(ws.rec),
+                                   _p(ws.gint), _p(ws.tile_counts), _p(ws.keys), _p(ws.status), s), "eg_project_fwd")
+            cb("project_fwd")
+            chk(lib.eg_bin(c, _p(ws.tile_counts), _p(ws.tile_offsets), _p(ws.status), _p(ws.rec), _p(ws.gint),
+                           _p(ws.keys), s), "eg_bin")
+            cb("bin")
+            tiles_bwd = pipeline == "tiles"
+            chk(lib.eg_raster_fwd(c, _p(ws.rec), _p(ws.tile_offsets), _p(ws.keys), _p(ws.flatten_ids), None, render0,
+                                  None, None, _p(ws.cmask) if tiles_bwd else None, _p(gt), gt_kind, _p(ws.loss_sum),
+                                  _p(ws.wpix), None if tiles_bwd else _p(ws.last_depth),
+                                  None if tiles_bwd else _p(ws.last_gid), None, None, _p(ws.status), s), "eg_raster_fwd")
+            cb("raster_fwd")
+            tile_stop = None
+        if pipeline == "tiles":
+            chk(lib.eg_raster_bwd(c, _p(ws.rec), _p(ws.tile_offsets), _p(ws.flatten_ids), _p(ws.cmask), None, None, 0,
+                                  None, _p(ws.wpix), seed, _p(ws.grad2d), _p(ws.status), s), "eg_raster_bwd")
+            cb("raster_bwd")
+            chk(lib.eg_project_bwd(c, _p(means), _p(quats), _p(scales), _p(opac), _p(viewmat), _p(K), _p(ws.rec),
+                                   _p(ws.gint), _p(ws.grad2d), 1, None, _p(g[0:3 * N]), _p(g[6 * N:10 * N]),
+                                   _p(g[3 * N:6 * N]), _p(g[10 * N:11 * N]), absg, s), "eg_project_bwd")
+            cb("project_bwd")
+        else:
+            chk(lib.eg_splat_bwd(c, _p(means), _p(quats), _p(scales), _p(opac), _p(viewmat), _p(K), _p(ws.rec),
+                                 _p(ws.gint), _p(ws.wpix), seed, _p(ws.last_depth), _p(ws.last_gid), tile_stop,
+                                 _p(ws.status), None, _p(g[0:3 * N]), _p(g[6 * N:10 * N]), _p(g[3 * N:6 * N]),
+                                 _p(g[10 * N:11 * N]), absg, s), "eg_splat_bwd")
+            cb("splat_bwd")
+        ws.pipeline = pipeline
         return ws
+
+    # ------------------------------------------------------------------ pipeline policy
+    def current_pipeline(self) -> str:
+        """``self.pipeline`` = "auto" (default) starts Gaussian-major and, fed by :meth:`note_status`, moves to the
+        tile pipeline for good once more than a quarter of the tiles needed the exact stop-rule fallback (opaque,
+        saturating scenes late in training); there the backward follows the footprint size (tile-major walk of
+        contribution masks for large Gaussians, Gaussian-major for small ones)."""
+        return self._auto_pipeline if self.pipeline == "auto" else self.pipeline
+
+    def note_status(self, hs, n_tiles: int) -> None:
+        """Feed back the status words of a finished step (any host read of them)."""
+        n_isects, stopped, redo = int(hs[_lib.EG_ST_NISECT]), int(hs[_lib.EG_ST_STOPPED]), int(hs[_lib.EG_ST_REDO])
+        if self.pipeline == "auto" and self._auto_pipeline == "splat" and stopped > 0.25 * n_tiles:
+            self._auto_pipeline = "tiles" if n_isects > 8 * self.num_points else "tiles+splat"
+        self.note_redo(redo, n_tiles)
 
     def _use_lazy(self, override=None) -> bool:
         mode = self.lazy_sort if override is None else override
@@ -343,7 +438,7 @@ class EdgeGaussianSplatting(torch.nn.Module):
             if not sync:
                 break
             hs = ws.status.cpu()
-            self.note_redo(int(hs[_lib.EG_ST_REDO]), ws.T)
+            self.note_status(hs, ws.T)
             if not int(hs[_lib.EG_ST_OVERFLOW]):
                 break
             # roll back the abs-grad accumulation is unnecessary: overflowed runs are no-ops in raster kernels

@@ -72,6 +72,8 @@ class SplatState:
     loss_sum: Optional[torch.Tensor] = None   # [1] f64
     isect_ids: Optional[torch.Tensor] = None  # [cap] i64
     cmask: Optional[torch.Tensor] = None      # [cap,8] i32: per-intersection contribution masks (backward work list)
+    last_depth: Optional[torch.Tensor] = None  # [H,W] u32 bits: depth key of the last Gaussian a stopped pixel composited
+    last_gid: Optional[torch.Tensor] = None    # [H,W] i32: ... and its id (eg_splat_bwd's per-pixel cut-off)
     grad2d: Optional[torch.Tensor] = None     # [N,8] f32, written by raster_bwd
     n_isects: Optional[int] = None            # known on the host only after a status read
 
@@ -167,9 +169,12 @@ class Engine:
             tile_counts.zero_()
 
     def raster_fwd(self, st: SplatState, *, gt: Optional[torch.Tensor] = None, want_alpha=True, want_render=True,
-                   want_isect_ids=False, want_wpix=False, want_cmask=True) -> SplatState:
+                   want_isect_ids=False, want_wpix=False, want_cmask=True, want_last_keys=False) -> SplatState:
         dev = st.rec.device
         H, W = st.height, st.width
+        if want_last_keys:
+            st.last_depth = torch.empty((H, W), dtype=torch.int32, device=dev)
+            st.last_gid = torch.empty((H, W), dtype=torch.int32, device=dev)
         st.last_ids = torch.empty((H, W), dtype=torch.int32, device=dev)
         st.alpha = torch.empty((H, W), dtype=torch.float32, device=dev) if want_alpha else None
         st.render0 = torch.empty((H, W), dtype=torch.float32, device=dev) if want_render else None
@@ -193,7 +198,8 @@ class Engine:
         _lib.check(self.lib.eg_raster_fwd(ctypes.byref(st.cfg), _p(st.rec), _p(st.tile_offsets), _p(st.keys),
                                           _p(st.flatten_ids), _p(st.isect_ids), _p(st.render0), _p(st.alpha),
                                           _p(st.last_ids), _p(st.cmask), _p(gt), gt_kind, _p(st.loss_sum), _p(st.wpix),
-                                          _p(st.status), _stream()), "eg_raster_fwd")
+                                          _p(st.last_depth), _p(st.last_gid), None, None, _p(st.status), _stream()),
+                   "eg_raster_fwd")
         return st
 
     # ------------------------------------------------------------------ backward
@@ -242,6 +248,48 @@ class Engine:
                                            _p(v_means), _p(v_quats), _p(v_scales), _p(v_opac), _p(absgrad_accum),
                                            _stream()), "eg_project_bwd")
         return v_means, v_quats, v_scales, v_opac
+
+    def splat_bwd(self, st: SplatState, means, quats, scales, opacities, viewmat, K, *,
+                  v_render: Optional[torch.Tensor] = None, v_alpha: Optional[torch.Tensor] = None,
+                  seed_scale: float = 1.0, out: Optional[torch.Tensor] = None, want_grad2d: bool = False,
+                  absgrad_accum: Optional[torch.Tensor] = None):
+        """K6 + K7 fused (Gaussian-major, no tile lists, no atomics).  Seed: the fused-loss ``st.wpix`` or
+        (v_render [H,W,C] and/or v_alpha [H,W]) with the forward's alpha image.  Needs the forward's
+        last_depth / last_gid planes (raster_fwd(want_last_keys=True)).  Returns
+        (v_means, v_quats, v_scales, v_opacities, grad2d or None) -- the first four are views of ``out``
+        laid out means|scales|quats|opacities like :meth:`project_bwd`."""
+        N, dev = st.N, st.rec.device
+        if st.last_depth is None or st.last_gid is None:
+            raise RuntimeError("splat_bwd needs the forward's last-key planes (raster_fwd(want_last_keys=True))")
+        if v_render is None and v_alpha is None:
+            if st.wpix is None:
+                raise RuntimeError("splat_bwd needs v_render / v_alpha or a fused-loss forward (wpix)")
+            wpix = st.wpix
+        else:
+            if st.alpha is None:
+                raise RuntimeError("splat_bwd with v_render / v_alpha needs the forward alpha image")
+            ch = 0
+            if v_render is not None:
+                v_render = v_render.contiguous()
+                ch = v_render.shape[-1] if v_render.dim() == 3 else 1
+            if v_alpha is not None:
+                v_alpha = v_alpha.contiguous()
+            wpix = torch.empty((st.height, st.width), dtype=torch.float32, device=dev)
+            _lib.check(self.lib.eg_make_seed(st.height * st.width, _p(st.alpha), _p(v_render), ch, _p(v_alpha),
+                                             _p(wpix), _stream()), "eg_make_seed")
+        if out is None:
+            out = torch.empty(11 * N, dtype=torch.float32, device=dev)
+        grad2d = torch.empty((N, 8), dtype=torch.float32, device=dev) if want_grad2d else None
+        v_means = out[0:3 * N].view(N, 3)
+        v_scales = out[3 * N:6 * N].view(N, 3)
+        v_quats = out[6 * N:10 * N].view(N, 4)
+        v_opac = out[10 * N:11 * N]
+        _lib.check(self.lib.eg_splat_bwd(ctypes.byref(st.cfg), _p(means), _p(quats), _p(scales), _p(opacities),
+                                         _p(viewmat), _p(K), _p(st.rec), _p(st.gint), _p(wpix), float(seed_scale),
+                                         _p(st.last_depth), _p(st.last_gid), None, _p(st.status), _p(grad2d), _p(v_means),
+                                         _p(v_quats), _p(v_scales), _p(v_opac), _p(absgrad_accum), _stream()),
+                   "eg_splat_bwd")
+        return v_means, v_quats, v_scales, v_opac, grad2d
 
     # ------------------------------------------------------------------ status
     def read_status(self, st: SplatState):

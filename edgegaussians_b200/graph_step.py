@@ -57,7 +57,7 @@ class GraphedRasterStep:
                 need = max(need, n_isects)
                 eng = get_engine(self.model.means.device)
                 eng.max_tile = max(eng.max_tile, int(hs[3]))
-                self.model.note_redo(int(hs[4]), ws.T)
+                self.model.note_status(hs, ws.T)
                 if not int(hs[1]):
                     break
                 self._capacity = int(n_isects * margin) + 1024

@@ -21,9 +21,18 @@ from torch import Tensor
 from .engine import SplatState, get_engine
 
 
+# Backward implementation of the gsplat-shaped op:
+#   "splat": eg_splat_bwd -- Gaussian-major raster backward fused with the projection backward (one kernel);
+#   "tiles": eg_raster_bwd (tile-major walk of the forward's contribution masks, atomics) + eg_project_bwd.
+# Both are kept: they share no code below the per-pair arithmetic, so each is the other's differential test.
+BACKWARD_IMPL = "splat"
+
+
 class _Holder:
     """Carries the non-tensor forward state between the two autograd Functions."""
     st: Optional[SplatState] = None
+    params = None   # (means, quats, scales, opacities, viewmat, K) as given to the projection
+    fused_grads = None  # (v_means, v_quats, v_scales, v_opac) produced by eg_splat_bwd inside _Raster.backward
 
 
 def _is_rec_view(t: Optional[Tensor], base: Tensor, col: int, width: int) -> bool:
@@ -55,8 +64,10 @@ class _ProjectBin(torch.autograd.Function):
                              near_plane=opts["near_plane"], far_plane=opts["far_plane"],
                              radius_clip=opts["radius_clip"], sync=True)
         holder.st = st
+        holder.params = (means_c, quats_c, scales_c, opac_c, vm, Kc)
         ctx.st = st
         ctx.eng = eng
+        ctx.holder = holder
         ctx.save_for_backward(means_c, quats_c, scales_c, opac_c, vm, Kc)
         rec = st.rec
         means2d = rec[:, 0:2].unsqueeze(0)     # [1,N,2]
@@ -71,8 +82,14 @@ class _ProjectBin(torch.autograd.Function):
         means, quats, scales, opac, vm, Kc = ctx.saved_tensors
         N = st.N
         base = st.grad2d
-        if (base is not None and _is_rec_view(v_means2d, base, 0, 2) and _is_rec_view(v_conics, base, 4, 3)
-                and _is_rec_view(v_opac, base, 7, 1)):
+        untouched = (base is not None and _is_rec_view(v_means2d, base, 0, 2) and _is_rec_view(v_conics, base, 4, 3)
+                     and _is_rec_view(v_opac, base, 7, 1))
+        if untouched and v_depths is None and ctx.holder.fused_grads is not None:
+            # eg_splat_bwd already carried the 2D gradients through the projection VJP in the same kernel
+            v_m, v_q, v_s, v_o = ctx.holder.fused_grads
+            ctx.holder.fused_grads = None
+            return v_m, v_q, v_s, v_o, None, None, None, None, None
+        if untouched:
             grad2d = base  # the raster backward's own buffer arrived untouched: no repacking
         else:
             grad2d = torch.zeros((N, 8), dtype=torch.float32, device=means.device)
@@ -96,8 +113,9 @@ class _Raster(torch.autograd.Function):
     def forward(ctx, means2d, conics, opac_eff, holder: _Holder, absgrad: bool, want_isect_ids: bool):
         st = holder.st
         eng = get_engine(st.rec.device)
-        eng.raster_fwd(st, want_alpha=True, want_render=True, want_isect_ids=want_isect_ids)
-        ctx.st, ctx.eng, ctx.absgrad = st, eng, absgrad
+        eng.raster_fwd(st, want_alpha=True, want_render=True, want_isect_ids=want_isect_ids,
+                       want_cmask=BACKWARD_IMPL == "tiles", want_last_keys=BACKWARD_IMPL == "splat")
+        ctx.st, ctx.eng, ctx.absgrad, ctx.holder = st, eng, absgrad, holder
         ctx.save_for_backward(means2d)
         return st.render0, st.alpha
 
@@ -105,8 +123,14 @@ class _Raster(torch.autograd.Function):
     def backward(ctx, v_render0, v_alpha):
         st, eng = ctx.st, ctx.eng
         (means2d,) = ctx.saved_tensors
-        grad2d = eng.raster_bwd(st, v_render=v_render0.unsqueeze(-1) if v_render0 is not None else None,
-                                v_alpha=v_alpha)
+        v_render = v_render0.unsqueeze(-1) if v_render0 is not None else None
+        if st.cmask is None:
+            means, quats, scales, opac, vm, Kc = ctx.holder.params
+            v_m, v_q, v_s, v_o, grad2d = eng.splat_bwd(st, means, quats, scales, opac, vm, Kc, v_render=v_render,
+                                                       v_alpha=v_alpha, want_grad2d=True)
+            ctx.holder.fused_grads = (v_m, v_q, v_s, v_o)
+        else:
+            grad2d = eng.raster_bwd(st, v_render=v_render, v_alpha=v_alpha)
         st.grad2d = grad2d
         if ctx.absgrad:
             means2d.absgrad = grad2d[:, 2:4].unsqueeze(0)  # [1,N,2], as gsplat sets it (edge_gs.py:612 reads it)

@@ -49,10 +49,18 @@
 extern "C" {
 #endif
 
-#define EG_ABI_VERSION 6
+#define EG_ABI_VERSION 7
 #define EG_CNT_STRIDE 32
 
-enum { EG_ST_NISECT = 0, EG_ST_OVERFLOW = 1, EG_ST_BADCOLOR = 2, EG_ST_MAXTILE = 3, EG_ST_REDO = 4, EG_ST_WORDS = 8 };
+enum {
+    EG_ST_NISECT = 0,   /* number of tile intersections (sum of tiles_per_gauss)                               */
+    EG_ST_OVERFLOW = 1, /* a key buffer was too small: raster / splat kernels are no-ops, caller re-runs       */
+    EG_ST_BADCOLOR = 2, /* a colour differed from 1                                                            */
+    EG_ST_MAXTILE = 3,  /* largest per-tile intersection count                                                 */
+    EG_ST_REDO = 4,     /* tiles composited a second time in sorted order (lazy sort / splat fallback)         */
+    EG_ST_STOPPED = 5,  /* tiles in which some pixel hit gsplat's transmittance stop (T * (1 - alpha) <= 1e-4) */
+    EG_ST_WORDS = 8
+};
 
 enum { EG_GT_NONE = 0, EG_GT_F32 = 1, EG_GT_U8 = 2 };
 
@@ -61,7 +69,9 @@ enum { EG_GT_NONE = 0, EG_GT_F32 = 1, EG_GT_U8 = 2 };
  * pixel came near gsplat's transmittance stop threshold -- when none does, the blend result cannot depend on
  * the order.  flatten_ids is then unordered inside such tiles (cmask stays aligned with it).
  * status[EG_ST_REDO] counts the tiles that had to be redone. */
-enum { EG_FLAG_LAZY_SORT = 1, EG_FLAG_COMPACT_KEYS = 2 };
+enum { EG_FLAG_LAZY_SORT = 1, EG_FLAG_COMPACT_KEYS = 2, EG_FLAG_NO_EMIT = 4 };
+/* EG_FLAG_NO_EMIT: eg_project_fwd neither counts nor emits tile intersections (Gaussian-major forward); it
+ * accumulates status[EG_ST_NISECT] = sum of tiles_per_gauss itself (no eg_bin in that pipeline). */
 /* EG_FLAG_COMPACT_KEYS: keys is a compact [isect_capacity] array segmented by tile_offsets instead of T
  * fixed-capacity buckets (for views where a few tiles hold most intersections and T * tile_capacity keys
  * would not fit): eg_project_fwd then only counts, eg_bin scans AND emits (second pass over the Gaussians,
@@ -114,11 +124,18 @@ int eg_bin(const eg_config *cfg, int32_t *tile_counts, int32_t *tile_offsets, in
  * cmask [cap,8] u32: per tile intersection (in flatten_ids order) the 256-bit mask of the tile's pixels
  * that composited that Gaussian; word w covers the 8x4 pixel block (x0 = 8*(w&1), y0 = 4*(w>>1)),
  * bit l the pixel (x0 + (l&7), y0 + (l>>3)).  It is the backward kernel's work list.
- * Any of render0 / alpha / last_ids / isect_ids / cmask / gt / loss_sum / wpix may be NULL. */
+ * last_depth [P] u32 / last_gid [P] i32 (both or neither): sort key (depth bits, Gaussian id) of the last
+ * Gaussian composited by each pixel that hit the transmittance stop, (0xffffffff, -1) elsewhere -- the
+ * per-pixel cut-off eg_splat_bwd needs; status[EG_ST_STOPPED] counts the tiles that contain such pixels.
+ * tile_stop [T] i32 / tile_cnt [T] i32 (both or neither): fallback mode of the Gaussian-major forward -- only the
+ * tiles flagged in tile_stop are processed, their keys are the first tile_cnt[t] entries of bucket t
+ * (eg_emit_flagged), always sorted; tile_offsets is then unused and flatten_ids needs T * tile_capacity entries.
+ * Any of render0 / alpha / last_ids / isect_ids / cmask / gt / loss_sum / wpix / last_* / tile_* may be NULL. */
 int eg_raster_fwd(const eg_config *cfg, const float *rec, const int32_t *tile_offsets, uint64_t *keys,
                   int32_t *flatten_ids, int64_t *isect_ids, float *render0, float *alpha,
                   int32_t *last_ids, uint32_t *cmask, const void *gt, int gt_kind, double *loss_sum,
-                  float *wpix, int32_t *status, void *stream);
+                  float *wpix, uint32_t *last_depth, int32_t *last_gid, const int32_t *tile_stop,
+                  const int32_t *tile_cnt, int32_t *status, void *stream);
 
 /* K6: compositing backward with abs-grad.  Replaces gsplat rasterize_to_pixels bwd.
  * The seed of pixel p is  w_p = (sum_ch v_render[p,ch] + v_alpha[p]) * (1 - alpha[p])  when
@@ -141,6 +158,48 @@ int eg_project_bwd(const eg_config *cfg, const float *means, const float *quats,
                    const int32_t *gint, float *grad2d, int zero_grad2d, const float *v_depths,
                    float *v_means, float *v_quats, float *v_scales, float *v_opacities,
                    float *absgrad_accum, void *stream);
+
+/* Gaussian-major forward of the fused training step (replaces isect_tiles + radix sort + rasterize_to_pixels fwd
+ * behind edge_gs.py:250-268 wherever gsplat's transmittance stop cannot trigger; exact fallback otherwise):
+ *   eg_splat_fwd      logT [P] fp32 (zero on entry) += log2(1 - alpha) of every (pixel, Gaussian) pair that passes
+ *                     gsplat's tile-rectangle / sigma / alpha tests (red.global.add.v4.f32, no tile lists);
+ *   eg_splat_resolve  per 16x16 tile: T = 2^logT, render = alpha = 1 - T, fused clamp + "whole" L1 loss + backward
+ *                     seed exactly as eg_raster_fwd (loss_sum, wpix), logT re-zeroed.  A tile in which some
+ *                     pixel's T is within 0.1 % of gsplat's stop threshold 1e-4 is NOT resolved: tile_stop[t] = 1
+ *                     and status[EG_ST_STOPPED] += 1 (tile_stop zeroed by the caller);
+ *   eg_emit_flagged   appends the keys of the Gaussians touching flagged tiles to keys [T, tile_capacity]
+ *                     (cursor tile_cnt [T] i32, zeroed by the caller); then eg_raster_fwd(tile_stop, tile_cnt)
+ *                     redoes exactly those tiles in sorted order.  Both return at once when nothing is flagged. */
+int eg_splat_fwd(const eg_config *cfg, const float *rec, const int32_t *gint, float *logT, const int32_t *status,
+                 void *stream);
+int eg_splat_resolve(const eg_config *cfg, float *logT, const void *gt, int gt_kind, double *loss_sum, float *wpix,
+                     float *render0, float *alpha, int32_t *tile_stop, int32_t *status, void *stream);
+int eg_emit_flagged(const eg_config *cfg, const float *rec, const int32_t *gint, const int32_t *tile_stop,
+                    int32_t *tile_cnt, uint64_t *keys, int32_t *status, void *stream);
+
+/* K6 + K7 fused, Gaussian-major (the fused training step's backward): replaces gsplat rasterize_to_pixels bwd
+ * + fully_fused_projection bwd + the opacity*compensation VJP + Exp/Sigmoid backward + update_absgrads
+ * (edge_gs.py:250-268, 603-613) in one kernel without tile lists or atomics.  Each warp owns 32 Gaussians, walks
+ * the pixel rows of their alpha >= 1/255 footprints (clipped to gsplat's tile rectangles) and re-applies the
+ * forward's exact per-pixel test, so the set of (pixel, Gaussian) pairs is the one the forward composited.
+ *   wpix [P]        per-pixel seed: seed_scale * wpix[p] = dL/d render(p) * T_final(p)   (eg_raster_fwd / eg_make_seed)
+ *   last_depth [P] u32, last_gid [P] i32 (both or neither): sort key (depth bits, id) of the last Gaussian each
+ *                   pixel composited, last_depth = 0xffffffff where the pixel never stopped; only read when
+ *                   status[EG_ST_STOPPED] != 0, and, when tile_stop [T] i32 is given (eg_splat_resolve), only
+ *                   inside the tiles it flags (the planes are undefined elsewhere).
+ *   grad2d_out [N,8] optional: the 2D gradients (layout of grad2d above), WRITTEN.
+ * Gradient outputs are WRITTEN (layout as eg_project_bwd); absgrad_accum [N] (may be NULL) += ||absgrad||_2. */
+int eg_splat_bwd(const eg_config *cfg, const float *means, const float *quats, const float *scales,
+                 const float *opacities, const float *viewmat, const float *K, const float *rec,
+                 const int32_t *gint, const float *wpix, float seed_scale, const uint32_t *last_depth,
+                 const int32_t *last_gid, const int32_t *tile_stop, const int32_t *status, float *grad2d_out,
+                 float *v_means,
+                 float *v_quats, float *v_scales, float *v_opacities, float *absgrad_accum, void *stream);
+
+/* Per-pixel seed of the gsplat-shaped autograd path:
+ *   wpix[p] = (sum_ch v_render[p,ch] + v_alpha[p]) * (1 - alpha[p])      (v_render / v_alpha may be NULL) */
+int eg_make_seed(int64_t n_pixels, const float *alpha, const float *v_render, int v_render_channels,
+                 const float *v_alpha, float *wpix, void *stream);
 
 /* a10 + a11: edge-direction and anisotropy regularisers, forward + backward in one pass.
  * Replaces compute_direction_loss / compute_ratio_loss + autograd (edge_gs.py:346-380).

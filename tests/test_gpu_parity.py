@@ -114,8 +114,13 @@ def _check_grad(name, key, got, ref, floor=0.0):
     assert n_bad <= max(2, int(5e-4 * err.size)), key
 
 
+@pytest.mark.parametrize("impl", ["splat", "tiles"])
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
-def test_backward_parity(case):
+def test_backward_parity(case, impl, monkeypatch):
+    """Both backward implementations of the gsplat-shaped op against the oracle: "splat" = eg_splat_bwd
+    (Gaussian-major, fused with the projection VJP), "tiles" = eg_raster_bwd + eg_project_bwd."""
+    import sys
+    monkeypatch.setattr(sys.modules["edgegaussians_b200.rasterization"], "BACKWARD_IMPL", impl)
     name, N, W, H, regime, seed, bs, view = case
     m, q, s, o, sc, op, vm, K = _inputs(N, W, H, regime, seed, bs, view)
     rng = np.random.default_rng(seed + 100)
@@ -139,10 +144,16 @@ def test_backward_parity(case):
     assert (ag >= np.abs(g2) - 1e-5 * np.abs(ag).max()).all()
 
 
+PIPELINES = ["splat", "tiles+splat", "tiles"]
+
+
+@pytest.mark.parametrize("pipeline", PIPELINES)
 @pytest.mark.parametrize("gt_dtype", ["f32", "u8"])
 @pytest.mark.parametrize("case", CASES[:5], ids=[c[0] for c in CASES[:5]])
-def test_fused_raster_step_parity(case, gt_dtype):
-    """raster_step == reference iteration (train_gaussians.py:81-102 with the "whole" L1 loss)."""
+def test_fused_raster_step_parity(case, gt_dtype, pipeline):
+    """raster_step == reference iteration (train_gaussians.py:81-102 with the "whole" L1 loss), for each of the
+    three fused pipelines (Gaussian-major with its exact stop-rule fallback, tile forward + Gaussian-major
+    backward, all tile-major)."""
     name, N, W, H, regime, seed, bs, view = case
     m, q, s, o, sc, op, vm, K = _inputs(N, W, H, regime, seed, bs, view)
     gt_u8 = synth.make_edge_map_u8(W, H, seed)
@@ -151,9 +162,12 @@ def test_fused_raster_step_parity(case, gt_dtype):
     model = EdgeGaussianSplatting(device=DEV)
     cam = OpenCVCamera.from_matrices(H, W, K, vm).to(DEV)
     model.set_params(m, s, q, o, viewcams=[cam])
+    model.pipeline = pipeline
     gt = _t(gt_u8) if gt_dtype == "u8" else _t(gt_f)
     for it in range(2):  # second call reuses the workspace and must give the same gradients
         loss = model.raster_step(0, gt)
+        assert model._ws.pipeline == pipeline
+        print(f"[{name}/{pipeline}] stopped tiles {int(model._ws.status[5])} / {model._ws.T}")
         assert abs(float(loss) - ref["loss"]) <= 2e-6 + 1e-5 * abs(ref["loss"]), (float(loss), ref["loss"])
         _check_grad(name, "v_means", model.means.grad.cpu().numpy(), ref["v_means"])
         _check_grad(name, "v_quats", model.quats.grad.cpu().numpy(), ref["v_quats"], 1e-6 * np.abs(ref["v_means"]).max())
