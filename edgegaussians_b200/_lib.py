@@ -59,7 +59,7 @@ def load(build_if_missing: bool = True):
     lib.eg_project_bwd.argtypes = [cfgp] + [P] * 9 + [c_int] + [P] * 7
     lib.eg_splat_bwd.argtypes = [cfgp] + [P] * 9 + [c_float] + [P] * 11
     lib.eg_splat_fwd.argtypes = [cfgp] + [P] * 5
-    lib.eg_splat_resolve.argtypes = [cfgp, P, P, c_int] + [P] * 7
+    lib.eg_splat_resolve.argtypes = [cfgp, P, P, c_int] + [P] * 8
     lib.eg_emit_flagged.argtypes = [cfgp] + [P] * 7
     lib.eg_make_seed.argtypes = [c_int64, P, P, c_int, P, P, P]
     lib.eg_reg_fwd_bwd.argtypes = [c_int, P, P, P, P, c_int, c_int, c_int, c_float, c_float, P, P, P, P, P]

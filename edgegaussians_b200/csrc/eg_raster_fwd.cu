@@ -194,13 +194,13 @@ __device__ void sort_large(u64 *__restrict__ gk, int L, u64 *s, int tid) {
 }
 
 template <int GT_KIND, bool WANT_LAST>
-__global__ void __launch_bounds__(RF_THREADS, 5) raster_fwd_kernel(
-    const eg_config cfg, int tw, const float4 *__restrict__ rec, const int32_t *__restrict__ tile_offsets,
-    u64 *__restrict__ keys, int32_t *__restrict__ flatten_ids, long long *__restrict__ isect_ids,
-    float *__restrict__ render0, float *__restrict__ alpha_out, int32_t *__restrict__ last_ids,
-    uint4 *__restrict__ cmask, const void *__restrict__ gt, double *__restrict__ loss_sum,
-    float *__restrict__ wpix, uint32_t *__restrict__ last_depth, int32_t *__restrict__ last_gid,
-    const int32_t *__restrict__ tile_stop, const int32_t *__restrict__ tile_cnt, int32_t *__restrict__ status) {
+__device__ __forceinline__ void raster_tile(
+    const eg_config &cfg, const int tw, const int tile, const bool flagged_only, const float4 *__restrict__ rec,
+    const int32_t *__restrict__ tile_offsets, u64 *__restrict__ keys, int32_t *__restrict__ flatten_ids,
+    long long *__restrict__ isect_ids, float *__restrict__ render0, float *__restrict__ alpha_out,
+    int32_t *__restrict__ last_ids, uint4 *__restrict__ cmask, const void *__restrict__ gt,
+    double *__restrict__ loss_sum, float *__restrict__ wpix, uint32_t *__restrict__ last_depth,
+    int32_t *__restrict__ last_gid, const int32_t *__restrict__ tile_cnt, int32_t *__restrict__ status) {
     __shared__ __align__(16) u64 sbuf[2 * SORT_CAP];  // sort exchange buffers, then the sorted ids
     __shared__ __align__(16) float4 sAB[2 * RF_THREADS];  // per Gaussian: (mean2d.x, mean2d.y, log2 opacity,
                                                           // sub-tile mask bits) , (folded conic fa, fb, fc, -)
@@ -208,14 +208,10 @@ __global__ void __launch_bounds__(RF_THREADS, 5) raster_fwd_kernel(
     uint32_t *sids = reinterpret_cast<uint32_t *>(sbuf);             // first 8 KB of the (dead) exchange buffers
     uint32_t *s_cm = reinterpret_cast<uint32_t *>(sbuf + SORT_CAP);  // second half: contribution masks [256][8]
 
-    if (status[EG_ST_OVERFLOW]) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile = blockIdx.x;
     const int tile_y = tile / tw, tile_x = tile - tile_y * tw;
-    // fallback of the Gaussian-major forward (eg_splat_fwd.cu): only the tiles eg_splat_resolve flagged, whose
-    // keys eg_emit_flagged appended to fixed-capacity buckets (count in tile_cnt, no scan)
-    const bool flagged_only = tile_stop != nullptr;
-    if (flagged_only && tile_stop[tile] == 0) return;
+    // flagged_only: fallback of the Gaussian-major forward (eg_splat_fwd.cu) -- the tile's keys were appended by
+    // eg_emit_flagged to its fixed-capacity bucket (count in tile_cnt, no scan)
     const int start = flagged_only ? tile * cfg.tile_capacity : tile_offsets[tile];
     const int L = flagged_only ? min(tile_cnt[tile], cfg.tile_capacity) : tile_offsets[tile + 1] - start;
 
@@ -400,12 +396,43 @@ __global__ void __launch_bounds__(RF_THREADS, 5) raster_fwd_kernel(
     }
 }
 
+template <int GT_KIND, bool WANT_LAST>
+__global__ void __launch_bounds__(RF_THREADS, 5) raster_fwd_kernel(
+    const eg_config cfg, int tw, const float4 *__restrict__ rec, const int32_t *__restrict__ tile_offsets,
+    u64 *__restrict__ keys, int32_t *__restrict__ flatten_ids, long long *__restrict__ isect_ids,
+    float *__restrict__ render0, float *__restrict__ alpha_out, int32_t *__restrict__ last_ids,
+    uint4 *__restrict__ cmask, const void *__restrict__ gt, double *__restrict__ loss_sum,
+    float *__restrict__ wpix, uint32_t *__restrict__ last_depth, int32_t *__restrict__ last_gid,
+    int32_t *__restrict__ status) {
+    if (status[EG_ST_OVERFLOW]) return;
+    raster_tile<GT_KIND, WANT_LAST>(cfg, tw, blockIdx.x, false, rec, tile_offsets, keys, flatten_ids, isect_ids, render0,
+                                    alpha_out, last_ids, cmask, gt, loss_sum, wpix, last_depth, last_gid, nullptr, status);
+}
+
+// Fallback of the Gaussian-major forward: a small persistent grid walks the list of flagged tiles (usually empty:
+// the kernel then costs a launch and nothing else).
+template <int GT_KIND>
+__global__ void __launch_bounds__(RF_THREADS, 5) raster_fwd_flagged_kernel(
+    const eg_config cfg, int tw, const float4 *__restrict__ rec, u64 *__restrict__ keys,
+    int32_t *__restrict__ flatten_ids, float *__restrict__ render0, float *__restrict__ alpha_out,
+    const void *__restrict__ gt, double *__restrict__ loss_sum, float *__restrict__ wpix,
+    uint32_t *__restrict__ last_depth, int32_t *__restrict__ last_gid, const int32_t *__restrict__ stop_list,
+    const int32_t *__restrict__ tile_cnt, int32_t *__restrict__ status) {
+    if (status[EG_ST_OVERFLOW]) return;
+    const int n = status[EG_ST_STOPPED];
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        __syncthreads();  // shared memory of the previous tile is dead
+        raster_tile<GT_KIND, true>(cfg, tw, stop_list[i], true, rec, nullptr, keys, flatten_ids, nullptr, render0,
+                                   alpha_out, nullptr, nullptr, gt, loss_sum, wpix, last_depth, last_gid, tile_cnt, status);
+    }
+}
+
 }  // namespace
 
 extern "C" int eg_raster_fwd(const eg_config *cfg, const float *rec, const int32_t *tile_offsets, uint64_t *keys,
                              int32_t *flatten_ids, int64_t *isect_ids, float *render0, float *alpha,
                              int32_t *last_ids, uint32_t *cmask, const void *gt, int gt_kind, double *loss_sum,
-                             float *wpix, uint32_t *last_depth, int32_t *last_gid, const int32_t *tile_stop,
+                             float *wpix, uint32_t *last_depth, int32_t *last_gid, const int32_t *stop_list,
                              const int32_t *tile_cnt, int32_t *status, void *stream) {
     if (cfg == nullptr || cfg->tile_size != EG_TILE) {
         eg_set_error("eg_raster_fwd: tile_size must be %d", EG_TILE);
@@ -419,11 +446,11 @@ extern "C" int eg_raster_fwd(const eg_config *cfg, const float *rec, const int32
         eg_set_error("eg_raster_fwd: last_depth and last_gid go together");
         return 1;
     }
-    if ((tile_stop == nullptr) != (tile_cnt == nullptr)) {
-        eg_set_error("eg_raster_fwd: tile_stop and tile_cnt go together");
+    if ((stop_list == nullptr) != (tile_cnt == nullptr)) {
+        eg_set_error("eg_raster_fwd: stop_list and tile_cnt go together");
         return 1;
     }
-    if (tile_stop == nullptr && tile_offsets == nullptr) {
+    if (stop_list == nullptr && tile_offsets == nullptr) {
         eg_set_error("eg_raster_fwd: tile_offsets is required");
         return 1;
     }
@@ -432,12 +459,30 @@ extern "C" int eg_raster_fwd(const eg_config *cfg, const float *rec, const int32
     eg_tile_grid(cfg->width, cfg->height, cfg->tile_size, &tw, &th);
     cudaStream_t s = (cudaStream_t)stream;
     const int grid = tw * th;
+    if (stop_list != nullptr) {  // flagged tiles only
+        if (last_depth == nullptr || isect_ids != nullptr || last_ids != nullptr || cmask != nullptr) {
+            eg_set_error("eg_raster_fwd: the flagged-tile mode writes last_depth / last_gid and no ids or masks");
+            return 1;
+        }
+        const int pgrid = grid < 148 * 5 ? grid : 148 * 5;
+#define EG_LAUNCHF(KIND)                                                                                          \
+    raster_fwd_flagged_kernel<KIND><<<pgrid, RF_THREADS, 0, s>>>(*cfg, tw, (const float4 *)rec, (u64 *)keys,       \
+                                                                 flatten_ids, render0, alpha, gt, loss_sum, wpix, \
+                                                                 last_depth, last_gid, stop_list, tile_cnt, status)
+        switch (gt_kind) {
+            case EG_GT_NONE: EG_LAUNCHF(EG_GT_NONE); break;
+            case EG_GT_F32: EG_LAUNCHF(EG_GT_F32); break;
+            case EG_GT_U8: EG_LAUNCHF(EG_GT_U8); break;
+            default: eg_set_error("eg_raster_fwd: bad gt_kind %d", gt_kind); return 1;
+        }
+#undef EG_LAUNCHF
+        return eg_check_launch("eg_raster_fwd/flagged");
+    }
 #define EG_LAUNCH2(KIND, WL)                                                                                     \
     raster_fwd_kernel<KIND, WL><<<grid, RF_THREADS, 0, s>>>(*cfg, tw, (const float4 *)rec, tile_offsets,         \
                                                             (u64 *)keys, flatten_ids, (long long *)isect_ids,    \
                                                             render0, alpha, last_ids, (uint4 *)cmask, gt,        \
-                                                            loss_sum, wpix, last_depth, last_gid, tile_stop,     \
-                                                            tile_cnt, status)
+                                                            loss_sum, wpix, last_depth, last_gid, status)
 #define EG_LAUNCH(KIND)                       \
     do {                                      \
         if (last_ids != nullptr || last_depth != nullptr) EG_LAUNCH2(KIND, true); \

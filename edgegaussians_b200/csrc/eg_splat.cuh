@@ -24,7 +24,8 @@ struct __align__(16) EgSplatG {
     float C;               // conic c
     unsigned depth_bits;   // float bits of the depth (sort key high word)
     int X0, X1;            // pixel columns [X0, X1) of the tile rectangle, clipped to the image
-    int ylo, start, gid, nrows;  // first row, index of its first row item in the warp's list, Gaussian id
+    int ylo, start, gid;   // first row, index of its first row item in the warp's list, Gaussian id
+    float inv2a;           // 0.5 / fa (< 0 for a proper conic)
 };
 
 // gsplat's per-pair test (rasterize_to_pixels): composited iff sigma >= 0 (p <= lo) and alpha >= 1/255
@@ -42,7 +43,6 @@ __device__ __forceinline__ bool eg_pair_valid_grad(float ov, float p, float lo, 
 __device__ __forceinline__ int eg_splat_setup(const eg_config &cfg, int tw, int th, int gid, const float4 r0,
                                               const float4 r1, int radius, EgSplatG &G) {
     G.gid = gid;
-    G.nrows = 0;
     G.start = 0;
     if (radius <= 0) return 0;
     const EgFold f = eg_fold(r1.x, r1.y, r1.z, r0.z);
@@ -56,6 +56,7 @@ __device__ __forceinline__ int eg_splat_setup(const eg_config &cfg, int tw, int 
     G.A = r1.x; G.B = r1.y; G.C = r1.z;
     G.depth_bits = __float_as_uint(r0.w);
     G.X0 = X0; G.X1 = X1;
+    G.inv2a = 0.5f / f.fa;
     // rows where max_x p(x, y) >= log2(1/255):  (fc - fb^2 / (4 fa)) dy^2 + lo >= L
     float ylo = (float)Y0, yhi = (float)(Y1 - 1);
     const float Kq = f.fc - f.fb * f.fb / (4.0f * f.fa);
@@ -66,8 +67,7 @@ __device__ __forceinline__ int eg_splat_setup(const eg_config &cfg, int tw, int 
     }
     if (!(yhi >= ylo)) return 0;
     G.ylo = (int)ylo;
-    G.nrows = (int)yhi - (int)ylo + 1;
-    return G.nrows;
+    return (int)yhi - (int)ylo + 1;
 }
 
 // lane = (Gaussian, row).  Conservative pixel span [xa, xb] of the row; false = empty.
@@ -76,9 +76,11 @@ __device__ __forceinline__ bool eg_row_span(const EgSplatG &G, float b1, float c
     if (G.fa < 0.0f) {
         const float disc = b1 * b1 - 4.0f * G.fa * (c0 - EG_L2AMIN_CONS);
         if (disc < 0.0f) return false;
-        const float inv = 0.5f / G.fa;  // < 0
+        const float inv = G.inv2a;  // 0.5 / fa < 0
         const float dxc = -b1 * inv;
-        const float w = -sqrtf(disc) * inv * 1.0001f + 0.02f;
+        float sq;
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(disc));  // the margins below dwarf its 2^-22 error
+        const float w = -sq * inv * 1.0001f + 0.02f;
         const float cx = G.mx - dxc - 0.5f;  // pixel index (continuous) of the row's maximum
         lo_x = fmaxf(lo_x, ceilf(cx - w));   // fmaxf / fminf drop a NaN operand: a NaN span is the full row
         hi_x = fminf(hi_x, floorf(cx + w));
@@ -88,11 +90,19 @@ __device__ __forceinline__ bool eg_row_span(const EgSplatG &G, float b1, float c
     return xb >= xa;
 }
 
-// smallest g in [0,32) with s_end[g] > item (s_end = inclusive prefix of the row counts; item < s_end[31])
-__device__ __forceinline__ int eg_find_owner(const int *s_end, int item) {
-    int g = 0;
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1)
-        if (s_end[g + s - 1] <= item) g += s;
-    return g;
-}
+// Row items of a warp's 32 Gaussians, without searching: the Gaussians that have rows are staged COMPACTED (index k
+// = rank among the non-empty ones), so their list ends e_k are strictly increasing.  For the batch of items
+// [base, base + 32) every Gaussian whose end falls in (base, base + 32] sets bit (end - base - 1) of a warp-wide
+// OR; the owner of item base + j is then  k_base + popc(mask & ((1 << j) - 1))  with k_base the number of ends <= base,
+// carried from batch to batch.  `end` / `nonempty` are the calling lane's values as a GAUSSIAN.
+struct EgOwnerIter {
+    int k_base;
+    __device__ __forceinline__ EgOwnerIter() : k_base(0) {}
+    __device__ __forceinline__ int owner(const int base, const int lane, const int end, const bool nonempty) {
+        const unsigned t = (unsigned)(end - base - 1);
+        const unsigned mask = __reduce_or_sync(0xffffffffu, (nonempty && t < 32u) ? (1u << t) : 0u);
+        const int k = k_base + __popc(mask & ((1u << lane) - 1u));
+        k_base += __popc(mask);
+        return k;
+    }
+};

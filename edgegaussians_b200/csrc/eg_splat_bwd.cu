@@ -139,9 +139,8 @@ __global__ void __launch_bounds__(SB_WARPS * 32) splat_bwd_kernel(
     float4 *__restrict__ grad2d_out,
     float *__restrict__ v_means, float *__restrict__ v_quats, float *__restrict__ v_scales,
     float *__restrict__ v_opacities, float *__restrict__ absgrad_accum) {
-    __shared__ EgSplatG s_g[SB_WARPS][32];
-    __shared__ int s_end[SB_WARPS][32];
-    __shared__ __align__(16) float s_acc[SB_WARPS][32][8];
+    __shared__ EgSplatG s_g[SB_WARPS][32];                   // compacted over the Gaussians that have rows
+    __shared__ __align__(16) float s_acc[SB_WARPS][32][8];   // same (compact) index
 
     if (status[EG_ST_OVERFLOW]) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -161,8 +160,6 @@ __global__ void __launch_bounds__(SB_WARPS * 32) splat_bwd_kernel(
         r1 = __ldg(rec + 2 * g + 1);
         opac_eff = r0.z;
         nrows = eg_splat_setup(cfg, tw, th, g, r0, r1, radius, G);
-    } else {
-        G.nrows = 0;
     }
     int incl = nrows;
 #pragma unroll
@@ -171,20 +168,22 @@ __global__ void __launch_bounds__(SB_WARPS * 32) splat_bwd_kernel(
         if (lane >= d) incl += t;
     }
     G.start = incl - nrows;
-    s_g[warp][lane] = G;
-    s_end[warp][lane] = incl;
+    const unsigned ne = __ballot_sync(0xffffffffu, nrows > 0);
+    const int kc = __popc(ne & ((1u << lane) - 1u));  // compact index of this lane's Gaussian (EgOwnerIter)
+    if (nrows > 0) s_g[warp][kc] = G;
 #pragma unroll
     for (int k = 0; k < 8; ++k) s_acc[warp][lane][k] = 0.0f;
     const int R = __shfl_sync(0xffffffffu, incl, 31);
     __syncwarp();
+    EgOwnerIter it;
 
     // ---------------- phase 2: lane = (Gaussian, row) ----------------
     for (int base = 0; base < R; base += 32) {
         const int item = base + lane;
         float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        int owner = 32;
+        int owner = it.owner(base, lane, incl, nrows > 0);
+        if (item >= R) owner = 32;
         if (item < R) {
-            owner = eg_find_owner(s_end[warp], item);
             const EgSplatG Go = s_g[warp][owner];
             const int y = Go.ylo + (item - Go.start);
             if (use_last) walk_row_bwd<true, ALIGNED>(Go, y, cfg.width, tw, wpix, last_depth, last_gid, tile_stop, v);
@@ -218,8 +217,8 @@ __global__ void __launch_bounds__(SB_WARPS * 32) splat_bwd_kernel(
     float vm[3] = {0.f, 0.f, 0.f}, vs[3] = {0.f, 0.f, 0.f}, vq[4] = {0.f, 0.f, 0.f, 0.f}, vo = 0.f;
     float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
     if (nrows > 0) {
-        const float4 a0 = *reinterpret_cast<const float4 *>(&s_acc[warp][lane][0]);
-        const float4 a1 = *reinterpret_cast<const float4 *>(&s_acc[warp][lane][4]);
+        const float4 a0 = *reinterpret_cast<const float4 *>(&s_acc[warp][kc][0]);
+        const float4 a1 = *reinterpret_cast<const float4 *>(&s_acc[warp][kc][4]);
         const float sc = seed_scale, asc = fabsf(seed_scale);
         g0 = make_float4(a0.x * sc, a0.y * sc, a0.z * asc, a0.w * asc);
         // v_opacity' = sum vis * v_alpha = -(sum v_sigma) / opacity'

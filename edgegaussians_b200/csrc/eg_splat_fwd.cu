@@ -51,10 +51,10 @@ __device__ __forceinline__ void walk_row_fwd(const EgSplatG &G, const int y, con
     const float b1 = eg_pow2row_b1(G.fb, dy), c0 = eg_pow2row_c0(G.fc, G.lo, dy);
     int xa, xb;
     if (!eg_row_span(G, b1, c0, xa, xb)) return;
-    float *row = logT + (size_t)y * (size_t)W;
-    const int cend = xb >> 2;
-    for (int c = xa >> 2; c <= cend; ++c) {
-        const int x = 4 * c;
+    int x = xa & ~3;
+    const int xend = xb & ~3;
+    float *ptr = logT + ((size_t)y * (size_t)W + (size_t)x);
+    for (; x <= xend; x += 4, ptr += 4) {
         const float px = (float)x + 0.5f;  // pixel centres x + 0.5 .. x + 3.5 are exact in fp32
         // ALIGNED: W % 4 == 0 and the tile rectangle's columns are multiples of 16, so an aligned chunk that
         // overlaps the span lies entirely inside the rectangle -- no per-pixel clipping needed
@@ -64,12 +64,12 @@ __device__ __forceinline__ void walk_row_fwd(const EgSplatG &G, const int y, con
         const float v3 = pair_fwd(G, b1, c0, px + 3.0f, ALIGNED || (x + 3 >= xa && x + 3 <= xb));
         if (ALIGNED) {
             if ((__float_as_uint(v0) | __float_as_uint(v1) | __float_as_uint(v2) | __float_as_uint(v3)) << 1)
-                eg_red_add_v4(row + x, v0, v1, v2, v3);
+                eg_red_add_v4(ptr, v0, v1, v2, v3);
         } else {
-            if (v0 != 0.0f) red_add_f32(row + x, v0);
-            if (v1 != 0.0f) red_add_f32(row + x + 1, v1);
-            if (v2 != 0.0f) red_add_f32(row + x + 2, v2);
-            if (v3 != 0.0f) red_add_f32(row + x + 3, v3);
+            if (v0 != 0.0f) red_add_f32(ptr, v0);
+            if (v1 != 0.0f) red_add_f32(ptr + 1, v1);
+            if (v2 != 0.0f) red_add_f32(ptr + 2, v2);
+            if (v3 != 0.0f) red_add_f32(ptr + 3, v3);
         }
     }
 }
@@ -81,7 +81,6 @@ __global__ void __launch_bounds__(SF_WARPS * 32) splat_fwd_kernel(const eg_confi
                                                                   float *__restrict__ logT,
                                                                   const int32_t *__restrict__ status) {
     __shared__ EgSplatG s_g[SF_WARPS][32];
-    __shared__ int s_end[SF_WARPS][32];
     if (status[EG_ST_OVERFLOW]) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = (blockIdx.x * SF_WARPS + warp) * 32 + lane;
@@ -90,8 +89,6 @@ __global__ void __launch_bounds__(SF_WARPS * 32) splat_fwd_kernel(const eg_confi
     if (g < cfg.n) {
         const int2 gi = __ldg(gint + g);
         nrows = eg_splat_setup(cfg, tw, th, g, __ldg(rec + 2 * g), __ldg(rec + 2 * g + 1), gi.x, G);
-    } else {
-        G.nrows = 0;
     }
     int incl = nrows;
 #pragma unroll
@@ -100,63 +97,68 @@ __global__ void __launch_bounds__(SF_WARPS * 32) splat_fwd_kernel(const eg_confi
         if (lane >= d) incl += t;
     }
     G.start = incl - nrows;
-    s_g[warp][lane] = G;
-    s_end[warp][lane] = incl;
+    const unsigned ne = __ballot_sync(0xffffffffu, nrows > 0);
+    if (nrows > 0) s_g[warp][__popc(ne & ((1u << lane) - 1u))] = G;  // compacted: see EgOwnerIter
     const int R = __shfl_sync(0xffffffffu, incl, 31);
     __syncwarp();
+    EgOwnerIter it;
     for (int base = 0; base < R; base += 32) {
         const int item = base + lane;
+        const int k = it.owner(base, lane, incl, nrows > 0);
         if (item < R) {
-            const int owner = eg_find_owner(s_end[warp], item);
-            const EgSplatG Go = s_g[warp][owner];
+            const EgSplatG Go = s_g[warp][k];
             walk_row_fwd<ALIGNED>(Go, Go.ylo + (item - Go.start), cfg.width, logT);
         }
     }
 }
 
+// Persistent: a few CTAs per SM stride over the tiles and issue ONE loss atomic each at the end (one atomic per
+// tile would serialise 7 500 fp64 additions on a single L2 address -- measured 60 us).
 template <int GT_KIND>
-__global__ void __launch_bounds__(256) splat_resolve_kernel(const eg_config cfg, const int tw,
+__global__ void __launch_bounds__(256) splat_resolve_kernel(const eg_config cfg, const int tw, const int n_tiles,
                                                             float *__restrict__ logT, const void *__restrict__ gt,
                                                             double *__restrict__ loss_sum, float *__restrict__ wpix,
                                                             float *__restrict__ render0, float *__restrict__ alpha_out,
                                                             int32_t *__restrict__ tile_stop,
+                                                            int32_t *__restrict__ stop_list,
                                                             int32_t *__restrict__ status) {
     __shared__ float s_red[8];
     if (status[EG_ST_OVERFLOW]) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile = blockIdx.x;
-    const int tile_y = tile / tw, tile_x = tile - tile_y * tw;
-    // a warp covers 2 rows x 16 pixels: each row segment is one 64-byte run
-    const int pxi = tile_x * EG_TILE + (tid & 15), pyi = tile_y * EG_TILE + (tid >> 4);
-    const bool inside = pxi < cfg.width && pyi < cfg.height;
-    const long long pix = (long long)pyi * cfg.width + pxi;
-    float T = 1.0f;
-    if (inside) {
-        T = eg_ex2(logT[pix]);
-        logT[pix] = 0.0f;  // clean for the next iteration's reductions
-    }
-    // some pixel of the tile may have hit gsplat's stop rule: the tile is redone exactly by eg_raster_fwd
-    if (__syncthreads_or(inside && !(T > EG_T_MIN * 1.001f))) {
-        if (tid == 0) {
-            tile_stop[tile] = 1;
-            atomicAdd(status + EG_ST_STOPPED, 1);
-        }
-        return;
-    }
     float absd = 0.0f;
-    if (inside) {
-        const float out = 1.0f - T;
-        if (alpha_out) alpha_out[pix] = out;
-        if (render0) render0[pix] = out;
-        if (GT_KIND != EG_GT_NONE) {
-            float gv;
-            if (GT_KIND == EG_GT_F32) gv = __ldg(reinterpret_cast<const float *>(gt) + pix);
-            else gv = __fdiv_rn((float)__ldg(reinterpret_cast<const unsigned char *>(gt) + pix), 255.0f);
-            const float d = fminf(fmaxf(out, 0.0f), 1.0f) - gv;
-            absd = fabsf(d);
-            const float sgn = (d > 0.0f) ? 1.0f : ((d < 0.0f) ? -1.0f : 0.0f);
-            const float pass = (out >= 0.0f && out <= 1.0f) ? 1.0f : 0.0f;
-            if (wpix) wpix[pix] = sgn * pass * T;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int tile_y = tile / tw, tile_x = tile - tile_y * tw;
+        // a warp covers 2 rows x 16 pixels: each row segment is one 64-byte run
+        const int pxi = tile_x * EG_TILE + (tid & 15), pyi = tile_y * EG_TILE + (tid >> 4);
+        const bool inside = pxi < cfg.width && pyi < cfg.height;
+        const long long pix = (long long)pyi * cfg.width + pxi;
+        float T = 1.0f;
+        if (inside) {
+            T = eg_ex2(logT[pix]);
+            logT[pix] = 0.0f;  // clean for the next iteration's reductions
+        }
+        // some pixel of the tile may have hit gsplat's stop rule: the tile is redone exactly by eg_raster_fwd
+        if (__syncthreads_or(inside && !(T > EG_T_MIN * 1.001f))) {
+            if (tid == 0) {
+                tile_stop[tile] = 1;
+                stop_list[atomicAdd(status + EG_ST_STOPPED, 1)] = tile;
+            }
+            continue;
+        }
+        if (inside) {
+            const float out = 1.0f - T;
+            if (alpha_out) alpha_out[pix] = out;
+            if (render0) render0[pix] = out;
+            if (GT_KIND != EG_GT_NONE) {
+                float gv;
+                if (GT_KIND == EG_GT_F32) gv = __ldg(reinterpret_cast<const float *>(gt) + pix);
+                else gv = __fdiv_rn((float)__ldg(reinterpret_cast<const unsigned char *>(gt) + pix), 255.0f);
+                const float d = fminf(fmaxf(out, 0.0f), 1.0f) - gv;
+                absd += fabsf(d);
+                const float sgn = (d > 0.0f) ? 1.0f : ((d < 0.0f) ? -1.0f : 0.0f);
+                const float pass = (out >= 0.0f && out <= 1.0f) ? 1.0f : 0.0f;
+                if (wpix) wpix[pix] = sgn * pass * T;
+            }
         }
     }
     if (GT_KIND != EG_GT_NONE && loss_sum != nullptr) {
@@ -165,10 +167,94 @@ __global__ void __launch_bounds__(256) splat_resolve_kernel(const eg_config cfg,
         if (lane == 0) s_red[warp] = absd;
         __syncthreads();
         if (tid == 0) {
-            float tsum = 0.0f;
+            double tsum = 0.0;
 #pragma unroll
-            for (int w = 0; w < 8; ++w) tsum += s_red[w];
-            if (tsum != 0.0f) atomicAdd(loss_sum, (double)tsum);
+            for (int w = 0; w < 8; ++w) tsum += (double)s_red[w];
+            if (tsum != 0.0) atomicAdd(loss_sum, tsum);
+        }
+    }
+}
+
+// Vectorised variant for W % 4 == 0 (the common case): a CTA handles 4 horizontally adjacent tiles per iteration
+// (64 x 16 pixels = 256 threads x 4 pixels), every access is a 128-bit one on a 256-byte contiguous row run, and
+// both loads of an iteration (accumulator, edge map) are issued before the first barrier.
+template <int GT_KIND>
+__global__ void __launch_bounds__(256) splat_resolve4_kernel(const eg_config cfg, const int tw, const int th,
+                                                             float *__restrict__ logT, const void *__restrict__ gt,
+                                                             double *__restrict__ loss_sum, float *__restrict__ wpix,
+                                                             float *__restrict__ render0, float *__restrict__ alpha_out,
+                                                             int32_t *__restrict__ tile_stop,
+                                                             int32_t *__restrict__ stop_list,
+                                                             int32_t *__restrict__ status) {
+    __shared__ float s_red[8];
+    __shared__ int s_flag[4];
+    if (status[EG_ST_OVERFLOW]) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row = tid >> 4, c4 = tid & 15, k = c4 >> 2;
+    const int ngx = (tw + 3) >> 2, n_groups = ngx * th;
+    float absd = 0.0f;
+    for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+        const int gy = grp / ngx, gx = grp - gy * ngx;
+        const int tile_x = gx * 4 + k;
+        const int x = gx * 64 + c4 * 4, y = gy * EG_TILE + row;
+        const bool inside = x < cfg.width && y < cfg.height;  // W % 4 == 0: the 4 pixels are in or out together
+        const long long pix = (long long)y * cfg.width + x;
+        if (tid < 4) s_flag[tid] = 0;
+        float4 l4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = l4;
+        if (inside) {
+            l4 = *reinterpret_cast<const float4 *>(logT + pix);
+            if (GT_KIND == EG_GT_F32) {
+                g4 = __ldg(reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(gt) + pix));
+            } else if (GT_KIND == EG_GT_U8) {
+                const uchar4 u = __ldg(reinterpret_cast<const uchar4 *>(reinterpret_cast<const unsigned char *>(gt) + pix));
+                g4 = make_float4(__fdiv_rn((float)u.x, 255.0f), __fdiv_rn((float)u.y, 255.0f),
+                                 __fdiv_rn((float)u.z, 255.0f), __fdiv_rn((float)u.w, 255.0f));
+            }
+        }
+        const float T[4] = {eg_ex2(l4.x), eg_ex2(l4.y), eg_ex2(l4.z), eg_ex2(l4.w)};
+        const float thr = EG_T_MIN * 1.001f;
+        const bool cand = inside && !(T[0] > thr && T[1] > thr && T[2] > thr && T[3] > thr);
+        __syncthreads();
+        if (cand) s_flag[k] = 1;  // some pixel of tile k may have hit gsplat's stop rule
+        __syncthreads();
+        const bool flagged = s_flag[k] != 0;
+        if (inside) *reinterpret_cast<float4 *>(logT + pix) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (flagged) {  // the tile is redone exactly by eg_raster_fwd
+            if (row == 0 && (c4 & 3) == 0 && tile_x < tw) {
+                const int tile = gy * tw + tile_x;
+                tile_stop[tile] = 1;
+                stop_list[atomicAdd(status + EG_ST_STOPPED, 1)] = tile;
+            }
+        } else if (inside) {
+            float o4[4], w4[4];
+            const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                o4[i] = 1.0f - T[i];
+                const float d = fminf(fmaxf(o4[i], 0.0f), 1.0f) - gv[i];
+                absd += fabsf(d);
+                const float sgn = (d > 0.0f) ? 1.0f : ((d < 0.0f) ? -1.0f : 0.0f);
+                const float pass = (o4[i] >= 0.0f && o4[i] <= 1.0f) ? 1.0f : 0.0f;
+                w4[i] = sgn * pass * T[i];
+            }
+            const float4 ov = make_float4(o4[0], o4[1], o4[2], o4[3]);
+            if (alpha_out) *reinterpret_cast<float4 *>(alpha_out + pix) = ov;
+            if (render0) *reinterpret_cast<float4 *>(render0 + pix) = ov;
+            if (GT_KIND != EG_GT_NONE && wpix)
+                *reinterpret_cast<float4 *>(wpix + pix) = make_float4(w4[0], w4[1], w4[2], w4[3]);
+        }
+        __syncthreads();  // s_flag is reset at the top of the next iteration
+    }
+    if (GT_KIND != EG_GT_NONE && loss_sum != nullptr) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) absd += __shfl_xor_sync(0xffffffffu, absd, d);
+        if (lane == 0) s_red[warp] = absd;
+        __syncthreads();
+        if (tid == 0) {
+            double tsum = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) tsum += (double)s_red[w];
+            if (tsum != 0.0) atomicAdd(loss_sum, tsum);
         }
     }
 }
@@ -228,22 +314,35 @@ extern "C" int eg_splat_fwd(const eg_config *cfg, const float *rec, const int32_
 }
 
 extern "C" int eg_splat_resolve(const eg_config *cfg, float *logT, const void *gt, int gt_kind, double *loss_sum,
-                                float *wpix, float *render0, float *alpha, int32_t *tile_stop, int32_t *status,
-                                void *stream) {
+                                float *wpix, float *render0, float *alpha, int32_t *tile_stop, int32_t *stop_list,
+                                int32_t *status, void *stream) {
     if (cfg == nullptr || cfg->tile_size != EG_TILE) {
         eg_set_error("eg_splat_resolve: tile_size must be %d", EG_TILE);
         return 1;
     }
-    if (logT == nullptr || tile_stop == nullptr || status == nullptr) {
-        eg_set_error("eg_splat_resolve: logT, tile_stop and status are required");
+    if (logT == nullptr || tile_stop == nullptr || stop_list == nullptr || status == nullptr) {
+        eg_set_error("eg_splat_resolve: logT, tile_stop, stop_list and status are required");
         return 1;
     }
     if (gt == nullptr) gt_kind = EG_GT_NONE;
     int tw, th;
     eg_tile_grid(cfg->width, cfg->height, cfg->tile_size, &tw, &th);
     cudaStream_t s = (cudaStream_t)stream;
-#define EG_RS_LAUNCH(KIND) \
-    splat_resolve_kernel<KIND><<<tw * th, 256, 0, s>>>(*cfg, tw, logT, gt, loss_sum, wpix, render0, alpha, tile_stop, status)
+    const int n_tiles = tw * th;
+    auto al16 = [](const void *p) { return ((uintptr_t)p & 15) == 0; };
+    const bool vec = cfg->width % 4 == 0 && al16(logT) && al16(wpix) && al16(render0) && al16(alpha) &&
+                     (gt_kind == EG_GT_U8 ? ((uintptr_t)gt & 3) == 0 : al16(gt));
+    const int n_units = vec ? ((tw + 3) / 4) * th : n_tiles;
+    const int grid = n_units < 148 * 8 ? n_units : 148 * 8;
+#define EG_RS_LAUNCH(KIND)                                                                                          \
+    do {                                                                                                            \
+        if (vec)                                                                                                    \
+            splat_resolve4_kernel<KIND><<<grid, 256, 0, s>>>(*cfg, tw, th, logT, gt, loss_sum, wpix, render0,       \
+                                                             alpha, tile_stop, stop_list, status);                  \
+        else                                                                                                        \
+            splat_resolve_kernel<KIND><<<grid, 256, 0, s>>>(*cfg, tw, n_tiles, logT, gt, loss_sum, wpix, render0,   \
+                                                            alpha, tile_stop, stop_list, status);                   \
+    } while (0)
     switch (gt_kind) {
         case EG_GT_NONE: EG_RS_LAUNCH(EG_GT_NONE); break;
         case EG_GT_F32: EG_RS_LAUNCH(EG_GT_F32); break;

@@ -70,6 +70,7 @@ class RasterStepWorkspace:
         # status | loss accumulator | tile_stop | tile_cnt | padded tile counters share one allocation: the
         # Gaussian-major pipeline clears only the small head, the tile pipeline all of it, with one memset each
         head = _lib.EG_ST_WORDS + 2 + 2 * T
+        self.stop_list = torch.empty(T, dtype=i32, device=device)  # ids of the tiles flagged by eg_splat_resolve
         self.zero_block = torch.zeros(head + T * _lib.EG_CNT_STRIDE, dtype=i32, device=device)
         self.zero_head = self.zero_block[:head]
         self.status = self.zero_block[:_lib.EG_ST_WORDS]
@@ -348,14 +349,14 @@ class EdgeGaussianSplatting(torch.nn.Module):
             chk(lib.eg_splat_fwd(c, _p(ws.rec), _p(ws.gint), _p(ws.logT), _p(ws.status), s), "eg_splat_fwd")
             cb("splat_fwd")
             chk(lib.eg_splat_resolve(c, _p(ws.logT), _p(gt), gt_kind, _p(ws.loss_sum), _p(ws.wpix), render0, None,
-                                     _p(ws.tile_stop), _p(ws.status), s), "eg_splat_resolve")
+                                     _p(ws.tile_stop), _p(ws.stop_list), _p(ws.status), s), "eg_splat_resolve")
             cb("splat_resolve")
             # exact redo of the tiles in which a pixel may have hit gsplat's stop rule (both return at once if none)
             chk(lib.eg_emit_flagged(c, _p(ws.rec), _p(ws.gint), _p(ws.tile_stop), _p(ws.tile_cnt), _p(ws.keys),
                                     _p(ws.status), s), "eg_emit_flagged")
             chk(lib.eg_raster_fwd(c, _p(ws.rec), None, _p(ws.keys), _p(ws.flatten_ids), None, render0, None, None, None,
                                   _p(gt), gt_kind, _p(ws.loss_sum), _p(ws.wpix), _p(ws.last_depth), _p(ws.last_gid),
-                                  _p(ws.tile_stop), _p(ws.tile_cnt), _p(ws.status), s), "eg_raster_fwd")
+                                  _p(ws.stop_list), _p(ws.tile_cnt), _p(ws.status), s), "eg_raster_fwd")
             cb("stop_fallback")
             tile_stop = _p(ws.tile_stop)
         else:

@@ -127,14 +127,15 @@ int eg_bin(const eg_config *cfg, int32_t *tile_counts, int32_t *tile_offsets, in
  * last_depth [P] u32 / last_gid [P] i32 (both or neither): sort key (depth bits, Gaussian id) of the last
  * Gaussian composited by each pixel that hit the transmittance stop, (0xffffffff, -1) elsewhere -- the
  * per-pixel cut-off eg_splat_bwd needs; status[EG_ST_STOPPED] counts the tiles that contain such pixels.
- * tile_stop [T] i32 / tile_cnt [T] i32 (both or neither): fallback mode of the Gaussian-major forward -- only the
- * tiles flagged in tile_stop are processed, their keys are the first tile_cnt[t] entries of bucket t
- * (eg_emit_flagged), always sorted; tile_offsets is then unused and flatten_ids needs T * tile_capacity entries.
+ * stop_list [T] i32 / tile_cnt [T] i32 (both or neither): fallback mode of the Gaussian-major forward -- only the
+ * status[EG_ST_STOPPED] tiles listed in stop_list (eg_splat_resolve) are processed by a small persistent grid,
+ * their keys are the first tile_cnt[t] entries of bucket t (eg_emit_flagged), always sorted; tile_offsets is then
+ * unused, flatten_ids needs T * tile_capacity entries, last_depth / last_gid are required.
  * Any of render0 / alpha / last_ids / isect_ids / cmask / gt / loss_sum / wpix / last_* / tile_* may be NULL. */
 int eg_raster_fwd(const eg_config *cfg, const float *rec, const int32_t *tile_offsets, uint64_t *keys,
                   int32_t *flatten_ids, int64_t *isect_ids, float *render0, float *alpha,
                   int32_t *last_ids, uint32_t *cmask, const void *gt, int gt_kind, double *loss_sum,
-                  float *wpix, uint32_t *last_depth, int32_t *last_gid, const int32_t *tile_stop,
+                  float *wpix, uint32_t *last_depth, int32_t *last_gid, const int32_t *stop_list,
                   const int32_t *tile_cnt, int32_t *status, void *stream);
 
 /* K6: compositing backward with abs-grad.  Replaces gsplat rasterize_to_pixels bwd.
@@ -165,15 +166,17 @@ int eg_project_bwd(const eg_config *cfg, const float *means, const float *quats,
  *                     gsplat's tile-rectangle / sigma / alpha tests (red.global.add.v4.f32, no tile lists);
  *   eg_splat_resolve  per 16x16 tile: T = 2^logT, render = alpha = 1 - T, fused clamp + "whole" L1 loss + backward
  *                     seed exactly as eg_raster_fwd (loss_sum, wpix), logT re-zeroed.  A tile in which some
- *                     pixel's T is within 0.1 % of gsplat's stop threshold 1e-4 is NOT resolved: tile_stop[t] = 1
- *                     and status[EG_ST_STOPPED] += 1 (tile_stop zeroed by the caller);
+ *                     pixel's T is within 0.1 % of gsplat's stop threshold 1e-4 is NOT resolved: tile_stop[t] = 1,
+ *                     its id is appended to stop_list [T] and status[EG_ST_STOPPED] += 1 (tile_stop zeroed by
+ *                     the caller);
  *   eg_emit_flagged   appends the keys of the Gaussians touching flagged tiles to keys [T, tile_capacity]
  *                     (cursor tile_cnt [T] i32, zeroed by the caller); then eg_raster_fwd(tile_stop, tile_cnt)
  *                     redoes exactly those tiles in sorted order.  Both return at once when nothing is flagged. */
 int eg_splat_fwd(const eg_config *cfg, const float *rec, const int32_t *gint, float *logT, const int32_t *status,
                  void *stream);
 int eg_splat_resolve(const eg_config *cfg, float *logT, const void *gt, int gt_kind, double *loss_sum, float *wpix,
-                     float *render0, float *alpha, int32_t *tile_stop, int32_t *status, void *stream);
+                     float *render0, float *alpha, int32_t *tile_stop, int32_t *stop_list, int32_t *status,
+                     void *stream);
 int eg_emit_flagged(const eg_config *cfg, const float *rec, const int32_t *gint, const int32_t *tile_stop,
                     int32_t *tile_cnt, uint64_t *keys, int32_t *status, void *stream);
 
