@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--no-lazy-sort", action="store_true", help="always sort every tile (gsplat order) in the tile pipelines")
     ap.add_argument("--pipeline", default="auto", choices=["auto", "splat", "tiles+splat", "tiles"],
                     help="fused-step pipeline (edge_gs.enqueue_raster_step); auto = what training would run")
+    ap.add_argument("--allreduce-chunks", type=int, default=4,
+                    help="N > 1: Gaussian ranges of the backward whose all-reduce overlaps the next range")
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
     return ap.parse_args()
 
@@ -221,7 +223,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     N, W, H, V = args.n, args.width, args.height, args.views
     P = W * H
@@ -235,7 +238,8 @@ def run_b200(args):
     model.lazy_sort = False if args.no_lazy_sort else "auto"
     model.pipeline = args.pipeline
 
-    step = GraphedRasterStep(model, W, H, n_slots=V, gt_dtype=torch.uint8, allreduce=world > 1)
+    step = GraphedRasterStep(model, W, H, n_slots=V, gt_dtype=torch.uint8, allreduce=world > 1,
+                             allreduce_chunks=args.allreduce_chunks)
     host_vm = [torch.from_numpy(vms[v]).pin_memory() for v in my_views]
     host_K = [torch.from_numpy(Ks[v]).pin_memory() for v in my_views]
     host_gt = [torch.from_numpy(g).pin_memory() for g in gts_u8]
@@ -292,11 +296,14 @@ def run_b200(args):
     hot_ms = e0.elapsed_time(e1)
     # the timed region lasts only tens of milliseconds: keep the same load running (untimed) for about a second so
     # that the nvidia-smi sampler (100 ms period) sees the clocks / throttle reasons this workload runs at
-    t_end = time.perf_counter() + 1.2
-    i = 0
-    while time.perf_counter() < t_end:
-        flush(); one_step(i); i += 1
-        if i % 64 == 0:
+    # (a fixed iteration COUNT agreed by all ranks: every step holds a collective, so a time-based loop would
+    # run a different number of all-reduces per rank and dead-lock)
+    n_cont = torch.tensor([max(32, min(20000, int(1200.0 * args.steps / max(total_ms, 1e-3))))], device=dev)
+    if world > 1:
+        dist.broadcast(n_cont, src=0)
+    for i in range(int(n_cont[0])):
+        flush(); one_step(i)
+        if i % 64 == 63:
             torch.cuda.synchronize()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -398,7 +405,7 @@ def run_b200(args):
                                                   "tiles": " (tile binning + per-tile sort/compositing, tile-major backward)"}[ws.pipeline],
                        "stopped_tiles": int(ws.status[5]),
                        "tile_sort": ("n/a" if ws.pipeline == "splat" else "lazy (only tiles near the transmittance stop threshold)" if model._use_lazy() else "every tile"),
-                       "execution": f"CUDA graph replay per iteration (1 memset + {len(kernels)} kernels: {', '.join(kernels)})" + ((", + NCCL all-reduce of the 11N fp32 gradient buffer " + ("captured in the graph" if step.allreduce_in_graph else "issued after the replay")) if world > 1 else ""),
+                       "execution": f"CUDA graph replay per iteration (1 memset + {len(kernels)} kernels: {', '.join(kernels)})" + ((", + NCCL all-reduce of the 11N fp32 gradient buffer " + (f"in {step.allreduce_chunks} Gaussian ranges on a side stream, overlapped with the backward of the next range" if step.chunked else "issued after the replay")) if world > 1 else ""),
                        "parallelism": f"view-sharded dp{world}" if world > 1 else "single GPU"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic_bytes(dom + "_kernel"), "peak_source": peak_src,

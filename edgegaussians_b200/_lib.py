@@ -57,7 +57,7 @@ def load(build_if_missing: bool = True):
     lib.eg_raster_fwd.argtypes = [cfgp] + [P] * 10 + [c_int] + [P] * 8
     lib.eg_raster_bwd.argtypes = [cfgp] + [P] * 6 + [c_int, P, P, c_float, P, P, P]
     lib.eg_project_bwd.argtypes = [cfgp] + [P] * 9 + [c_int] + [P] * 7
-    lib.eg_splat_bwd.argtypes = [cfgp] + [P] * 9 + [c_float] + [P] * 11
+    lib.eg_splat_bwd.argtypes = [cfgp] + [P] * 9 + [c_float] + [P] * 4 + [c_int, c_int] + [P] * 7
     lib.eg_splat_fwd.argtypes = [cfgp] + [P] * 5
     lib.eg_splat_resolve.argtypes = [cfgp, P, P, c_int] + [P] * 8
     lib.eg_emit_flagged.argtypes = [cfgp] + [P] * 7

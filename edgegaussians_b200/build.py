@@ -18,6 +18,7 @@ SOURCES = ["eg_api.cu", "eg_project_fwd.cu", "eg_bin.cu", "eg_raster_fwd.cu", "e
            "eg_project_bwd.cu", "eg_reg.cu", "eg_knn.cu", "eg_adam.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
+NVCC_FLAGS += os.environ.get("EG_NVCC_EXTRA", "").split()  # tuning experiments, e.g. -DEG_ROWS_PER_ITEM=4
 
 
 def _nvcc() -> str:

@@ -18,14 +18,23 @@
 // log2(1/255) minus a margin that covers ex2.approx / lg2.approx error: only used to BOUND spans
 #define EG_L2AMIN_CONS (-7.9965f)
 
+// consecutive pixel rows of one Gaussian handled by one lane per work item: amortises the per-item overhead
+// (owner lookup, staging fetch, segmented reduction) and evens out the per-lane work
+#ifndef EG_ROWS_PER_ITEM
+#define EG_ROWS_PER_ITEM 2
+#endif
+
 struct __align__(16) EgSplatG {
     float mx, my, fa, fb;  // mean2d, folded conic (eg_fold)
     float fc, lo, A, B;    // ..., log2(opacity'), conic a, b
     float C;               // conic c
     unsigned depth_bits;   // float bits of the depth (sort key high word)
-    int X0, X1;            // pixel columns [X0, X1) of the tile rectangle, clipped to the image
-    int ylo, start, gid;   // first row, index of its first row item in the warp's list, Gaussian id
+    int X01;               // pixel columns [X0, X1) of the tile rectangle, clipped to the image: X0 | X1 << 16
+    int nrows;             // pixel rows [ylo, ylo + nrows)
+    int ylo, start, gid;   // first row, index of its first work item in the warp's list, Gaussian id
     float inv2a;           // 0.5 / fa (< 0 for a proper conic)
+    __device__ __forceinline__ int X0() const { return X01 & 0xffff; }
+    __device__ __forceinline__ int X1() const { return (int)((unsigned)X01 >> 16); }
 };
 
 // gsplat's per-pair test (rasterize_to_pixels): composited iff sigma >= 0 (p <= lo) and alpha >= 1/255
@@ -39,11 +48,39 @@ __device__ __forceinline__ bool eg_pair_valid_grad(float ov, float p, float lo, 
     return in_span && p <= lo && (__float_as_uint(ov) - lo_bits) <= (hi_bits - lo_bits);
 }
 
-// lane = Gaussian.  Returns the number of pixel rows the Gaussian can touch (0 = none).
+// v if the pair is composited with an unclamped alpha (eg_pair_valid_grad), else 0 -- as ONE predicate chain
+// (integer range check, float compare AND-ed into the same predicate, select), which nvcc otherwise expands into
+// a chain of selects
+__device__ __forceinline__ float eg_select_valid_grad(float v, float ov, float p, float lo) {
+    float r;
+    asm("{\n\t.reg .pred q;\n\t.reg .u32 t;\n\t"
+        "sub.u32 t, %1, 0x3b808081;\n\t"
+        "setp.le.u32 q, t, 0x03ff3df6;\n\t"
+        "setp.le.and.f32 q, %2, %3, q;\n\t"
+        "selp.f32 %0, %4, 0f00000000, q;\n\t}"
+        : "=f"(r)
+        : "r"(__float_as_uint(ov)), "f"(p), "f"(lo), "f"(v));
+    return r;
+}
+// same for the forward's test (eg_pair_valid): alpha >= 1/255  <=>  bits(ov) - bits(1/255) <= bits(+inf) - bits(1/255)
+__device__ __forceinline__ float eg_select_valid(float v, float ov, float p, float lo) {
+    float r;
+    asm("{\n\t.reg .pred q;\n\t.reg .u32 t;\n\t"
+        "sub.u32 t, %1, 0x3b808081;\n\t"
+        "setp.le.u32 q, t, 0x43ff7f7f;\n\t"
+        "setp.le.and.f32 q, %2, %3, q;\n\t"
+        "selp.f32 %0, %4, 0f00000000, q;\n\t}"
+        : "=f"(r)
+        : "r"(__float_as_uint(ov)), "f"(p), "f"(lo), "f"(v));
+    return r;
+}
+
+// lane = Gaussian.  Returns the number of work items (groups of EG_ROWS_PER_ITEM pixel rows) of the Gaussian, 0 = none.
 __device__ __forceinline__ int eg_splat_setup(const eg_config &cfg, int tw, int th, int gid, const float4 r0,
                                               const float4 r1, int radius, EgSplatG &G) {
     G.gid = gid;
     G.start = 0;
+    G.nrows = 0;
     if (radius <= 0) return 0;
     const EgFold f = eg_fold(r1.x, r1.y, r1.z, r0.z);
     if (!(f.lo >= EG_L2AMIN_CONS)) return 0;  // opacity' < 1/255: alpha >= 1/255 can never hold
@@ -55,7 +92,7 @@ __device__ __forceinline__ int eg_splat_setup(const eg_config &cfg, int tw, int 
     G.mx = r0.x; G.my = r0.y; G.fa = f.fa; G.fb = f.fb; G.fc = f.fc; G.lo = f.lo;
     G.A = r1.x; G.B = r1.y; G.C = r1.z;
     G.depth_bits = __float_as_uint(r0.w);
-    G.X0 = X0; G.X1 = X1;
+    G.X01 = X0 | (X1 << 16);  // image sides < 65536 (checked by the host wrappers)
     G.inv2a = 0.5f / f.fa;
     // rows where max_x p(x, y) >= log2(1/255):  (fc - fb^2 / (4 fa)) dy^2 + lo >= L
     float ylo = (float)Y0, yhi = (float)(Y1 - 1);
@@ -67,12 +104,13 @@ __device__ __forceinline__ int eg_splat_setup(const eg_config &cfg, int tw, int 
     }
     if (!(yhi >= ylo)) return 0;
     G.ylo = (int)ylo;
-    return (int)yhi - (int)ylo + 1;
+    G.nrows = (int)yhi - (int)ylo + 1;
+    return (G.nrows + EG_ROWS_PER_ITEM - 1) / EG_ROWS_PER_ITEM;
 }
 
 // lane = (Gaussian, row).  Conservative pixel span [xa, xb] of the row; false = empty.
 __device__ __forceinline__ bool eg_row_span(const EgSplatG &G, float b1, float c0, int &xa, int &xb) {
-    float lo_x = (float)G.X0, hi_x = (float)(G.X1 - 1);
+    float lo_x = (float)G.X0(), hi_x = (float)(G.X1() - 1);
     if (G.fa < 0.0f) {
         const float disc = b1 * b1 - 4.0f * G.fa * (c0 - EG_L2AMIN_CONS);
         if (disc < 0.0f) return false;

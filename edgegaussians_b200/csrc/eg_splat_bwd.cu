@@ -55,7 +55,7 @@ struct RowAcc {
     float S0, S1, S2, ax, ay;
 };
 
-template <bool HAS_LAST>
+template <bool HAS_LAST, bool CLIP>
 __device__ __forceinline__ void pair_bwd(const EgSplatG &G, const float b1, const float c0, const float Bdy,
                                          const float Cdy, const float px, const bool in_span, const float w,
                                          const unsigned dl, const int *__restrict__ gid_px, RowAcc &r) {
@@ -63,14 +63,18 @@ __device__ __forceinline__ void pair_bwd(const EgSplatG &G, const float b1, cons
     const float p = eg_pow2row(G.fa, b1, c0, dx);  // log2(opacity * exp(-sigma)), bit-identical to the forward's
     const float ov = eg_ex2(p);
     // composited (sigma >= 0, alpha >= 1/255) and alpha not clamped (gsplat: no gradient through the clamp)
-    bool valid = eg_pair_valid_grad(ov, p, G.lo, in_span);
-    if (HAS_LAST) {
-        if (valid && G.depth_bits >= dl)  // rare: at or behind the pixel's last composited Gaussian
-            valid = G.depth_bits == dl && G.gid <= __ldg(gid_px);
-    }
     const float ra = eg_rcp(1.0f - ov);
     float vs = (ov * w) * ra;  // -v_sigma = alpha * T_final * seed / (1 - alpha); the sign is applied per row
-    vs = valid ? vs : 0.0f;
+    if (!HAS_LAST && !CLIP) {
+        vs = eg_select_valid_grad(vs, ov, p, G.lo);
+    } else {
+        bool valid = eg_pair_valid_grad(ov, p, G.lo, in_span);
+        if (HAS_LAST) {
+            if (valid && G.depth_bits >= dl)  // rare: at or behind the pixel's last composited Gaussian
+                valid = G.depth_bits == dl && G.gid <= __ldg(gid_px);
+        }
+        vs = valid ? vs : 0.0f;
+    }
     const float vd = vs * dx;
     r.S0 += vs;
     r.S1 += vd;
@@ -108,30 +112,30 @@ __device__ __forceinline__ void walk_row_bwd(const EgSplatG &G, const int y, con
             }
             const float px = (float)x + 0.5f;  // pixel centres x + 0.5 .. x + 3.5 are exact in fp32
             // ALIGNED: an aligned chunk that overlaps the span lies inside the tile rectangle (see eg_splat_fwd.cu)
-            pair_bwd<HAS_LAST>(G, b1, c0, Bdy, Cdy, px, ALIGNED || (x >= xa && x <= xb), w4.x, d4.x, grow + x, r);
-            pair_bwd<HAS_LAST>(G, b1, c0, Bdy, Cdy, px + 1.0f, ALIGNED || (x + 1 >= xa && x + 1 <= xb), w4.y, d4.y,
+            pair_bwd<HAS_LAST, !ALIGNED>(G, b1, c0, Bdy, Cdy, px, ALIGNED || (x >= xa && x <= xb), w4.x, d4.x, grow + x, r);
+            pair_bwd<HAS_LAST, !ALIGNED>(G, b1, c0, Bdy, Cdy, px + 1.0f, ALIGNED || (x + 1 >= xa && x + 1 <= xb), w4.y, d4.y,
                                grow + x + 1, r);
-            pair_bwd<HAS_LAST>(G, b1, c0, Bdy, Cdy, px + 2.0f, ALIGNED || (x + 2 >= xa && x + 2 <= xb), w4.z, d4.z,
+            pair_bwd<HAS_LAST, !ALIGNED>(G, b1, c0, Bdy, Cdy, px + 2.0f, ALIGNED || (x + 2 >= xa && x + 2 <= xb), w4.z, d4.z,
                                grow + x + 2, r);
-            pair_bwd<HAS_LAST>(G, b1, c0, Bdy, Cdy, px + 3.0f, ALIGNED || (x + 3 >= xa && x + 3 <= xb), w4.w, d4.w,
+            pair_bwd<HAS_LAST, !ALIGNED>(G, b1, c0, Bdy, Cdy, px + 3.0f, ALIGNED || (x + 3 >= xa && x + 3 <= xb), w4.w, d4.w,
                                grow + x + 3, r);
             w4 = wn;
         }
     }
-    // row moments (of -v_sigma) -> (v_mean2d.x, .y, absgrad.x, .y, v_conic.a, .b, .c, sum v_sigma)
-    v[0] = -fmaf(G.A, r.S1, Bdy * r.S0);
-    v[1] = -fmaf(G.B, r.S1, Cdy * r.S0);
-    v[2] = r.ax;
-    v[3] = r.ay;
-    v[4] = -0.5f * r.S2;
-    v[5] = -dy * r.S1;
-    v[6] = -0.5f * dy * dy * r.S0;
-    v[7] = -r.S0;
+    // row moments (of -v_sigma) -> (v_mean2d.x, .y, absgrad.x, .y, v_conic.a, .b, .c, sum v_sigma), accumulated
+    v[0] -= fmaf(G.A, r.S1, Bdy * r.S0);
+    v[1] -= fmaf(G.B, r.S1, Cdy * r.S0);
+    v[2] += r.ax;
+    v[3] += r.ay;
+    v[4] -= 0.5f * r.S2;
+    v[5] -= dy * r.S1;
+    v[6] -= 0.5f * dy * dy * r.S0;
+    v[7] -= r.S0;
 }
 
 template <bool RAW, bool ALIGNED>
 __global__ void __launch_bounds__(SB_WARPS * 32) splat_bwd_kernel(
-    const eg_config cfg, const int tw, const int th, const float *__restrict__ means, const float *__restrict__ quats,
+    const eg_config cfg, const int g_begin, const int g_end, const int tw, const int th, const float *__restrict__ means, const float *__restrict__ quats,
     const float *__restrict__ scales, const float *__restrict__ opacities, const float *__restrict__ viewmat,
     const float *__restrict__ Kmat, const float4 *__restrict__ rec, const int2 *__restrict__ gint,
     const float *__restrict__ wpix, const float seed_scale, const unsigned *__restrict__ last_depth,
@@ -144,8 +148,8 @@ __global__ void __launch_bounds__(SB_WARPS * 32) splat_bwd_kernel(
 
     if (status[EG_ST_OVERFLOW]) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = (blockIdx.x * SB_WARPS + warp) * 32 + lane;
-    const bool live = g < cfg.n;
+    const int g = g_begin + (blockIdx.x * SB_WARPS + warp) * 32 + lane;
+    const bool live = g < g_end;
     const bool use_last = last_depth != nullptr && last_gid != nullptr && status[EG_ST_STOPPED] != 0;
 
     // ---------------- phase 1: lane = Gaussian ----------------
@@ -159,7 +163,7 @@ __global__ void __launch_bounds__(SB_WARPS * 32) splat_bwd_kernel(
         const float4 r0 = __ldg(rec + 2 * g);
         r1 = __ldg(rec + 2 * g + 1);
         opac_eff = r0.z;
-        nrows = eg_splat_setup(cfg, tw, th, g, r0, r1, radius, G);
+        nrows = eg_splat_setup(cfg, tw, th, g, r0, r1, radius, G);  // work items (row groups)
     }
     int incl = nrows;
 #pragma unroll
@@ -185,9 +189,14 @@ __global__ void __launch_bounds__(SB_WARPS * 32) splat_bwd_kernel(
         if (item >= R) owner = 32;
         if (item < R) {
             const EgSplatG Go = s_g[warp][owner];
-            const int y = Go.ylo + (item - Go.start);
-            if (use_last) walk_row_bwd<true, ALIGNED>(Go, y, cfg.width, tw, wpix, last_depth, last_gid, tile_stop, v);
-            else walk_row_bwd<false, ALIGNED>(Go, y, cfg.width, tw, wpix, nullptr, nullptr, nullptr, v);
+            const int r0 = EG_ROWS_PER_ITEM * (item - Go.start);
+#pragma unroll
+            for (int r = 0; r < EG_ROWS_PER_ITEM; ++r) {
+                if (r0 + r >= Go.nrows) break;
+                const int y = Go.ylo + r0 + r;
+                if (use_last) walk_row_bwd<true, ALIGNED>(Go, y, cfg.width, tw, wpix, last_depth, last_gid, tile_stop, v);
+                else walk_row_bwd<false, ALIGNED>(Go, y, cfg.width, tw, wpix, nullptr, nullptr, nullptr, v);
+            }
         }
         // segmented sum over the (contiguous) lanes that share an owner
 #pragma unroll
@@ -261,7 +270,7 @@ extern "C" int eg_splat_bwd(const eg_config *cfg, const float *means, const floa
                             const float *opacities, const float *viewmat, const float *K, const float *rec,
                             const int32_t *gint, const float *wpix, float seed_scale, const uint32_t *last_depth,
                             const int32_t *last_gid, const int32_t *tile_stop, const int32_t *status,
-                            float *grad2d_out, float *v_means,
+                            int g_begin, int g_end, float *grad2d_out, float *v_means,
                             float *v_quats, float *v_scales, float *v_opacities, float *absgrad_accum, void *stream) {
     if (cfg == nullptr || cfg->tile_size != EG_TILE) {
         eg_set_error("eg_splat_bwd: tile_size must be %d", EG_TILE);
@@ -275,15 +284,21 @@ extern "C" int eg_splat_bwd(const eg_config *cfg, const float *means, const floa
         eg_set_error("eg_splat_bwd: last_depth and last_gid go together");
         return 1;
     }
-    if (cfg->n <= 0) return 0;
+    if (g_end < 0 || g_end > cfg->n) g_end = cfg->n;
+    if (g_begin < 0) g_begin = 0;
+    if (g_begin >= g_end) return 0;
+    if (cfg->width >= 65536 || cfg->height >= 65536) {
+        eg_set_error("eg_splat_bwd: image sides must be < 65536");
+        return 1;
+    }
     int tw, th;
     eg_tile_grid(cfg->width, cfg->height, cfg->tile_size, &tw, &th);
-    const int block = SB_WARPS * 32, grid = (cfg->n + block - 1) / block;
+    const int block = SB_WARPS * 32, grid = (g_end - g_begin + block - 1) / block;
     cudaStream_t s = (cudaStream_t)stream;
     const bool aligned = (cfg->width % 4 == 0) && (((uintptr_t)wpix & 15) == 0) &&
                          (last_depth == nullptr || ((uintptr_t)last_depth & 15) == 0);
 #define EG_SB_LAUNCH(RAWP, AL)                                                                                       \
-    splat_bwd_kernel<RAWP, AL><<<grid, block, 0, s>>>(*cfg, tw, th, means, quats, scales, opacities, viewmat, K,    \
+    splat_bwd_kernel<RAWP, AL><<<grid, block, 0, s>>>(*cfg, g_begin, g_end, tw, th, means, quats, scales, opacities, viewmat, K,    \
                                                       (const float4 *)rec, (const int2 *)gint, wpix, seed_scale,    \
                                                       last_depth, last_gid, tile_stop, status,                      \
                                                       (float4 *)grad2d_out, v_means,                                \

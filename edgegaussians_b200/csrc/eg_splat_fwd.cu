@@ -36,12 +36,14 @@ __device__ __forceinline__ void red_add_f32(float *addr, float v) {
 }
 
 // log2(1 - alpha) of one pair, 0 when gsplat skips it (sigma < 0 or alpha < 1/255)
+template <bool CLIP>
 __device__ __forceinline__ float pair_fwd(const EgSplatG &G, const float b1, const float c0, const float px,
                                           const bool in_span) {
     const float dx = G.mx - px;
     const float p = eg_pow2row(G.fa, b1, c0, dx);
     const float ov = eg_ex2(p);
     const float l = eg_lg2(1.0f - fminf(EG_ALPHA_MAX, ov));
+    if (!CLIP) return eg_select_valid(l, ov, p, G.lo);
     return eg_pair_valid(ov, p, G.lo, in_span) ? l : 0.0f;
 }
 
@@ -58,10 +60,10 @@ __device__ __forceinline__ void walk_row_fwd(const EgSplatG &G, const int y, con
         const float px = (float)x + 0.5f;  // pixel centres x + 0.5 .. x + 3.5 are exact in fp32
         // ALIGNED: W % 4 == 0 and the tile rectangle's columns are multiples of 16, so an aligned chunk that
         // overlaps the span lies entirely inside the rectangle -- no per-pixel clipping needed
-        const float v0 = pair_fwd(G, b1, c0, px, ALIGNED || (x >= xa && x <= xb));
-        const float v1 = pair_fwd(G, b1, c0, px + 1.0f, ALIGNED || (x + 1 >= xa && x + 1 <= xb));
-        const float v2 = pair_fwd(G, b1, c0, px + 2.0f, ALIGNED || (x + 2 >= xa && x + 2 <= xb));
-        const float v3 = pair_fwd(G, b1, c0, px + 3.0f, ALIGNED || (x + 3 >= xa && x + 3 <= xb));
+        const float v0 = pair_fwd<!ALIGNED>(G, b1, c0, px, ALIGNED || (x >= xa && x <= xb));
+        const float v1 = pair_fwd<!ALIGNED>(G, b1, c0, px + 1.0f, ALIGNED || (x + 1 >= xa && x + 1 <= xb));
+        const float v2 = pair_fwd<!ALIGNED>(G, b1, c0, px + 2.0f, ALIGNED || (x + 2 >= xa && x + 2 <= xb));
+        const float v3 = pair_fwd<!ALIGNED>(G, b1, c0, px + 3.0f, ALIGNED || (x + 3 >= xa && x + 3 <= xb));
         if (ALIGNED) {
             if ((__float_as_uint(v0) | __float_as_uint(v1) | __float_as_uint(v2) | __float_as_uint(v3)) << 1)
                 eg_red_add_v4(ptr, v0, v1, v2, v3);
@@ -107,7 +109,10 @@ __global__ void __launch_bounds__(SF_WARPS * 32) splat_fwd_kernel(const eg_confi
         const int k = it.owner(base, lane, incl, nrows > 0);
         if (item < R) {
             const EgSplatG Go = s_g[warp][k];
-            walk_row_fwd<ALIGNED>(Go, Go.ylo + (item - Go.start), cfg.width, logT);
+            const int r0 = EG_ROWS_PER_ITEM * (item - Go.start);
+#pragma unroll
+            for (int r = 0; r < EG_ROWS_PER_ITEM; ++r)
+                if (r0 + r < Go.nrows) walk_row_fwd<ALIGNED>(Go, Go.ylo + r0 + r, cfg.width, logT);
         }
     }
 }
@@ -302,6 +307,10 @@ extern "C" int eg_splat_fwd(const eg_config *cfg, const float *rec, const int32_
         return 1;
     }
     if (cfg->n <= 0) return 0;
+    if (cfg->width >= 65536 || cfg->height >= 65536) {
+        eg_set_error("eg_splat_fwd: image sides must be < 65536");
+        return 1;
+    }
     int tw, th;
     eg_tile_grid(cfg->width, cfg->height, cfg->tile_size, &tw, &th);
     const int block = SF_WARPS * 32, grid = (cfg->n + block - 1) / block;

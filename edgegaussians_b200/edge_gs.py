@@ -300,7 +300,8 @@ class EdgeGaussianSplatting(torch.nn.Module):
         return ws
 
     def enqueue_raster_step(self, viewmat, K, W, H, gt, *, loss_weight=1.0, accumulate_absgrad=True, capacity=None,
-                            want_render=False, stage_cb=None, lazy_sort=None, pipeline=None) -> RasterStepWorkspace:
+                            want_render=False, stage_cb=None, lazy_sort=None, pipeline=None,
+                            parts="all") -> RasterStepWorkspace:
         """Enqueue one fused forward+backward iteration on the current stream. No host sync, no
         allocation after the first call for a given (N, W, H): CUDA-graph capturable.
 
@@ -312,7 +313,10 @@ class EdgeGaussianSplatting(torch.nn.Module):
         ``pipeline`` (default: :meth:`current_pipeline`), all three give gsplat's result:
           "splat"        Gaussian-major forward (eg_splat_fwd/resolve, exact per-tile fallback) + eg_splat_bwd;
           "tiles+splat"  tile binning + per-tile sort/compositing (eg_raster_fwd) + eg_splat_bwd;
-          "tiles"        eg_raster_fwd with contribution masks + eg_raster_bwd + eg_project_bwd."""
+          "tiles"        eg_raster_fwd with contribution masks + eg_raster_bwd + eg_project_bwd.
+
+        ``parts="forward"`` stops after the forward (loss, backward seed); the backward is then issued with
+        :meth:`enqueue_backward_range` (Gaussian ranges, for the chunked gradient all-reduce of parallel.py)."""
         lib = get_engine(self.means.device).lib
         ws = self._workspace(W, H, capacity)
         N = ws.N
@@ -358,7 +362,6 @@ class EdgeGaussianSplatting(torch.nn.Module):
                                   _p(gt), gt_kind, _p(ws.loss_sum), _p(ws.wpix), _p(ws.last_depth), _p(ws.last_gid),
                                   _p(ws.stop_list), _p(ws.tile_cnt), _p(ws.status), s), "eg_raster_fwd")
             cb("stop_fallback")
-            tile_stop = _p(ws.tile_stop)
         else:
             ws.zero_block.zero_()   # + the padded tile counters
             cb("memset")
@@ -374,7 +377,12 @@ class EdgeGaussianSplatting(torch.nn.Module):
                                   _p(ws.wpix), None if tiles_bwd else _p(ws.last_depth),
                                   None if tiles_bwd else _p(ws.last_gid), None, None, _p(ws.status), s), "eg_raster_fwd")
             cb("raster_fwd")
-            tile_stop = None
+        ws.pipeline = pipeline
+        ws.bwd_args = (cfg, viewmat, K, seed, accumulate_absgrad)
+        if parts == "forward":
+            if pipeline == "tiles":
+                raise ValueError("parts='forward' needs a pipeline with the Gaussian-major backward")
+            return ws
         if pipeline == "tiles":
             chk(lib.eg_raster_bwd(c, _p(ws.rec), _p(ws.tile_offsets), _p(ws.flatten_ids), _p(ws.cmask), None, None, 0,
                                   None, _p(ws.wpix), seed, _p(ws.grad2d), _p(ws.status), s), "eg_raster_bwd")
@@ -384,13 +392,23 @@ class EdgeGaussianSplatting(torch.nn.Module):
                                    _p(g[3 * N:6 * N]), _p(g[10 * N:11 * N]), absg, s), "eg_project_bwd")
             cb("project_bwd")
         else:
-            chk(lib.eg_splat_bwd(c, _p(means), _p(quats), _p(scales), _p(opac), _p(viewmat), _p(K), _p(ws.rec),
-                                 _p(ws.gint), _p(ws.wpix), seed, _p(ws.last_depth), _p(ws.last_gid), tile_stop,
-                                 _p(ws.status), None, _p(g[0:3 * N]), _p(g[6 * N:10 * N]), _p(g[3 * N:6 * N]),
-                                 _p(g[10 * N:11 * N]), absg, s), "eg_splat_bwd")
+            self.enqueue_backward_range(ws, 0, N)
             cb("splat_bwd")
-        ws.pipeline = pipeline
         return ws
+
+    def enqueue_backward_range(self, ws: RasterStepWorkspace, g_begin: int, g_end: int) -> None:
+        """eg_splat_bwd for the Gaussians [g_begin, g_end) of the step whose forward was just enqueued: their
+        slices of ws.grads (and of self.absgrads) are final when this launch completes."""
+        cfg, viewmat, K, seed, accumulate_absgrad = ws.bwd_args
+        lib = get_engine(self.means.device).lib
+        N, g = ws.N, ws.grads
+        means, quats, scales, opac = self.means.data, self.quats.data, self.scales.data, self.opacities.data
+        _lib.check(lib.eg_splat_bwd(ctypes.byref(cfg), _p(means), _p(quats), _p(scales), _p(opac), _p(viewmat), _p(K),
+                                    _p(ws.rec), _p(ws.gint), _p(ws.wpix), seed, _p(ws.last_depth), _p(ws.last_gid),
+                                    _p(ws.tile_stop) if ws.pipeline == "splat" else None, _p(ws.status),
+                                    int(g_begin), int(g_end), None, _p(g[0:3 * N]), _p(g[6 * N:10 * N]),
+                                    _p(g[3 * N:6 * N]), _p(g[10 * N:11 * N]),
+                                    _p(self.absgrads) if accumulate_absgrad else None, _stream()), "eg_splat_bwd")
 
     # ------------------------------------------------------------------ pipeline policy
     def current_pipeline(self) -> str:

@@ -286,7 +286,7 @@ class Engine:
         v_opac = out[10 * N:11 * N]
         _lib.check(self.lib.eg_splat_bwd(ctypes.byref(st.cfg), _p(means), _p(quats), _p(scales), _p(opacities),
                                          _p(viewmat), _p(K), _p(st.rec), _p(st.gint), _p(wpix), float(seed_scale),
-                                         _p(st.last_depth), _p(st.last_gid), None, _p(st.status), _p(grad2d), _p(v_means),
+                                         _p(st.last_depth), _p(st.last_gid), None, _p(st.status), 0, -1, _p(grad2d), _p(v_means),
                                          _p(v_quats), _p(v_scales), _p(v_opac), _p(absgrad_accum), _stream()),
                    "eg_splat_bwd")
         return v_means, v_quats, v_scales, v_opac, grad2d

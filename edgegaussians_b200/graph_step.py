@@ -18,7 +18,8 @@ from .engine import get_engine
 
 class GraphedRasterStep:
     def __init__(self, model: EdgeGaussianSplatting, width: int, height: int, n_slots: int, gt_dtype=torch.uint8,
-                 loss_weight: float = 1.0, accumulate_absgrad: bool = True, allreduce_group=None, allreduce: bool = False):
+                 loss_weight: float = 1.0, accumulate_absgrad: bool = True, allreduce_group=None, allreduce: bool = False,
+                 allreduce_chunks: int = 4):
         dev = model.means.device
         self.model, self.W, self.H, self.n_slots = model, width, height, n_slots
         self.loss_weight, self.accumulate_absgrad = loss_weight, accumulate_absgrad
@@ -30,6 +31,12 @@ class GraphedRasterStep:
         # stack -- torch 2.11 / NCCL 2.28.9 -- so it is not done.)
         self.allreduce, self.allreduce_group = allreduce, allreduce_group
         self.allreduce_in_graph = False
+        # Gaussian-major backward: gradients become final range by range, so the backward is launched in
+        # `allreduce_chunks` Gaussian ranges (outside the graph) and the all-reduce of a finished range runs on a
+        # side stream while the next range is computed; only the last range's collective is exposed.
+        self.allreduce_chunks = max(1, int(allreduce_chunks))
+        self.comm_stream = torch.cuda.Stream(device=dev) if allreduce else None
+        self.chunked = False
         self.graphs: Dict[int, torch.cuda.CUDAGraph] = {}
         self.ws: Optional[RasterStepWorkspace] = None
         self._capacity = None
@@ -40,10 +47,16 @@ class GraphedRasterStep:
         self.Ks[slot].copy_(K.reshape(3, 3), non_blocking=non_blocking)
         self.gts[slot].copy_(gt, non_blocking=non_blocking)
 
-    def _enqueue(self, slot: int, stage_cb=None):
+    def _distributed(self) -> bool:
+        if not self.allreduce:
+            return False
+        import torch.distributed as dist
+        return dist.is_initialized() and dist.get_world_size(self.allreduce_group) > 1
+
+    def _enqueue(self, slot: int, stage_cb=None, parts="all"):
         return self.model.enqueue_raster_step(self.viewmats[slot], self.Ks[slot], self.W, self.H, self.gts[slot],
                                               loss_weight=self.loss_weight, accumulate_absgrad=self.accumulate_absgrad,
-                                              capacity=self._capacity, stage_cb=stage_cb)
+                                              capacity=self._capacity, stage_cb=stage_cb, parts=parts)
 
     def calibrate(self, slots=None, margin: float = 1.3) -> int:
         """Eager runs (with a host read of the status words) that size the intersection capacity for
@@ -61,6 +74,17 @@ class GraphedRasterStep:
                 if not int(hs[1]):
                     break
                 self._capacity = int(n_isects * margin) + 1024
+        if self._distributed():
+            # every rank must run the same pipeline: the collective pattern (one all-reduce vs. ranged ones) and
+            # the buffer sizes follow from it.  Agree on the most conservative choice and the largest capacity.
+            import torch.distributed as dist
+            order = ["splat", "tiles+splat", "tiles"]
+            t = torch.tensor([order.index(self.model.current_pipeline()), need], dtype=torch.int64,
+                             device=self.model.means.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.allreduce_group)
+            if self.model.pipeline == "auto":
+                self.model._auto_pipeline = order[int(t[0])]
+            need = int(t[1])
         self._capacity = max(int(need * margin) + 1024, 1 << 16)
         self.ws = self.model._workspace(self.W, self.H, self._capacity)
         self.model.install_grads(self.ws)
@@ -72,8 +96,10 @@ class GraphedRasterStep:
             self.calibrate([slot])
         g = torch.cuda.CUDAGraph()
         torch.cuda.synchronize()
+        self.chunked = (self._distributed() and self.allreduce_chunks > 1
+                        and self.model.current_pipeline() != "tiles" and stage_cb is None)
         with torch.cuda.graph(g):
-            ws = self._enqueue(slot, stage_cb=stage_cb)
+            ws = self._enqueue(slot, stage_cb=stage_cb, parts="forward" if self.chunked else "all")
         assert ws is self.ws, "workspace changed during capture"
         if stage_cb is None:
             self.graphs[slot] = g
@@ -84,10 +110,24 @@ class GraphedRasterStep:
         if g is None:
             g = self.capture(slot)
         g.replay()
-        if self.allreduce and not self.allreduce_in_graph:
+        if self._distributed():
             import torch.distributed as dist
-            if dist.is_initialized() and dist.get_world_size(self.allreduce_group) > 1:
-                dist.all_reduce(self.ws.grads, group=self.allreduce_group)
+            from . import parallel
+            ws = self.ws
+            if self.chunked:
+                main = torch.cuda.current_stream()
+                for g0, g1 in parallel.gaussian_ranges(ws.N, self.allreduce_chunks):
+                    self.model.enqueue_backward_range(ws, g0, g1)
+                    ev = torch.cuda.Event()
+                    ev.record(main)
+                    self.comm_stream.wait_event(ev)
+                    with torch.cuda.stream(self.comm_stream):
+                        parallel.allreduce_range(ws.grads, ws.N, g0, g1, self.allreduce_group)
+                done = torch.cuda.Event()
+                done.record(self.comm_stream)
+                main.wait_event(done)   # the optimizer / next step needs the reduced gradients
+            else:
+                dist.all_reduce(ws.grads, group=self.allreduce_group)
         return self.ws
 
     def loss(self) -> torch.Tensor:

@@ -50,6 +50,41 @@ def allreduce_gradients(flat: torch.Tensor, absgrad_increment: Optional[torch.Te
         flat.div_(dist.get_world_size(group))
 
 
+def gaussian_ranges(n: int, chunks: int, align: int = 128) -> List[tuple]:
+    """Split [0, n) into at most ``chunks`` contiguous ranges whose boundaries are multiples of ``align`` (the
+    Gaussians one CTA of eg_splat_bwd owns)."""
+    chunks = max(1, int(chunks))
+    per = -(-n // chunks)
+    per = -(-per // align) * align
+    return [(b, min(n, b + per)) for b in range(0, n, per)]
+
+
+def range_slices(flat: torch.Tensor, n: int, g0: int, g1: int):
+    """The four slices of the flat gradient buffer (means | scales | quats | opacities) that hold the
+    Gaussians [g0, g1)."""
+    return [flat[3 * g0:3 * g1], flat[3 * n + 3 * g0:3 * n + 3 * g1], flat[6 * n + 4 * g0:6 * n + 4 * g1],
+            flat[10 * n + g0:10 * n + g1]]
+
+
+def allreduce_range(flat: torch.Tensor, n: int, g0: int, g1: int, group=None) -> None:
+    """Sum the gradients of the Gaussians [g0, g1) over all ranks in place (issued on the current stream).  The
+    Gaussian-major backward finishes its gradients range by range, so the collective of one range runs while
+    the next range is still being computed.  On NCCL the four slices go out as one grouped launch."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    parts = range_slices(flat, n, g0, g1)
+    if flat.is_cuda and hasattr(dist, "_coalescing_manager"):
+        try:
+            with dist._coalescing_manager(group=group, device=flat.device):
+                for t in parts:
+                    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            return
+        except (RuntimeError, TypeError, NotImplementedError):
+            pass
+    for t in parts:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+
+
 def sync_absgrads(model, group=None) -> None:
     """Sum the per-rank abs-grad statistics (model.absgrads, accumulated locally by the fused step) over all
     ranks.  Needed only where the reference reads them: at densification (edge_gs.py:544-576), i.e. once per

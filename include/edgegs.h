@@ -190,13 +190,16 @@ int eg_emit_flagged(const eg_config *cfg, const float *rec, const int32_t *gint,
  *                   pixel composited, last_depth = 0xffffffff where the pixel never stopped; only read when
  *                   status[EG_ST_STOPPED] != 0, and, when tile_stop [T] i32 is given (eg_splat_resolve), only
  *                   inside the tiles it flags (the planes are undefined elsewhere).
+ *   g_begin, g_end  only the Gaussians [g_begin, g_end) are processed (g_end < 0: all) -- every Gaussian has one
+ *                   owner, so the view-sharded multi-GPU step launches the backward in Gaussian ranges and
+ *                   all-reduces the gradients of a finished range while the next one is being computed.
  *   grad2d_out [N,8] optional: the 2D gradients (layout of grad2d above), WRITTEN.
  * Gradient outputs are WRITTEN (layout as eg_project_bwd); absgrad_accum [N] (may be NULL) += ||absgrad||_2. */
 int eg_splat_bwd(const eg_config *cfg, const float *means, const float *quats, const float *scales,
                  const float *opacities, const float *viewmat, const float *K, const float *rec,
                  const int32_t *gint, const float *wpix, float seed_scale, const uint32_t *last_depth,
-                 const int32_t *last_gid, const int32_t *tile_stop, const int32_t *status, float *grad2d_out,
-                 float *v_means,
+                 const int32_t *last_gid, const int32_t *tile_stop, const int32_t *status, int g_begin, int g_end,
+                 float *grad2d_out, float *v_means,
                  float *v_quats, float *v_scales, float *v_opacities, float *absgrad_accum, void *stream);
 
 /* Per-pixel seed of the gsplat-shaped autograd path:

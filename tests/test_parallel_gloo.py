@@ -36,7 +36,12 @@ def _worker(rank, world, port, n, n_views, out_dir):
             view = parallel.views_for_step(perm, step, world)[rank]
             flat = _fake_view_grad(view, n) if view is not None else torch.zeros(11 * n)
             inc = torch.full((n,), float(view + 1)) if view is not None else torch.zeros(n)
-            parallel.allreduce_gradients(flat, inc)
+            if step % 2 == 0:
+                parallel.allreduce_gradients(flat, inc)
+            else:  # the chunked form the Gaussian-major backward uses: range by range
+                for g0, g1 in parallel.gaussian_ranges(n, 3, align=8):
+                    parallel.allreduce_range(flat, n, g0, g1)
+                dist.all_reduce(inc)
             total += flat
             absg += inc
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), total=total.numpy(), absg=absg.numpy(), perm=np.array(perm))
@@ -70,5 +75,12 @@ def test_views_for_step_and_layout():
     assert vs[0, 0] == 3 * n and vq[0, 0] == 6 * n and vo[0, 0] == 10 * n
     vm[0, 0] = -1.0
     assert flat[0] == -1.0                                          # views, not copies
+    assert parallel.gaussian_ranges(1000, 4) == [(0, 256), (256, 512), (512, 768), (768, 1000)]
+    assert parallel.gaussian_ranges(100, 4) == [(0, 100)] and parallel.gaussian_ranges(37, 3, align=8) == [(0, 16), (16, 32), (32, 37)]
+    covered = torch.zeros(11 * n)
+    for g0, g1 in parallel.gaussian_ranges(n, 2, align=2):
+        for t in parallel.range_slices(covered, n, g0, g1):
+            t += 1
+    assert bool((covered == 1).all())                               # the ranges tile the flat buffer exactly once
     assert parallel.view_permutation(10, 1, 3) == parallel.view_permutation(10, 1, 3)
     assert parallel.view_permutation(10, 1, 3) != parallel.view_permutation(10, 2, 3)
