@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--no-lazy-sort", action="store_true", help="always sort every tile (gsplat order) in the tile pipelines")
     ap.add_argument("--pipeline", default="auto", choices=["auto", "splat", "tiles+splat", "tiles"],
                     help="fused-step pipeline (edge_gs.enqueue_raster_step); auto = what training would run")
-    ap.add_argument("--allreduce-chunks", type=int, default=4,
+    ap.add_argument("--allreduce-chunks", type=int, default=1,
                     help="N > 1: Gaussian ranges of the backward whose all-reduce overlaps the next range")
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
     return ap.parse_args()
@@ -77,8 +77,8 @@ def workload_name(args):
 
 def ncu_traffic_bytes(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full
-    summary (profiles/r1_ncu_full_summary.txt, written by scripts/summarise_profiles.py); None if absent."""
-    path = os.path.join(ROOT, "profiles", "r1_ncu_full_summary.txt")
+    summary (profiles/r1_splat_ncu_full_summary.txt, written by scripts/summarise_profiles.py); None if absent."""
+    path = os.path.join(ROOT, "profiles", "r1_splat_ncu_full_summary.txt")
     if not os.path.exists(path):
         return None
     mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}

@@ -62,6 +62,45 @@ __device__ __forceinline__ void eg_red_add_v4(float *addr, float a, float b, flo
                  : "memory");
 }
 
+// Packed fp32x2 arithmetic (Blackwell FFMA2 / FADD2 / FMUL2: two IEEE-rn fp32 operations per issued instruction,
+// operands in even-aligned register pairs).  Element-wise results are bit-identical to the scalar .rn forms.
+typedef unsigned long long eg_f2;
+__device__ __forceinline__ eg_f2 f2_pack(float lo, float hi) {
+    eg_f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ eg_f2 f2_dup(float v) { return f2_pack(v, v); }
+__device__ __forceinline__ void f2_unpack(eg_f2 v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ eg_f2 f2_fma(eg_f2 a, eg_f2 b, eg_f2 c) {
+    eg_f2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ eg_f2 f2_add(eg_f2 a, eg_f2 b) {
+    eg_f2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ eg_f2 f2_mul(eg_f2 a, eg_f2 b) {
+    eg_f2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// in-place forms for loop-carried accumulators (keeps them in one register pair: no copies)
+__device__ __forceinline__ void f2_acc(eg_f2 &acc, eg_f2 b) { asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(b)); }
+__device__ __forceinline__ void f2_acc_fma(eg_f2 &acc, eg_f2 a, eg_f2 b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ eg_f2 f2_abs(eg_f2 a) { return a & 0x7fffffff7fffffffull; }
+__device__ __forceinline__ float f2_hsum(eg_f2 a) {
+    float lo, hi;
+    f2_unpack(a, lo, hi);
+    return lo + hi;
+}
+
 // sigma and opacity*exp(-sigma) with a FIXED operation order (explicit intrinsics, no compiler
 // contraction) so that the forward and the backward kernels take identical skip decisions
 // (sigma < 0, alpha < 1/255) for every (pixel, Gaussian) pair.

@@ -27,6 +27,9 @@
 namespace {
 
 constexpr int SB_WARPS = 4;
+#ifndef EG_SB_MINBLOCKS
+#define EG_SB_MINBLOCKS 6   // resident CTAs per SM the register allocation is bounded for
+#endif
 
 template <bool ALIGNED>
 __device__ __forceinline__ float4 ld_f4(const float *__restrict__ row, int c, int xlim) {
@@ -83,6 +86,55 @@ __device__ __forceinline__ void pair_bwd(const EgSplatG &G, const float b1, cons
     r.ay += fabsf(vs * fmaf(G.B, dx, Cdy));
 }
 
+// Two pixels per step on the packed fp32x2 pipe (ALIGNED rows only: no per-pixel clipping, see eg_splat_fwd.cu).
+// Same element-wise operations and roundings as pair_bwd; only MUFU and the validity select stay scalar.
+struct RowConst2 {
+    eg_f2 mx, fa, b1, c0, A, B, Bdy, Cdy;
+};
+struct RowAcc2 {
+    eg_f2 S0, S1, S2;
+    float ax0, ax1, ay0, ay1;  // scalar: FADD takes |x| as a free operand modifier, the packed add does not
+};
+
+template <bool HAS_LAST>
+__device__ __forceinline__ void pair2_bwd(const EgSplatG &G, const RowConst2 &k, const eg_f2 npx, const float w0,
+                                          const float w1, const unsigned dl0, const unsigned dl1,
+                                          const int *__restrict__ gid_px, RowAcc2 &r) {
+    const eg_f2 dx = f2_add(k.mx, npx);                       // mean2d.x - pixel centre
+    const eg_f2 p = f2_fma(f2_fma(k.fa, dx, k.b1), dx, k.c0);  // eg_pow2row
+    float p0, p1;
+    f2_unpack(p, p0, p1);
+    const float ov0 = eg_ex2(p0), ov1 = eg_ex2(p1);
+    const eg_f2 ov = f2_pack(ov0, ov1);
+    float om0, om1;
+    f2_unpack(f2_fma(ov, f2_dup(-1.0f), f2_dup(1.0f)), om0, om1);  // 1 - alpha
+    const eg_f2 vsu = f2_mul(f2_mul(ov, f2_pack(w0, w1)), f2_pack(eg_rcp(om0), eg_rcp(om1)));
+    float v0, v1;
+    f2_unpack(vsu, v0, v1);
+    if (!HAS_LAST) {
+        v0 = eg_select_valid_grad(v0, ov0, p0, G.lo);
+        v1 = eg_select_valid_grad(v1, ov1, p1, G.lo);
+    } else {
+        bool a0 = eg_pair_valid_grad(ov0, p0, G.lo, true), a1 = eg_pair_valid_grad(ov1, p1, G.lo, true);
+        if (a0 && G.depth_bits >= dl0) a0 = G.depth_bits == dl0 && G.gid <= __ldg(gid_px);
+        if (a1 && G.depth_bits >= dl1) a1 = G.depth_bits == dl1 && G.gid <= __ldg(gid_px + 1);
+        v0 = a0 ? v0 : 0.0f;
+        v1 = a1 ? v1 : 0.0f;
+    }
+    const eg_f2 vs = f2_pack(v0, v1);
+    const eg_f2 vd = f2_mul(vs, dx);
+    f2_acc(r.S0, vs);
+    f2_acc(r.S1, vd);
+    f2_acc_fma(r.S2, vd, dx);
+    float t0, t1, u0, u1;
+    f2_unpack(f2_mul(vs, f2_fma(k.A, dx, k.Bdy)), t0, t1);
+    f2_unpack(f2_mul(vs, f2_fma(k.B, dx, k.Cdy)), u0, u1);
+    r.ax0 += fabsf(t0);
+    r.ax1 += fabsf(t1);
+    r.ay0 += fabsf(u0);
+    r.ay1 += fabsf(u1);
+}
+
 template <bool HAS_LAST, bool ALIGNED>
 __device__ __forceinline__ void walk_row_bwd(const EgSplatG &G, const int y, const int W, const int tw,
                                              const float *__restrict__ wpix, const unsigned *__restrict__ last_depth,
@@ -102,23 +154,47 @@ __device__ __forceinline__ void walk_row_bwd(const EgSplatG &G, const int y, con
         int c = xa >> 2;
         const int cend = xb >> 2;
         float4 w4 = ld_f4<ALIGNED>(wrow, c, W);
+        if (ALIGNED) {
+            RowConst2 k2;
+            k2.mx = f2_dup(G.mx); k2.fa = f2_dup(G.fa); k2.b1 = f2_dup(b1); k2.c0 = f2_dup(c0);
+            k2.A = f2_dup(G.A); k2.B = f2_dup(G.B); k2.Bdy = f2_dup(Bdy); k2.Cdy = f2_dup(Cdy);
+            RowAcc2 r2;
+            r2.S0 = r2.S1 = r2.S2 = 0ull;
+            r2.ax0 = r2.ax1 = r2.ay0 = r2.ay1 = 0.0f;
+            // negated pixel centres of the chunk: -(x + 0.5), -(x + 1.5) | -(x + 2.5), -(x + 3.5)   (exact in fp32)
+            const float nb = -((float)(4 * c) + 0.5f);
+            eg_f2 npa = f2_pack(nb, nb - 1.0f), npb = f2_pack(nb - 2.0f, nb - 3.0f);
+            const eg_f2 m4 = f2_dup(-4.0f);
+            for (; c <= cend; ++c) {
+                float4 wn = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c < cend) wn = ld_f4<true>(wrow, c + 1, W);  // next chunk in flight while this one is evaluated
+                const int x = 4 * c;
+                uint4 d4 = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+                if (HAS_LAST) {  // the planes are only defined in tiles where some pixel stopped
+                    if (srow == nullptr || __ldg(srow + (x >> 4)) != 0) d4 = ld_u4<true>(drow, c, W);
+                }
+                pair2_bwd<HAS_LAST>(G, k2, npa, w4.x, w4.y, d4.x, d4.y, grow + x, r2);
+                pair2_bwd<HAS_LAST>(G, k2, npb, w4.z, w4.w, d4.z, d4.w, grow + x + 2, r2);
+                f2_acc(npa, m4);
+                f2_acc(npb, m4);
+                w4 = wn;
+            }
+            r.S0 = f2_hsum(r2.S0); r.S1 = f2_hsum(r2.S1); r.S2 = f2_hsum(r2.S2);
+            r.ax = r2.ax0 + r2.ax1; r.ay = r2.ay0 + r2.ay1;
+        } else
         for (; c <= cend; ++c) {
             float4 wn = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (c < cend) wn = ld_f4<ALIGNED>(wrow, c + 1, W);  // next chunk in flight while this one is evaluated
+            if (c < cend) wn = ld_f4<ALIGNED>(wrow, c + 1, W);
             const int x = 4 * c;
             uint4 d4 = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-            if (HAS_LAST) {  // the planes are only defined in tiles where some pixel stopped (a chunk never straddles tiles)
+            if (HAS_LAST) {
                 if (srow == nullptr || __ldg(srow + (x >> 4)) != 0) d4 = ld_u4<ALIGNED>(drow, c, W);
             }
-            const float px = (float)x + 0.5f;  // pixel centres x + 0.5 .. x + 3.5 are exact in fp32
-            // ALIGNED: an aligned chunk that overlaps the span lies inside the tile rectangle (see eg_splat_fwd.cu)
-            pair_bwd<HAS_LAST, !ALIGNED>(G, b1, c0, Bdy, Cdy, px, ALIGNED || (x >= xa && x <= xb), w4.x, d4.x, grow + x, r);
-            pair_bwd<HAS_LAST, !ALIGNED>(G, b1, c0, Bdy, Cdy, px + 1.0f, ALIGNED || (x + 1 >= xa && x + 1 <= xb), w4.y, d4.y,
-                               grow + x + 1, r);
-            pair_bwd<HAS_LAST, !ALIGNED>(G, b1, c0, Bdy, Cdy, px + 2.0f, ALIGNED || (x + 2 >= xa && x + 2 <= xb), w4.z, d4.z,
-                               grow + x + 2, r);
-            pair_bwd<HAS_LAST, !ALIGNED>(G, b1, c0, Bdy, Cdy, px + 3.0f, ALIGNED || (x + 3 >= xa && x + 3 <= xb), w4.w, d4.w,
-                               grow + x + 3, r);
+            const float px = (float)x + 0.5f;
+            pair_bwd<HAS_LAST, true>(G, b1, c0, Bdy, Cdy, px, x >= xa && x <= xb, w4.x, d4.x, grow + x, r);
+            pair_bwd<HAS_LAST, true>(G, b1, c0, Bdy, Cdy, px + 1.0f, x + 1 >= xa && x + 1 <= xb, w4.y, d4.y, grow + x + 1, r);
+            pair_bwd<HAS_LAST, true>(G, b1, c0, Bdy, Cdy, px + 2.0f, x + 2 >= xa && x + 2 <= xb, w4.z, d4.z, grow + x + 2, r);
+            pair_bwd<HAS_LAST, true>(G, b1, c0, Bdy, Cdy, px + 3.0f, x + 3 >= xa && x + 3 <= xb, w4.w, d4.w, grow + x + 3, r);
             w4 = wn;
         }
     }
@@ -134,7 +210,7 @@ __device__ __forceinline__ void walk_row_bwd(const EgSplatG &G, const int y, con
 }
 
 template <bool RAW, bool ALIGNED>
-__global__ void __launch_bounds__(SB_WARPS * 32) splat_bwd_kernel(
+__global__ void __launch_bounds__(SB_WARPS * 32, EG_SB_MINBLOCKS) splat_bwd_kernel(
     const eg_config cfg, const int g_begin, const int g_end, const int tw, const int th, const float *__restrict__ means, const float *__restrict__ quats,
     const float *__restrict__ scales, const float *__restrict__ opacities, const float *__restrict__ viewmat,
     const float *__restrict__ Kmat, const float4 *__restrict__ rec, const int2 *__restrict__ gint,

@@ -7,6 +7,6 @@ mkdir -p gpurun_out
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${TAG}.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu_${TAG}.log 2>&1
 ncu --set full --clock-control none --import-source on \
-    -k regex:"raster_fwd_kernel|raster_bwd_kernel|project_fwd_kernel|project_bwd_kernel|scan_kernel" -s 5 -c 5 \
+    -k regex:"project_fwd_kernel|splat_fwd_kernel|splat_resolve4_kernel|emit_flagged_kernel|raster_fwd_flagged_kernel|splat_bwd_kernel" -s 6 -c 6 \
     -o gpurun_out/prof_${TAG} python scripts/profile_step.py --iters 3 > gpurun_out/prof_${TAG}.log 2>&1
 tail -2 gpurun_out/prof_${TAG}.log

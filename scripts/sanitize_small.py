@@ -18,9 +18,11 @@ for (N, W, H, regime, bs) in [(3000, 200, 136, "mixed", 0.02), (6000, 64, 48, "m
     model = EdgeGaussianSplatting(device=dev)
     model.set_params(m, s, q, o, viewcams=[OpenCVCamera.from_matrices(H, W, Ks[0], vms[0]).to(dev)])
     gt = torch.as_tensor(synth.make_edge_map_u8(W, H, 0)).to(dev)
-    for lazy in (True, False):
-        model.lazy_sort = lazy
-        loss = model.raster_step(0, gt)
+    for pipeline in ("splat", "tiles+splat", "tiles"):
+        model.pipeline = pipeline
+        for lazy in (True, False):
+            model.lazy_sort = lazy
+            loss = model.raster_step(0, gt)
     model.train()
     out = model(0)
     out["rgb"][:, :, 0].mean().backward()

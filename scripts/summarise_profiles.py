@@ -50,7 +50,10 @@ if os.path.exists(rep):
             "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
             "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__warps_active.avg.pct_of_peak_sustained_active",
             "launch__registers_per_thread", "launch__shared_mem_per_block_static", "launch__grid_size", "launch__block_size",
-            "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
+            "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+            "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+            "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+            "sm__inst_issued.avg.per_cycle_active"]
     idx = [(w, Hh.index(w)) for w in want if w in Hh]
     units = rws[1]
     with open(os.path.join(pr, f"{tag}_ncu_full_summary.txt"), "w") as f:
@@ -60,7 +63,7 @@ if os.path.exists(rep):
             f.write("\n")
             for w, i in idx:
                 f.write(f"{w:75s} {r[i][:90]} {units[i]}\n")
-    for kern in ("raster_fwd", "raster_bwd"):
+    for kern in ("splat_fwd", "splat_bwd"):
         o = subprocess.run([sys.executable, os.path.join(root, "scripts", "ncu_lines.py"), rep, kern, "40", "ins"],
                            capture_output=True, text=True).stdout
         with open(os.path.join(pr, f"{tag}_{kern}_source_hotspots.txt"), "w") as f:
