@@ -91,9 +91,10 @@ __device__ __forceinline__ void pair_bwd(const EgSplatG &G, const float b1, cons
 struct RowConst2 {
     eg_f2 mx, fa, b1, c0, A, B, Bdy, Cdy;
 };
+// Loop-carried sums stay SCALAR: ptxas keeps scalar accumulators in place but copies 64-bit asm results around
+// (14 MOVs per chunk on the ALU pipe, which is the busiest pipe of this kernel), and FADD takes |x| for free.
 struct RowAcc2 {
-    eg_f2 S0, S1, S2;
-    float ax0, ax1, ay0, ay1;  // scalar: FADD takes |x| as a free operand modifier, the packed add does not
+    float S0a, S0b, S1a, S1b, S2a, S2b, ax0, ax1, ay0, ay1;
 };
 
 template <bool HAS_LAST>
@@ -122,10 +123,15 @@ __device__ __forceinline__ void pair2_bwd(const EgSplatG &G, const RowConst2 &k,
         v1 = a1 ? v1 : 0.0f;
     }
     const eg_f2 vs = f2_pack(v0, v1);
-    const eg_f2 vd = f2_mul(vs, dx);
-    f2_acc(r.S0, vs);
-    f2_acc(r.S1, vd);
-    f2_acc_fma(r.S2, vd, dx);
+    float d0, d1, e0, e1;
+    f2_unpack(f2_mul(vs, dx), d0, d1);
+    f2_unpack(dx, e0, e1);
+    r.S0a += v0;
+    r.S0b += v1;
+    r.S1a += d0;
+    r.S1b += d1;
+    r.S2a = fmaf(d0, e0, r.S2a);
+    r.S2b = fmaf(d1, e1, r.S2b);
     float t0, t1, u0, u1;
     f2_unpack(f2_mul(vs, f2_fma(k.A, dx, k.Bdy)), t0, t1);
     f2_unpack(f2_mul(vs, f2_fma(k.B, dx, k.Cdy)), u0, u1);
@@ -159,13 +165,13 @@ __device__ __forceinline__ void walk_row_bwd(const EgSplatG &G, const int y, con
             k2.mx = f2_dup(G.mx); k2.fa = f2_dup(G.fa); k2.b1 = f2_dup(b1); k2.c0 = f2_dup(c0);
             k2.A = f2_dup(G.A); k2.B = f2_dup(G.B); k2.Bdy = f2_dup(Bdy); k2.Cdy = f2_dup(Cdy);
             RowAcc2 r2;
-            r2.S0 = r2.S1 = r2.S2 = 0ull;
+            r2.S0a = r2.S0b = r2.S1a = r2.S1b = r2.S2a = r2.S2b = 0.0f;
             r2.ax0 = r2.ax1 = r2.ay0 = r2.ay1 = 0.0f;
             // negated pixel centres of the chunk: -(x + 0.5), -(x + 1.5) | -(x + 2.5), -(x + 3.5)   (exact in fp32)
-            const float nb = -((float)(4 * c) + 0.5f);
-            eg_f2 npa = f2_pack(nb, nb - 1.0f), npb = f2_pack(nb - 2.0f, nb - 3.0f);
-            const eg_f2 m4 = f2_dup(-4.0f);
+            float nb = -((float)(4 * c) + 0.5f);
             for (; c <= cend; ++c) {
+                const eg_f2 npa = f2_pack(nb, nb - 1.0f), npb = f2_pack(nb - 2.0f, nb - 3.0f);
+                nb -= 4.0f;
                 float4 wn = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (c < cend) wn = ld_f4<true>(wrow, c + 1, W);  // next chunk in flight while this one is evaluated
                 const int x = 4 * c;
@@ -175,11 +181,9 @@ __device__ __forceinline__ void walk_row_bwd(const EgSplatG &G, const int y, con
                 }
                 pair2_bwd<HAS_LAST>(G, k2, npa, w4.x, w4.y, d4.x, d4.y, grow + x, r2);
                 pair2_bwd<HAS_LAST>(G, k2, npb, w4.z, w4.w, d4.z, d4.w, grow + x + 2, r2);
-                f2_acc(npa, m4);
-                f2_acc(npb, m4);
                 w4 = wn;
             }
-            r.S0 = f2_hsum(r2.S0); r.S1 = f2_hsum(r2.S1); r.S2 = f2_hsum(r2.S2);
+            r.S0 = r2.S0a + r2.S0b; r.S1 = r2.S1a + r2.S1b; r.S2 = r2.S2a + r2.S2b;
             r.ax = r2.ax0 + r2.ax1; r.ay = r2.ay0 + r2.ay1;
         } else
         for (; c <= cend; ++c) {

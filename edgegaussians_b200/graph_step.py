@@ -130,5 +130,25 @@ class GraphedRasterStep:
                 dist.all_reduce(ws.grads, group=self.allreduce_group)
         return self.ws
 
+    def poll_policy(self) -> bool:
+        """Host read of the last step's status words (one small D2H copy: call it every few hundred steps, not per
+        step).  Feeds the model's pipeline policy; when the policy moves (e.g. the scene has become opaque enough
+        that most tiles need the sorted fallback) the captured graphs are dropped and re-captured on next use.
+        Returns True when that happened.  In a distributed run every rank must call it at the same step."""
+        before = self.model.current_pipeline()
+        hs = self.ws.status.cpu()
+        self.model.note_status(hs, self.ws.T)
+        code = torch.tensor([["splat", "tiles+splat", "tiles"].index(self.model.current_pipeline())],
+                            dtype=torch.int64, device=self.ws.status.device)
+        if self._distributed():
+            import torch.distributed as dist
+            dist.all_reduce(code, op=dist.ReduceOp.MAX, group=self.allreduce_group)
+            if self.model.pipeline == "auto":
+                self.model._auto_pipeline = ["splat", "tiles+splat", "tiles"][int(code[0])]
+        changed = self.model.current_pipeline() != before
+        if changed:
+            self.graphs.clear()
+        return changed
+
     def loss(self) -> torch.Tensor:
         return (self.ws.loss_sum[0] / float(self.W * self.H)).float()

@@ -177,6 +177,31 @@ def test_fused_raster_step_parity(case, gt_dtype, pipeline):
     assert model.absgrads_normalize_factor == 3
 
 
+def test_backward_in_gaussian_ranges_matches_single_launch():
+    """eg_splat_bwd over [0,N) in three Gaussian ranges (what the chunked multi-GPU all-reduce launches) writes
+    exactly the gradients of the single launch: every Gaussian has one owner, no atomics are involved."""
+    name, N, W, H, regime, seed, bs, view = CASES[1]
+    m, q, s, o, sc, op, vm, K = _inputs(N, W, H, regime, seed, bs, view)
+    model = EdgeGaussianSplatting(device=DEV)
+    cam = OpenCVCamera.from_matrices(H, W, K, vm).to(DEV)
+    model.set_params(m, s, q, o, viewcams=[cam])
+    gt = _t(synth.make_edge_map_u8(W, H, seed))
+    from edgegaussians_b200 import parallel
+    # one forward (its float reductions are order-dependent in the last bit), then both backward forms on its seed
+    ws = model.enqueue_raster_step(cam.viewmat.reshape(4, 4), cam.K.reshape(3, 3), W, H, gt, accumulate_absgrad=False,
+                                   parts="forward")
+    model.enqueue_backward_range(ws, 0, N)
+    full = ws.grads.clone()
+    assert float(full.abs().max()) > 0
+    ws.grads.fill_(float("nan"))
+    ranges = parallel.gaussian_ranges(N, 3)
+    assert len(ranges) == 3 and ranges[0][0] == 0 and ranges[-1][1] == N
+    for g0, g1 in reversed(ranges):
+        model.enqueue_backward_range(ws, g0, g1)
+    torch.cuda.synchronize()
+    assert torch.equal(ws.grads, full)
+
+
 def test_autograd_path_matches_fused_path():
     """get_outputs -> compute_projection_loss('whole') -> backward -> update_absgrads (the reference's
     own call sequence through the gsplat-shaped op) agrees with raster_step."""
