@@ -425,6 +425,16 @@ class EdgeGaussianSplatting(torch.nn.Module):
             self._auto_pipeline = "tiles" if n_isects > 8 * self.num_points else "tiles+splat"
         self.note_redo(redo, n_tiles)
 
+    @staticmethod
+    def max_tile_load(ws: RasterStepWorkspace, hs) -> int:
+        """Largest per-tile key count of the step that just ran (sizes the tile buckets after an overflow).  The tile
+        pipelines report it in the status words; in the Gaussian-major pipeline only flagged tiles have buckets
+        and the cursors of eg_emit_flagged hold their true sizes."""
+        m = int(hs[_lib.EG_ST_MAXTILE])
+        if getattr(ws, "pipeline", None) == "splat" and int(hs[_lib.EG_ST_STOPPED]) > 0:
+            m = max(m, int(ws.tile_cnt.max()))
+        return m
+
     def _use_lazy(self, override=None) -> bool:
         mode = self.lazy_sort if override is None else override
         return self._lazy_on if mode == "auto" else bool(mode)
@@ -461,7 +471,7 @@ class EdgeGaussianSplatting(torch.nn.Module):
             if not int(hs[_lib.EG_ST_OVERFLOW]):
                 break
             # roll back the abs-grad accumulation is unnecessary: overflowed runs are no-ops in raster kernels
-            get_engine(self.means.device).note_status(int(hs[_lib.EG_ST_NISECT]), int(hs[_lib.EG_ST_MAXTILE]))
+            get_engine(self.means.device).note_status(int(hs[_lib.EG_ST_NISECT]), self.max_tile_load(ws, hs))
         self.install_grads(ws)
         self.absgrads_normalize_factor += 1
         self.step += 1

@@ -69,7 +69,7 @@ class GraphedRasterStep:
                 n_isects = int(hs[0])
                 need = max(need, n_isects)
                 eng = get_engine(self.model.means.device)
-                eng.max_tile = max(eng.max_tile, int(hs[3]))
+                eng.max_tile = max(eng.max_tile, self.model.max_tile_load(ws, hs))
                 self.model.note_status(hs, ws.T)
                 if not int(hs[1]):
                     break
