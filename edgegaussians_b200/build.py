@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_C")
 LIB = os.path.join(OUT_DIR, "libedgegs.so")
-SOURCES = ["eg_api.cu", "eg_project_fwd.cu", "eg_bin.cu", "eg_raster_fwd.cu", "eg_raster_bwd.cu", "eg_splat_bwd.cu", "eg_splat_fwd.cu",
+SOURCES = ["eg_api.cu", "eg_project_fwd.cu", "eg_bin.cu", "eg_raster_fwd.cu", "eg_raster_bwd.cu", "eg_splat_bwd.cu", "eg_splat_fwd.cu", "eg_comm.cu",
            "eg_project_bwd.cu", "eg_reg.cu", "eg_knn.cu", "eg_adam.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
@@ -56,7 +56,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if verbose:
                 print(log[-1])
     if force or _stale(LIB, objs):
-        cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+        cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

@@ -410,6 +410,20 @@ class EdgeGaussianSplatting(torch.nn.Module):
                                     _p(g[3 * N:6 * N]), _p(g[10 * N:11 * N]),
                                     _p(self.absgrads) if accumulate_absgrad else None, _stream()), "eg_splat_bwd")
 
+    def enqueue_backward_allreduce(self, ws: RasterStepWorkspace, comm, n_ranges: int) -> None:
+        """The whole backward of the step whose forward was just enqueued, in ``n_ranges`` Gaussian ranges, with the
+        gradients of each finished range all-reduced over the ranks of ``comm`` (parallel.NativeComm) on its side
+        stream while the next range is computed -- one C call (eg_splat_bwd_allreduce)."""
+        cfg, viewmat, K, seed, accumulate_absgrad = ws.bwd_args
+        lib = get_engine(self.means.device).lib
+        means, quats, scales, opac = self.means.data, self.quats.data, self.scales.data, self.opacities.data
+        _lib.check(lib.eg_splat_bwd_allreduce(
+            ctypes.byref(cfg), _p(means), _p(quats), _p(scales), _p(opac), _p(viewmat), _p(K), _p(ws.rec), _p(ws.gint),
+            _p(ws.wpix), seed, _p(ws.last_depth), _p(ws.last_gid),
+            _p(ws.tile_stop) if ws.pipeline == "splat" else None, _p(ws.status), _p(ws.grads),
+            _p(self.absgrads) if accumulate_absgrad else None, int(n_ranges), comm.handle,
+            ctypes.c_void_p(comm.stream.cuda_stream), _stream()), "eg_splat_bwd_allreduce")
+
     # ------------------------------------------------------------------ pipeline policy
     def current_pipeline(self) -> str:
         """``self.pipeline`` = "auto" (default) starts Gaussian-major and, fed by :meth:`note_status`, moves to the

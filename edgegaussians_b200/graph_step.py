@@ -37,6 +37,7 @@ class GraphedRasterStep:
         self.allreduce_chunks = max(1, int(allreduce_chunks))
         self.comm_stream = torch.cuda.Stream(device=dev) if allreduce else None
         self.chunked = False
+        self.native_comm = None   # parallel.NativeComm: ranged backward + collectives as one C call
         self.graphs: Dict[int, torch.cuda.CUDAGraph] = {}
         self.ws: Optional[RasterStepWorkspace] = None
         self._capacity = None
@@ -98,6 +99,9 @@ class GraphedRasterStep:
         torch.cuda.synchronize()
         self.chunked = (self._distributed() and self.allreduce_chunks > 1
                         and self.model.current_pipeline() != "tiles" and stage_cb is None)
+        if self.chunked and self.native_comm is None and not getattr(self, "python_ranges", False):
+            from .parallel import NativeComm
+            self.native_comm = NativeComm(self.model.means.device, self.allreduce_group)
         with torch.cuda.graph(g):
             ws = self._enqueue(slot, stage_cb=stage_cb, parts="forward" if self.chunked else "all")
         assert ws is self.ws, "workspace changed during capture"
@@ -114,7 +118,9 @@ class GraphedRasterStep:
             import torch.distributed as dist
             from . import parallel
             ws = self.ws
-            if self.chunked:
+            if self.chunked and self.native_comm is not None:
+                self.model.enqueue_backward_allreduce(ws, self.native_comm, self.allreduce_chunks)
+            elif self.chunked:
                 main = torch.cuda.current_stream()
                 for g0, g1 in parallel.gaussian_ranges(ws.N, self.allreduce_chunks):
                     self.model.enqueue_backward_range(ws, g0, g1)

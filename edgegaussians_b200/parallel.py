@@ -85,6 +85,36 @@ def allreduce_range(flat: torch.Tensor, n: int, g0: int, g1: int, group=None) ->
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
 
 
+class NativeComm:
+    """Communicator of libedgegs.so (eg_comm_*, NCCL underneath) over the ranks of ``group``: what
+    ``eg_splat_bwd_allreduce`` exchanges gradients through.  torch.distributed only carries the 128-byte
+    rendezvous id.  Collective: every rank of the group must construct it at the same point."""
+
+    def __init__(self, device: torch.device, group=None):
+        import ctypes
+        from . import _lib
+        self.lib = _lib.load()
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        id_t = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            buf = (ctypes.c_char * 128)()
+            _lib.check(self.lib.eg_comm_unique_id(ctypes.cast(buf, ctypes.c_void_p)), "eg_comm_unique_id")
+            id_t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        carrier = id_t.to(device) if dist.get_backend(group) == "nccl" else id_t
+        dist.broadcast(carrier, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        raw = bytes(carrier.cpu().numpy().tobytes())
+        self.handle = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(self.lib.eg_comm_init(ctypes.c_char_p(raw), self.rank, self.world, ctypes.byref(self.handle)),
+                       "eg_comm_init")
+        self.stream = torch.cuda.Stream(device=device)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.eg_comm_destroy(self.handle)
+            self.handle = None
+
+
 def sync_absgrads(model, group=None) -> None:
     """Sum the per-rank abs-grad statistics (model.absgrads, accumulated locally by the fused step) over all
     ranks.  Needed only where the reference reads them: at densification (edge_gs.py:544-576), i.e. once per

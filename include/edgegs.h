@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define EG_ABI_VERSION 7
+#define EG_ABI_VERSION 8
 #define EG_CNT_STRIDE 32
 
 enum {
@@ -201,6 +201,25 @@ int eg_splat_bwd(const eg_config *cfg, const float *means, const float *quats, c
                  const int32_t *last_gid, const int32_t *tile_stop, const int32_t *status, int g_begin, int g_end,
                  float *grad2d_out, float *v_means,
                  float *v_quats, float *v_scales, float *v_opacities, float *absgrad_accum, void *stream);
+
+/* View-sharded multi-GPU step (no reference counterpart: the reference is single-GPU, train_gaussians.py:311; the
+ * sharding is SURVEY.md section 8e's): a communicator over the ranks' GPUs and the backward + exchange as ONE call.
+ * NCCL is resolved at run time (dlopen libnccl.so.2), the library does not link against it.
+ *   eg_comm_unique_id  rank 0: 128-byte rendezvous id (host memory), to be broadcast to the other ranks by the caller
+ *   eg_comm_init       collective over all ranks, on the calling thread's current CUDA device
+ *   eg_splat_bwd_allreduce  eg_splat_bwd over [0, N) in n_ranges (<= 16) Gaussian ranges on `stream`; the gradients
+ *                      of each finished range (its slices of grads = means | scales | quats | opacities, 11 N
+ *                      floats, WRITTEN then summed over ranks in place) are all-reduced on `comm_stream` while the
+ *                      next range is computed; `stream` finally waits for the last collective.  absgrad_accum
+ *                      stays per rank (sum it where it is consumed, edge_gs.py:544-576). */
+int eg_comm_unique_id(void *id128);
+int eg_comm_init(const void *id128, int rank, int world, void **comm_out);
+int eg_comm_destroy(void *comm);
+int eg_splat_bwd_allreduce(const eg_config *cfg, const float *means, const float *quats, const float *scales,
+                           const float *opacities, const float *viewmat, const float *K, const float *rec,
+                           const int32_t *gint, const float *wpix, float seed_scale, const uint32_t *last_depth,
+                           const int32_t *last_gid, const int32_t *tile_stop, const int32_t *status, float *grads,
+                           float *absgrad_accum, int n_ranges, void *comm, void *comm_stream, void *stream);
 
 /* Per-pixel seed of the gsplat-shaped autograd path:
  *   wpix[p] = (sum_ch v_render[p,ch] + v_alpha[p]) * (1 - alpha[p])      (v_render / v_alpha may be NULL) */
