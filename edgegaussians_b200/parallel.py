@@ -107,7 +107,8 @@ class NativeComm:
         with torch.cuda.device(device):
             _lib.check(self.lib.eg_comm_init(ctypes.c_char_p(raw), self.rank, self.world, ctypes.byref(self.handle)),
                        "eg_comm_init")
-        self.stream = torch.cuda.Stream(device=device)
+        # high priority: the collective of a finished range must get SMs while the next range's backward is running
+        self.stream = torch.cuda.Stream(device=device, priority=-1)
 
     def close(self):
         if getattr(self, "handle", None):
