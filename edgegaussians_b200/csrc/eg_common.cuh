@@ -89,18 +89,6 @@ __device__ __forceinline__ eg_f2 f2_mul(eg_f2 a, eg_f2 b) {
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
-// in-place forms for loop-carried accumulators (keeps them in one register pair: no copies)
-__device__ __forceinline__ void f2_acc(eg_f2 &acc, eg_f2 b) { asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(b)); }
-__device__ __forceinline__ void f2_acc_fma(eg_f2 &acc, eg_f2 a, eg_f2 b) {
-    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
-}
-__device__ __forceinline__ eg_f2 f2_abs(eg_f2 a) { return a & 0x7fffffff7fffffffull; }
-__device__ __forceinline__ float f2_hsum(eg_f2 a) {
-    float lo, hi;
-    f2_unpack(a, lo, hi);
-    return lo + hi;
-}
-
 // sigma and opacity*exp(-sigma) with a FIXED operation order (explicit intrinsics, no compiler
 // contraction) so that the forward and the backward kernels take identical skip decisions
 // (sigma < 0, alpha < 1/255) for every (pixel, Gaussian) pair.

@@ -14,11 +14,12 @@
 // Gaussian the pixel composited", which the forward kernels leave in two per-pixel planes (last_depth,
 // last_gid; last_depth = 0xffffffff where the pixel never stopped).  So:
 //   phase 1  lane = Gaussian : record -> tile rectangle, folded conic, row range (eg_splat_setup);
-//   phase 2  lane = (Gaussian, row) : walk the row's span in aligned 4-pixel chunks (one LDG.128 of the
-//            per-pixel seed  w_p = seed * T_final(p)  per chunk), accumulate the row's moments
-//            S0 = sum v_sigma, S1 = sum v_sigma dx, S2 = sum v_sigma dx^2 and the two abs-sums in registers,
-//            turn them into the 8 per-Gaussian 2D gradients, segmented-reduce over the lanes of the same
-//            Gaussian (shuffles) and add into the warp's private shared-memory accumulators;
+//   phase 2  lane = (Gaussian, EG_ROWS_PER_ITEM rows) : walk each row's span in aligned 4-pixel chunks (one LDG.128
+//            of the per-pixel seed  w_p = seed * T_final(p)  per chunk, the next chunk's load in flight), two
+//            pixels per instruction on the packed fp32x2 pipe; accumulate the row's moments S0 = sum v_sigma,
+//            S1 = sum v_sigma dx, S2 = sum v_sigma dx^2 and the two abs-sums in registers, turn them into the 8
+//            per-Gaussian 2D gradients, segmented-reduce over the lanes of the same Gaussian (shuffles) and
+//            add into the warp's private shared-memory accumulators;
 //   phase 3  lane = Gaussian : projection VJP + exp/sigmoid VJP + abs-grad norm, gradients written with plain
 //            stores (each Gaussian has exactly one owner).
 #include "eg_project_vjp.cuh"
