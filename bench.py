@@ -50,6 +50,8 @@ def parse_args():
                     help="fused-step pipeline (edge_gs.enqueue_raster_step); auto = what training would run")
     ap.add_argument("--allreduce-chunks", type=int, default=1,
                     help="N > 1: Gaussian ranges of the backward whose all-reduce overlaps the next range")
+    ap.add_argument("--torch-allreduce", action="store_true",
+                    help="N > 1: all-reduce through torch.distributed instead of the library's own communicator")
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
     return ap.parse_args()
 
@@ -239,7 +241,7 @@ def run_b200(args):
     model.pipeline = args.pipeline
 
     step = GraphedRasterStep(model, W, H, n_slots=V, gt_dtype=torch.uint8, allreduce=world > 1,
-                             allreduce_chunks=args.allreduce_chunks)
+                             allreduce_chunks=args.allreduce_chunks, native_allreduce=not args.torch_allreduce)
     host_vm = [torch.from_numpy(vms[v]).pin_memory() for v in my_views]
     host_K = [torch.from_numpy(Ks[v]).pin_memory() for v in my_views]
     host_gt = [torch.from_numpy(g).pin_memory() for g in gts_u8]
@@ -405,7 +407,7 @@ def run_b200(args):
                                                   "tiles": " (tile binning + per-tile sort/compositing, tile-major backward)"}[ws.pipeline],
                        "stopped_tiles": int(ws.status[5]),
                        "tile_sort": ("n/a" if ws.pipeline == "splat" else "lazy (only tiles near the transmittance stop threshold)" if model._use_lazy() else "every tile"),
-                       "execution": f"CUDA graph replay per iteration (1 memset + {len(kernels)} kernels: {', '.join(kernels)})" + ((", + NCCL all-reduce of the 11N fp32 gradient buffer " + (f"in {step.allreduce_chunks} Gaussian ranges on a side stream, overlapped with the backward of the next range" if step.chunked else "issued after the replay")) if world > 1 else ""),
+                       "execution": f"CUDA graph replay per iteration (1 memset + {ws.n_kernels} kernels; stages: {', '.join(kernels)})" + ((", + NCCL all-reduce of the 11N fp32 gradient buffer " + (f"in {step.allreduce_chunks} Gaussian ranges on a side stream, overlapped with the backward of the next range" if step.chunked else ("issued on the compute stream after the replay (libedgegs communicator)" if step.native_comm is not None else "issued after the replay (torch.distributed)"))) if world > 1 else ""),
                        "parallelism": f"view-sharded dp{world}" if world > 1 else "single GPU"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic_bytes(dom + "_kernel"), "peak_source": peak_src,
@@ -416,7 +418,7 @@ def run_b200(args):
             "e2e": {"value": world * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "api": "GraphedRasterStep.set_view(pinned host) + replay + loss readback"},
             "value_no_l2_flush": world * args.steps / (hot_ms * 1e-3),
-            "gpu_launches": len(kernels) * args.steps,
+            "gpu_launches": ws.n_kernels * args.steps,
             "clocks": clocks,
             "wall_s_timed_region": t_wall,
         }

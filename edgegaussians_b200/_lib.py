@@ -21,7 +21,7 @@ EG_FLAG_NO_EMIT = 4
 
 EXPORTS = ["eg_last_error", "eg_abi_version", "eg_tile_grid", "eg_project_fwd", "eg_bin", "eg_raster_fwd",
            "eg_raster_bwd", "eg_project_bwd", "eg_splat_bwd", "eg_make_seed", "eg_splat_fwd", "eg_splat_resolve", "eg_emit_flagged",
-           "eg_comm_unique_id", "eg_comm_init", "eg_comm_destroy", "eg_splat_bwd_allreduce", "eg_reg_fwd_bwd", "eg_knn_workspace_bytes", "eg_knn", "eg_adam_step"]
+           "eg_comm_unique_id", "eg_comm_init", "eg_comm_destroy", "eg_comm_allreduce", "eg_splat_bwd_allreduce", "eg_reg_fwd_bwd", "eg_knn_workspace_bytes", "eg_knn", "eg_adam_step"]
 
 
 class EgConfig(Structure):
@@ -65,6 +65,7 @@ def load(build_if_missing: bool = True):
     lib.eg_comm_unique_id.argtypes = [P]
     lib.eg_comm_init.argtypes = [P, c_int, c_int, POINTER(c_void_p)]
     lib.eg_comm_destroy.argtypes = [P]
+    lib.eg_comm_allreduce.argtypes = [P, c_int64, P, P]
     lib.eg_splat_bwd_allreduce.argtypes = [cfgp] + [P] * 9 + [c_float] + [P] * 6 + [c_int, P, P, P]
     lib.eg_make_seed.argtypes = [c_int64, P, P, c_int, P, P, P]
     lib.eg_reg_fwd_bwd.argtypes = [c_int, P, P, P, P, c_int, c_int, c_int, c_float, c_float, P, P, P, P, P]

@@ -120,6 +120,18 @@ extern "C" int eg_comm_destroy(void *comm) {
     return 0;
 }
 
+extern "C" int eg_comm_allreduce(float *buf, int64_t count, void *comm, void *stream) {
+    if (buf == nullptr || comm == nullptr || count < 0) {
+        eg_set_error("eg_comm_allreduce: bad arguments");
+        return 1;
+    }
+    EgComm *c = reinterpret_cast<EgComm *>(comm);
+    if (c->world == 1 || count == 0) return 0;
+    if (int rc = g_nccl.AllReduce(buf, buf, (size_t)count, kNcclFloat32, kNcclSum, c->comm, (cudaStream_t)stream))
+        return nccl_fail("ncclAllReduce", rc);
+    return 0;
+}
+
 extern "C" int eg_splat_bwd_allreduce(const eg_config *cfg, const float *means, const float *quats,
                                       const float *scales, const float *opacities, const float *viewmat,
                                       const float *K, const float *rec, const int32_t *gint, const float *wpix,

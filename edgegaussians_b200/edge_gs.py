@@ -378,6 +378,7 @@ class EdgeGaussianSplatting(torch.nn.Module):
                                   None if tiles_bwd else _p(ws.last_gid), None, None, _p(ws.status), s), "eg_raster_fwd")
             cb("raster_fwd")
         ws.pipeline = pipeline
+        ws.n_kernels = {"splat": 6, "tiles+splat": 4, "tiles": 5}[pipeline]   # launches of this library per iteration
         ws.bwd_args = (cfg, viewmat, K, seed, accumulate_absgrad)
         if parts == "forward":
             if pipeline == "tiles":

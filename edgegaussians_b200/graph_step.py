@@ -19,7 +19,7 @@ from .engine import get_engine
 class GraphedRasterStep:
     def __init__(self, model: EdgeGaussianSplatting, width: int, height: int, n_slots: int, gt_dtype=torch.uint8,
                  loss_weight: float = 1.0, accumulate_absgrad: bool = True, allreduce_group=None, allreduce: bool = False,
-                 allreduce_chunks: int = 4):
+                 allreduce_chunks: int = 1, native_allreduce: bool = True):
         dev = model.means.device
         self.model, self.W, self.H, self.n_slots = model, width, height, n_slots
         self.loss_weight, self.accumulate_absgrad = loss_weight, accumulate_absgrad
@@ -38,6 +38,9 @@ class GraphedRasterStep:
         self.comm_stream = torch.cuda.Stream(device=dev) if allreduce else None
         self.chunked = False
         self.native_comm = None   # parallel.NativeComm: ranged backward + collectives as one C call
+        # one all-reduce per step through libedgegs' own communicator, enqueued straight on the compute stream
+        # (torch.distributed routes through an internal stream: two extra event hops per step)
+        self.native_allreduce = native_allreduce
         self.graphs: Dict[int, torch.cuda.CUDAGraph] = {}
         self.ws: Optional[RasterStepWorkspace] = None
         self._capacity = None
@@ -99,7 +102,8 @@ class GraphedRasterStep:
         torch.cuda.synchronize()
         self.chunked = (self._distributed() and self.allreduce_chunks > 1
                         and self.model.current_pipeline() != "tiles" and stage_cb is None)
-        if self.chunked and self.native_comm is None and not getattr(self, "python_ranges", False):
+        if (self._distributed() and self.native_comm is None and not getattr(self, "python_ranges", False)
+                and (self.chunked or self.native_allreduce)):
             from .parallel import NativeComm
             self.native_comm = NativeComm(self.model.means.device, self.allreduce_group)
         with torch.cuda.graph(g):
@@ -132,6 +136,8 @@ class GraphedRasterStep:
                 done = torch.cuda.Event()
                 done.record(self.comm_stream)
                 main.wait_event(done)   # the optimizer / next step needs the reduced gradients
+            elif self.native_comm is not None and self.native_allreduce:
+                self.native_comm.allreduce_(ws.grads)
             else:
                 dist.all_reduce(ws.grads, group=self.allreduce_group)
         return self.ws

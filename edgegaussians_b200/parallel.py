@@ -110,6 +110,14 @@ class NativeComm:
         # high priority: the collective of a finished range must get SMs while the next range's backward is running
         self.stream = torch.cuda.Stream(device=device, priority=-1)
 
+    def allreduce_(self, flat: torch.Tensor) -> None:
+        """In-place fp32 sum over the ranks, enqueued directly on the current stream."""
+        import ctypes
+        from . import _lib
+        _lib.check(self.lib.eg_comm_allreduce(ctypes.c_void_p(flat.data_ptr()), flat.numel(), self.handle,
+                                              ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                   "eg_comm_allreduce")
+
     def close(self):
         if getattr(self, "handle", None):
             self.lib.eg_comm_destroy(self.handle)

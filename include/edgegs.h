@@ -215,6 +215,8 @@ int eg_splat_bwd(const eg_config *cfg, const float *means, const float *quats, c
 int eg_comm_unique_id(void *id128);
 int eg_comm_init(const void *id128, int rank, int world, void **comm_out);
 int eg_comm_destroy(void *comm);
+/* in-place fp32 sum over the ranks, enqueued directly on `stream` (no side stream, no event hops) */
+int eg_comm_allreduce(float *buf, int64_t count, void *comm, void *stream);
 int eg_splat_bwd_allreduce(const eg_config *cfg, const float *means, const float *quats, const float *scales,
                            const float *opacities, const float *viewmat, const float *K, const float *rec,
                            const int32_t *gint, const float *wpix, float seed_scale, const uint32_t *last_depth,
