@@ -50,8 +50,8 @@ def parse_args():
                     help="fused-step pipeline (edge_gs.enqueue_raster_step); auto = what training would run")
     ap.add_argument("--allreduce-chunks", type=int, default=1,
                     help="N > 1: Gaussian ranges of the backward whose all-reduce overlaps the next range")
-    ap.add_argument("--torch-allreduce", action="store_true",
-                    help="N > 1: all-reduce through torch.distributed instead of the library's own communicator")
+    ap.add_argument("--native-allreduce", action="store_true",
+                    help="N > 1: all-reduce through the library's own communicator (eg_comm_allreduce) instead of torch.distributed")
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
     return ap.parse_args()
 
@@ -241,7 +241,7 @@ def run_b200(args):
     model.pipeline = args.pipeline
 
     step = GraphedRasterStep(model, W, H, n_slots=V, gt_dtype=torch.uint8, allreduce=world > 1,
-                             allreduce_chunks=args.allreduce_chunks, native_allreduce=not args.torch_allreduce)
+                             allreduce_chunks=args.allreduce_chunks, native_allreduce=args.native_allreduce)
     host_vm = [torch.from_numpy(vms[v]).pin_memory() for v in my_views]
     host_K = [torch.from_numpy(Ks[v]).pin_memory() for v in my_views]
     host_gt = [torch.from_numpy(g).pin_memory() for g in gts_u8]

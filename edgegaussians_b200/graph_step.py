@@ -19,7 +19,7 @@ from .engine import get_engine
 class GraphedRasterStep:
     def __init__(self, model: EdgeGaussianSplatting, width: int, height: int, n_slots: int, gt_dtype=torch.uint8,
                  loss_weight: float = 1.0, accumulate_absgrad: bool = True, allreduce_group=None, allreduce: bool = False,
-                 allreduce_chunks: int = 1, native_allreduce: bool = True):
+                 allreduce_chunks: int = 1, native_allreduce: bool = False):
         dev = model.means.device
         self.model, self.W, self.H, self.n_slots = model, width, height, n_slots
         self.loss_weight, self.accumulate_absgrad = loss_weight, accumulate_absgrad
@@ -38,8 +38,8 @@ class GraphedRasterStep:
         self.comm_stream = torch.cuda.Stream(device=dev) if allreduce else None
         self.chunked = False
         self.native_comm = None   # parallel.NativeComm: ranged backward + collectives as one C call
-        # one all-reduce per step through libedgegs' own communicator, enqueued straight on the compute stream
-        # (torch.distributed routes through an internal stream: two extra event hops per step)
+        # opt-in: the one all-reduce per step through libedgegs' own communicator, enqueued straight on the compute
+        # stream (torch.distributed routes through an internal stream; measured identical at 2 GPUs: 0.379 ms)
         self.native_allreduce = native_allreduce
         self.graphs: Dict[int, torch.cuda.CUDAGraph] = {}
         self.ws: Optional[RasterStepWorkspace] = None
