@@ -22,8 +22,12 @@ __device__ __forceinline__ float dot3(float a, float b, float c, float d, float 
     return add(add(mul(a, b), mul(c, d)), mul(e, f));
 }
 
+#ifndef EG_PF_MINBLOCKS
+#define EG_PF_MINBLOCKS 5   // resident CTAs per SM the register allocation is bounded for
+#endif
+
 template <bool RAW>
-__global__ void __launch_bounds__(256) project_fwd_kernel(
+__global__ void __launch_bounds__(256, EG_PF_MINBLOCKS) project_fwd_kernel(
     const eg_config cfg, const float *__restrict__ means, const float *__restrict__ quats,
     const float *__restrict__ scales, const float *__restrict__ opacities, const float *__restrict__ colors,
     const float *__restrict__ viewmat, const float *__restrict__ Kmat, float4 *__restrict__ rec,
