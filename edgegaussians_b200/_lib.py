@@ -21,7 +21,8 @@ EG_FLAG_NO_EMIT = 4
 
 EXPORTS = ["eg_last_error", "eg_abi_version", "eg_tile_grid", "eg_project_fwd", "eg_bin", "eg_raster_fwd",
            "eg_raster_bwd", "eg_project_bwd", "eg_splat_bwd", "eg_make_seed", "eg_splat_fwd", "eg_splat_resolve", "eg_emit_flagged",
-           "eg_comm_unique_id", "eg_comm_init", "eg_comm_destroy", "eg_comm_allreduce", "eg_splat_bwd_allreduce", "eg_reg_fwd_bwd", "eg_knn_workspace_bytes", "eg_knn", "eg_adam_step"]
+           "eg_comm_unique_id", "eg_comm_init", "eg_comm_destroy", "eg_comm_allreduce", "eg_splat_bwd_allreduce", "eg_reg_fwd_bwd", "eg_knn_workspace_bytes", "eg_knn", "eg_adam_step",
+           "eg_projecting_fraction"]
 
 
 class EgConfig(Structure):
@@ -71,6 +72,7 @@ def load(build_if_missing: bool = True):
     lib.eg_reg_fwd_bwd.argtypes = [c_int, P, P, P, P, c_int, c_int, c_int, c_float, c_float, P, P, P, P, P]
     lib.eg_knn_workspace_bytes.argtypes = [c_int]
     lib.eg_knn.argtypes = [c_int, P, c_int, c_int, P, P, ctypes.c_size_t, P]
+    lib.eg_projecting_fraction.argtypes = [c_int, P, c_int, P, P, P, P, P, P, P]
     lib.eg_adam_step.argtypes = [c_int64, P, P, P, P] + [c_double] * 6 + [c_int, P]
     for name in EXPORTS[2:]:
         getattr(lib, name).restype = c_int

@@ -269,6 +269,18 @@ class EdgeGaussianSplatting(torch.nn.Module):
         self.absgrads += self.xys.absgrad[0].norm(dim=-1)
         self.absgrads_normalize_factor += 1
 
+    # ------------------------------------------------------------------ visibility filter (section 8f-4)
+    def not_projecting_mask(self, min_projecting_fraction=0.1) -> torch.Tensor:
+        """The cull mask of cull_gaussians_not_projecting (edge_gs.py:578-601): True where the mean lands on an
+        edge pixel in fewer than ``min_projecting_fraction`` of the views.  One kernel over all views instead of
+        the reference's per-view CPU loop; the optimizer surgery it feeds (cull_gaussians) is out of scope."""
+        from .visibility import PackedViews, projecting_fraction
+        key = (len(self.viewcams), len(self.edge_masks))
+        if getattr(self, "_packed_views_key", None) != key:
+            self._packed_views = PackedViews(self.viewcams, self.edge_masks, self.means.device)
+            self._packed_views_key = key
+        return projecting_fraction(self.means.data, self._packed_views) < min_projecting_fraction
+
     # ------------------------------------------------------------------ regularisers (a10-a12)
     def update_nearest_neighbors(self):
         from .knn import knn_indices

@@ -249,6 +249,16 @@ size_t eg_knn_workspace_bytes(int n);
 int eg_knn(int n, const float *points, int kk, int skip, int32_t *out, void *workspace,
            size_t workspace_bytes, void *stream);
 
+/* "next", SURVEY.md section 8f-4: batched visibility filter.  Replaces the per-view CPU loop of
+ * cull_gaussians_not_projecting (edge_gs.py:578-601) up to its threshold: fraction [N] fp32 = share of the
+ * n_views views in which the Gaussian's mean projects (P = K @ viewmat[:3,:4], round half to even, no depth test --
+ * the reference's arithmetic) inside the image and onto a non-zero pixel of that view's edge mask.
+ * viewmats [V,16], Ks [V,9], sizes [V,2] i32 = (width, height), masks u8 = the views' [H,W] masks back to back,
+ * mask_offsets [V] i64 = start of each view's mask in `masks`.  At most 1024 views per call. */
+int eg_projecting_fraction(int n, const float *means, int n_views, const float *viewmats, const float *Ks,
+                           const int32_t *sizes, const uint8_t *masks, const int64_t *mask_offsets,
+                           float *fraction, void *stream);
+
 /* a13 ("next"): fused Adam update of one parameter tensor, torch.optim.Adam
  * semantics as configured at utils/train_utils.py:48-65 (no weight decay, no amsgrad);
  * bias_correction{1,2} = 1 - beta{1,2}^t.  Hyper-parameters are doubles (as Python floats are) and are

@@ -78,3 +78,16 @@ def test_ratio_loss_matches_reference(golden_dir):
     loss, vs = rp.ratio_loss(g["scales"])
     assert loss == pytest.approx(float(g["ratio_loss"]), rel=1e-5)
     np.testing.assert_allclose(vs, g["ratio_vscales"], atol=1e-8, rtol=1e-4)
+
+
+def test_projecting_fraction_matches_reference(golden_dir):
+    """the port of cull_gaussians_not_projecting against the masks the real
+    reference method computed (tests/golden/make_golden_visibility.py)."""
+    g = _load(golden_dir, "visibility.npz")
+    sizes = g["sizes"]
+    masks = [np.unpackbits(g[f"edge_mask{v}"])[: int(w) * int(h)].reshape(int(h), int(w)).astype(bool)
+             for v, (w, h) in enumerate(sizes)]
+    frac = rp.projecting_fraction(g["means"], g["Ks"], g["viewmats"], sizes, masks)
+    assert frac.shape == (g["means"].shape[0],) and 0.0 <= frac.min() and frac.max() <= 1.0
+    for thr in (0.1, 0.3, 0.5):
+        np.testing.assert_array_equal(frac < np.float32(thr), g[f"cull_mask_{thr}"])
