@@ -47,6 +47,18 @@ __device__ __forceinline__ float pair_fwd(const EgSplatG &G, const float b1, con
     return eg_pair_valid(ov, p, G.lo, in_span) ? l : 0.0f;
 }
 
+// log2(1 - alpha) of two adjacent pixels; the exponent runs on the packed fp32x2 pipe (element-wise bit-identical
+// to eg_pow2row), MUFU and the validity select stay scalar.  ALIGNED rows only (no per-pixel clipping).
+__device__ __forceinline__ void pair2_fwd(const EgSplatG &G, const eg_f2 mx2, const eg_f2 fa2, const eg_f2 b12,
+                                          const eg_f2 c02, const eg_f2 npx, float &l0, float &l1) {
+    const eg_f2 dx = f2_add(mx2, npx);
+    float p0, p1;
+    f2_unpack(f2_fma(f2_fma(fa2, dx, b12), dx, c02), p0, p1);
+    const float ov0 = eg_ex2(p0), ov1 = eg_ex2(p1);
+    l0 = eg_select_valid(eg_lg2(1.0f - fminf(EG_ALPHA_MAX, ov0)), ov0, p0, G.lo);
+    l1 = eg_select_valid(eg_lg2(1.0f - fminf(EG_ALPHA_MAX, ov1)), ov1, p1, G.lo);
+}
+
 template <bool ALIGNED>
 __device__ __forceinline__ void walk_row_fwd(const EgSplatG &G, const int y, const int W, float *__restrict__ logT) {
     const float dy = G.my - ((float)y + 0.5f);
@@ -56,23 +68,30 @@ __device__ __forceinline__ void walk_row_fwd(const EgSplatG &G, const int y, con
     int x = xa & ~3;
     const int xend = xb & ~3;
     float *ptr = logT + ((size_t)y * (size_t)W + (size_t)x);
-    for (; x <= xend; x += 4, ptr += 4) {
-        const float px = (float)x + 0.5f;  // pixel centres x + 0.5 .. x + 3.5 are exact in fp32
-        // ALIGNED: W % 4 == 0 and the tile rectangle's columns are multiples of 16, so an aligned chunk that
-        // overlaps the span lies entirely inside the rectangle -- no per-pixel clipping needed
-        const float v0 = pair_fwd<!ALIGNED>(G, b1, c0, px, ALIGNED || (x >= xa && x <= xb));
-        const float v1 = pair_fwd<!ALIGNED>(G, b1, c0, px + 1.0f, ALIGNED || (x + 1 >= xa && x + 1 <= xb));
-        const float v2 = pair_fwd<!ALIGNED>(G, b1, c0, px + 2.0f, ALIGNED || (x + 2 >= xa && x + 2 <= xb));
-        const float v3 = pair_fwd<!ALIGNED>(G, b1, c0, px + 3.0f, ALIGNED || (x + 3 >= xa && x + 3 <= xb));
-        if (ALIGNED) {
+    if (ALIGNED) {
+        // W % 4 == 0 and the tile rectangle's columns are multiples of 16, so an aligned chunk that overlaps the span
+        // lies entirely inside the rectangle -- no per-pixel clipping needed
+        const eg_f2 mx2 = f2_dup(G.mx), fa2 = f2_dup(G.fa), b12 = f2_dup(b1), c02 = f2_dup(c0);
+        float nb = -((float)x + 0.5f);  // negated pixel centre, exact; carried from chunk to chunk (no int->float per chunk)
+        for (; x <= xend; x += 4, ptr += 4, nb -= 4.0f) {
+            float v0, v1, v2, v3;
+            pair2_fwd(G, mx2, fa2, b12, c02, f2_pack(nb, nb - 1.0f), v0, v1);
+            pair2_fwd(G, mx2, fa2, b12, c02, f2_pack(nb - 2.0f, nb - 3.0f), v2, v3);
             if ((__float_as_uint(v0) | __float_as_uint(v1) | __float_as_uint(v2) | __float_as_uint(v3)) << 1)
                 eg_red_add_v4(ptr, v0, v1, v2, v3);
-        } else {
-            if (v0 != 0.0f) red_add_f32(ptr, v0);
-            if (v1 != 0.0f) red_add_f32(ptr + 1, v1);
-            if (v2 != 0.0f) red_add_f32(ptr + 2, v2);
-            if (v3 != 0.0f) red_add_f32(ptr + 3, v3);
         }
+        return;
+    }
+    for (; x <= xend; x += 4, ptr += 4) {
+        const float px = (float)x + 0.5f;  // pixel centres x + 0.5 .. x + 3.5 are exact in fp32
+        const float v0 = pair_fwd<true>(G, b1, c0, px, x >= xa && x <= xb);
+        const float v1 = pair_fwd<true>(G, b1, c0, px + 1.0f, x + 1 >= xa && x + 1 <= xb);
+        const float v2 = pair_fwd<true>(G, b1, c0, px + 2.0f, x + 2 >= xa && x + 2 <= xb);
+        const float v3 = pair_fwd<true>(G, b1, c0, px + 3.0f, x + 3 >= xa && x + 3 <= xb);
+        if (v0 != 0.0f) red_add_f32(ptr, v0);
+        if (v1 != 0.0f) red_add_f32(ptr + 1, v1);
+        if (v2 != 0.0f) red_add_f32(ptr + 2, v2);
+        if (v3 != 0.0f) red_add_f32(ptr + 3, v3);
     }
 }
 
@@ -272,26 +291,26 @@ __global__ void __launch_bounds__(256) emit_flagged_kernel(const eg_config cfg, 
                                                            int32_t *__restrict__ tile_cnt,
                                                            unsigned long long *__restrict__ keys,
                                                            int32_t *__restrict__ status) {
-    if (status[EG_ST_STOPPED] == 0 || status[EG_ST_OVERFLOW]) return;
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= cfg.n) return;
-    const int2 gi = __ldg(gint + g);
-    if (gi.x <= 0 || gi.y <= 0) return;
-    const float4 r0 = __ldg(rec + 2 * g);
-    uint32_t x0, y0, x1, y1;
-    eg_tile_rect(r0.x, r0.y, gi.x, tw, th, x0, y0, x1, y1);
-    const unsigned long long key = ((unsigned long long)__float_as_uint(r0.w) << 32) | (unsigned int)g;
-    for (uint32_t i = y0; i < y1; ++i)
-        for (uint32_t j = x0; j < x1; ++j) {
-            const size_t t = (size_t)i * tw + j;
-            if (__ldg(tile_stop + t) == 0) continue;
-            const int pos = atomicAdd(tile_cnt + t, 1);
-            if (pos < cfg.tile_capacity) keys[t * (size_t)cfg.tile_capacity + pos] = key;
-            else {  // bucket too small: the caller re-runs with tile_capacity >= status[EG_ST_MAXTILE]
-                status[EG_ST_OVERFLOW] = 1;
-                atomicMax(status + EG_ST_MAXTILE, pos + 1);
+    if (status[EG_ST_STOPPED] == 0 || status[EG_ST_OVERFLOW]) return;  // the usual case: a small grid, gone at once
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < cfg.n; g += gridDim.x * blockDim.x) {
+        const int2 gi = __ldg(gint + g);
+        if (gi.x <= 0 || gi.y <= 0) continue;
+        const float4 r0 = __ldg(rec + 2 * g);
+        uint32_t x0, y0, x1, y1;
+        eg_tile_rect(r0.x, r0.y, gi.x, tw, th, x0, y0, x1, y1);
+        const unsigned long long key = ((unsigned long long)__float_as_uint(r0.w) << 32) | (unsigned int)g;
+        for (uint32_t i = y0; i < y1; ++i)
+            for (uint32_t j = x0; j < x1; ++j) {
+                const size_t t = (size_t)i * tw + j;
+                if (__ldg(tile_stop + t) == 0) continue;
+                const int pos = atomicAdd(tile_cnt + t, 1);
+                if (pos < cfg.tile_capacity) keys[t * (size_t)cfg.tile_capacity + pos] = key;
+                else {  // bucket too small: the caller re-runs with tile_capacity >= status[EG_ST_MAXTILE]
+                    status[EG_ST_OVERFLOW] = 1;
+                    atomicMax(status + EG_ST_MAXTILE, pos + 1);
+                }
             }
-        }
+    }
 }
 
 }  // namespace
@@ -371,7 +390,8 @@ extern "C" int eg_emit_flagged(const eg_config *cfg, const float *rec, const int
     if (cfg->n <= 0) return 0;
     int tw, th;
     eg_tile_grid(cfg->width, cfg->height, cfg->tile_size, &tw, &th);
-    emit_flagged_kernel<<<(cfg->n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+    const int blocks = (cfg->n + 255) / 256, grid = blocks < 148 * 4 ? blocks : 148 * 4;
+    emit_flagged_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
         *cfg, tw, th, (const float4 *)rec, (const int2 *)gint, tile_stop, tile_cnt, (unsigned long long *)keys, status);
     return eg_check_launch("eg_emit_flagged");
 }
