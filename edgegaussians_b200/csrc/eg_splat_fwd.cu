@@ -20,6 +20,8 @@
 // and eg_raster_fwd sorts and composites just those tiles front to back with the stop rule.  With the
 // reference's translucent Gaussians (opacity 0.08 at init, configs/*.json:35) no tile is flagged and both
 // fallback kernels return immediately.
+#include <cstdlib>
+
 #include "eg_splat.cuh"
 
 namespace {
@@ -132,6 +134,113 @@ __global__ void __launch_bounds__(SF_WARPS * 32) splat_fwd_kernel(const eg_confi
 #pragma unroll
             for (int r = 0; r < EG_ROWS_PER_ITEM; ++r)
                 if (r0 + r < Go.nrows) walk_row_fwd<ALIGNED>(Go, Go.ylo + r0 + r, cfg.width, logT);
+        }
+    }
+}
+
+// Chunk-balanced variant (W % 4 == 0): lane = one aligned 4-pixel chunk.
+// The row-per-lane walk above leaves lanes idle while the longest row of a 32-row batch finishes (69 % of the slots
+// are used) and makes every lane of a reduction instruction touch a different 128-byte line.  Here a batch of 32 rows
+// first derives its spans (lane = row), then the chunks of those rows form a dense list (same owner lookup as for the
+// rows) that the warp consumes 32 chunks at a time: every lane evaluates exactly one chunk, and the chunks of a row
+// sit in adjacent lanes, so their vector reductions share cache lines.
+struct __align__(16) EgRowDesc {
+    float mx, fa, b1, c0;   // eg_pow2row constants of the row
+    float lo, nb0;          // log2(opacity'), negated centre of the row's first visited pixel
+    int cstart, pad;        // index of the row's first chunk in the batch's chunk list
+    float *ptr;             // &logT[y][4 * first chunk]
+    long long pad2;
+};
+
+__global__ void __launch_bounds__(SF_WARPS * 32) splat_fwd_chunks_kernel(const eg_config cfg, const int tw, const int th,
+                                                                         const float4 *__restrict__ rec,
+                                                                         const int2 *__restrict__ gint,
+                                                                         float *__restrict__ logT,
+                                                                         const int32_t *__restrict__ status) {
+    __shared__ EgSplatG s_g[SF_WARPS][32];
+    __shared__ EgRowDesc s_row[SF_WARPS][32];
+    if (status[EG_ST_OVERFLOW]) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    const int g = (blockIdx.x * SF_WARPS + warp) * 32 + lane;
+    EgSplatG G;
+    G.nrows = 0;
+    if (g < cfg.n) {
+        const int2 gi = __ldg(gint + g);
+        eg_splat_setup(cfg, tw, th, g, __ldg(rec + 2 * g), __ldg(rec + 2 * g + 1), gi.x, G);
+    }
+    const int nrows = G.nrows;
+    int incl = nrows;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    G.start = incl - nrows;
+    const unsigned ne = __ballot_sync(0xffffffffu, nrows > 0);
+    if (nrows > 0) s_g[warp][__popc(ne & lt)] = G;  // compacted: see EgOwnerIter
+    const int R = __shfl_sync(0xffffffffu, incl, 31);
+    __syncwarp();
+    EgOwnerIter rows;
+    for (int base = 0; base < R; base += 32) {
+        // ---- lane = row: span -> chunk count, row descriptor ----
+        const int item = base + lane;
+        const int k = rows.owner(base, lane, incl, nrows > 0);
+        int nch = 0;
+        EgRowDesc D;
+        if (item < R) {
+            const EgSplatG Go = s_g[warp][k];
+            const int y = Go.ylo + (item - Go.start);
+            const float dy = Go.my - ((float)y + 0.5f);
+            const float b1 = eg_pow2row_b1(Go.fb, dy), c0 = eg_pow2row_c0(Go.fc, Go.lo, dy);
+            int xa, xb;
+            if (eg_row_span(Go, b1, c0, xa, xb)) {
+                const int c_first = xa >> 2;
+                nch = (xb >> 2) - c_first + 1;
+                D.mx = Go.mx; D.fa = Go.fa; D.b1 = b1; D.c0 = c0; D.lo = Go.lo;
+                D.nb0 = -((float)(4 * c_first) + 0.5f);
+                D.ptr = logT + ((size_t)y * (size_t)cfg.width + (size_t)(4 * c_first));
+            }
+        }
+        int cincl = nch;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, cincl, d);
+            if (lane >= d) cincl += t;
+        }
+        const int C = __shfl_sync(0xffffffffu, cincl, 31);
+        const unsigned nz = __ballot_sync(0xffffffffu, nch > 0);
+        __syncwarp();  // the previous batch's descriptors are dead
+        if (nch > 0) {
+            D.cstart = cincl - nch;
+            s_row[warp][__popc(nz & lt)] = D;
+        }
+        __syncwarp();
+        // ---- lane = chunk ----
+        EgOwnerIter chunks;
+        for (int cb = 0; cb < C; cb += 32) {
+            const int ci = cb + lane;
+            const int r = chunks.owner(cb, lane, cincl, nch > 0);
+            if (ci < C) {
+                const EgRowDesc Dr = s_row[warp][r];
+                const int j = ci - Dr.cstart;
+                const float nb = Dr.nb0 - (float)(4 * j);  // exact
+                float l0, l1, l2, l3;
+                {
+                    const eg_f2 mx2 = f2_dup(Dr.mx), fa2 = f2_dup(Dr.fa), b12 = f2_dup(Dr.b1), c02 = f2_dup(Dr.c0);
+                    float p0, p1, p2, p3;
+                    const eg_f2 dxa = f2_add(mx2, f2_pack(nb, nb - 1.0f)), dxb = f2_add(mx2, f2_pack(nb - 2.0f, nb - 3.0f));
+                    f2_unpack(f2_fma(f2_fma(fa2, dxa, b12), dxa, c02), p0, p1);
+                    f2_unpack(f2_fma(f2_fma(fa2, dxb, b12), dxb, c02), p2, p3);
+                    const float o0 = eg_ex2(p0), o1 = eg_ex2(p1), o2 = eg_ex2(p2), o3 = eg_ex2(p3);
+                    l0 = eg_select_valid(eg_lg2(1.0f - fminf(EG_ALPHA_MAX, o0)), o0, p0, Dr.lo);
+                    l1 = eg_select_valid(eg_lg2(1.0f - fminf(EG_ALPHA_MAX, o1)), o1, p1, Dr.lo);
+                    l2 = eg_select_valid(eg_lg2(1.0f - fminf(EG_ALPHA_MAX, o2)), o2, p2, Dr.lo);
+                    l3 = eg_select_valid(eg_lg2(1.0f - fminf(EG_ALPHA_MAX, o3)), o3, p3, Dr.lo);
+                }
+                if ((__float_as_uint(l0) | __float_as_uint(l1) | __float_as_uint(l2) | __float_as_uint(l3)) << 1)
+                    eg_red_add_v4(Dr.ptr + 4 * j, l0, l1, l2, l3);
+            }
         }
     }
 }
@@ -334,7 +443,11 @@ extern "C" int eg_splat_fwd(const eg_config *cfg, const float *rec, const int32_
     eg_tile_grid(cfg->width, cfg->height, cfg->tile_size, &tw, &th);
     const int block = SF_WARPS * 32, grid = (cfg->n + block - 1) / block;
     cudaStream_t s = (cudaStream_t)stream;
-    if ((cfg->width % 4 == 0) && (((uintptr_t)logT & 15) == 0))
+    // EG_FWD_ROWS=1 selects the row-per-lane walk on aligned images too (A/B measurements)
+    static const bool rows_only = getenv("EG_FWD_ROWS") != nullptr && getenv("EG_FWD_ROWS")[0] == '1';
+    if ((cfg->width % 4 == 0) && (((uintptr_t)logT & 15) == 0) && !rows_only)
+        splat_fwd_chunks_kernel<<<grid, block, 0, s>>>(*cfg, tw, th, (const float4 *)rec, (const int2 *)gint, logT, status);
+    else if ((cfg->width % 4 == 0) && (((uintptr_t)logT & 15) == 0))
         splat_fwd_kernel<true><<<grid, block, 0, s>>>(*cfg, tw, th, (const float4 *)rec, (const int2 *)gint, logT, status);
     else
         splat_fwd_kernel<false><<<grid, block, 0, s>>>(*cfg, tw, th, (const float4 *)rec, (const int2 *)gint, logT, status);
