@@ -196,6 +196,12 @@ class EdgeGaussianSplatting(torch.nn.Module):
         self.gauss_params = torch.nn.ParameterDict({
             k: torch.nn.Parameter(state_dict[f"gauss_params.{k}"].to(self.device)) for k in ["means", "scales", "quats", "opacities"]})
 
+    def export_as_ply(self, ply_path):  # edge_gs.py:635-642
+        from .io_utils import write_gaussian_params_as_ply
+        write_gaussian_params_as_ply(self.means.detach().cpu().numpy(), torch.exp(self.scales).detach().cpu().numpy(),
+                                     self.quats.detach().cpu().numpy(),
+                                     torch.sigmoid(self.opacities).detach().cpu().numpy(), ply_path)
+
     # ------------------------------------------------------------------ forward through the gsplat-shaped op (a2)
     def get_outputs(self, camera: BaseCamera) -> Dict[str, Union[torch.Tensor, List]]:
         if self.config.rasterize_mode not in ["antialiased", "classic"]:
