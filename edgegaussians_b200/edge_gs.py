@@ -35,16 +35,25 @@ from .rasterization import rasterization
 
 @dataclass
 class EdgeGaussianSplattingConfig:
-    """Hot-path subset of edge_gs.py:16-54 (unknown keys are ignored, as dacite does there)."""
+    """The fields of edge_gs.py:16-54 this package uses (unknown keys are ignored, as dacite does there)."""
     init_scales_val: float = 0.005
     init_opacity_val: float = 0.08
     edge_detection_threshold: float = 0.5
     rasterize_mode: str = "antialiased"   # not a dataclass field in the reference: always "antialiased"
+    # densify / cull bookkeeping (edge_gs.py:384-488, 544-576)
+    dup_threshold_type: str = "percentile"
+    dup_threshold_value: float = 0.95
+    dup_factor: int = 2
+    init_dup_rand_noise_scale: float = 0.05
+    cull_opacity_type: str = "absolute"
+    cull_opacity_value: float = 0.05
+    reset_opacity_value: float = 0.08
+    cull_gaussians_not_projecting_threshold: float = 0.35
 
     @classmethod
     def from_dict(cls, data: Optional[dict]):
         data = data or {}
-        names = {"init_scales_val", "init_opacity_val", "edge_detection_threshold"}
+        names = {f for f in cls.__dataclass_fields__ if f != "rasterize_mode"}
         return cls(**{k: v for k, v in data.items() if k in names})
 
 
@@ -274,6 +283,92 @@ class EdgeGaussianSplatting(torch.nn.Module):
             self.reset_absgrads()
         self.absgrads += self.xys.absgrad[0].norm(dim=-1)
         self.absgrads_normalize_factor += 1
+
+    # ------------------------------------------------------------------ densify / cull bookkeeping (section 8f-3)
+    # Mirrors of edge_gs.py:384-488, 544-576.  Everything stays on the parameters' device (the reference detours
+    # through numpy for the threshold); `optimizers` is the reference's dict name -> single-parameter Adam
+    # (utils/train_utils.py:48-65).  Resizing N invalidates the fused step's workspace and graphs (rebuilt on use).
+    def _resize_optimizer(self, optimizer, new_param, resize):
+        """Re-key the optimizer to ``new_param``; ``resize`` maps each per-element state tensor to its new rows."""
+        old = optimizer.param_groups[0]["params"][0]
+        state = optimizer.state.pop(old, {})
+        for key in ("exp_avg", "exp_avg_sq"):
+            if key in state:
+                state[key] = resize(state[key])
+        optimizer.param_groups[0]["params"] = [new_param]
+        optimizer.state[new_param] = state
+
+    def _after_resize(self):
+        self._ws = None
+        self._packed_views_key = None
+
+    def reset_opacities(self):  # edge_gs.py:425-429 (clamps the stored logits, as the reference does)
+        self.opacities.data = torch.clamp(self.opacities.data, max=self.config.reset_opacity_value)
+
+    def cull_gaussians(self, optimizers, cull_mask, reset_rest=True):  # edge_gs.py:413-423
+        keep = ~cull_mask.to(self.means.device)
+        for name in list(self.gauss_params.keys()):
+            self.gauss_params[name] = torch.nn.Parameter(self.gauss_params[name].data[keep])
+        if reset_rest:
+            self.reset_opacities()
+        for name, params in self.get_gaussian_param_groups().items():
+            self._resize_optimizer(optimizers[name], params[0], lambda t: t[keep])
+        self.absgrads = self.absgrads[keep]
+        self._after_resize()
+        return int(cull_mask.sum())
+
+    def dup_gaussians(self, optimizers, dup_mask):  # edge_gs.py:460-474
+        mask = torch.as_tensor(dup_mask).to(self.means.device).reshape(-1)
+        copies = self.config.dup_factor - 1
+        for name in list(self.gauss_params.keys()):
+            p = self.gauss_params[name].data
+            extra = torch.cat([p[mask]] * copies, dim=0) if copies > 0 else p[:0]
+            if name == "means":  # the copies are jittered; one randn_like over all of them, as in the reference
+                extra = extra + torch.randn_like(extra) * self.config.init_dup_rand_noise_scale
+            self.gauss_params[name] = torch.nn.Parameter(torch.cat([p, extra], dim=0))
+        n_new = copies * int(mask.sum())
+        for name, params in self.get_gaussian_param_groups().items():
+            self._resize_optimizer(optimizers[name], params[0],
+                                   lambda t: torch.cat([t, t.new_zeros((n_new,) + tuple(t.shape[1:]))], dim=0))
+        self._after_resize()
+        return int(mask.sum())
+
+    def duplicate_all_existing_gaussians(self, optimizers):  # edge_gs.py:491-496
+        return self.dup_gaussians(optimizers, torch.ones(self.num_points, dtype=torch.bool))
+
+    def cull_gaussians_opacity(self, optimizers):  # edge_gs.py:477-488
+        act = torch.sigmoid(self.opacities)
+        if self.config.cull_opacity_type == "percentile":
+            mask = act < torch.quantile(act, self.config.cull_opacity_value)
+        elif self.config.cull_opacity_type == "absolute":
+            mask = act < self.config.cull_opacity_value
+        else:
+            raise ValueError(f"unknown cull_opacity_type {self.config.cull_opacity_type!r}")
+        return self.cull_gaussians(optimizers, mask.reshape(-1))
+
+    def duplicate_high_pos_gradients(self, optimizers):  # edge_gs.py:544-576
+        grads = self.absgrads / self.absgrads_normalize_factor
+        grads_n = (grads - grads.min()) / (grads.max() - grads.min())
+        kind, value = self.config.dup_threshold_type, self.config.dup_threshold_value
+        if kind == "percentile_top":
+            # reference quirk kept: the threshold is a quantile of the RAW statistic, compared with the NORMALISED one
+            nq = int(1 / value)
+            thresh = torch.quantile(grads, (nq - 1) / nq, interpolation="lower") if nq > 1 else grads.new_zeros(())
+            mask = grads_n > thresh
+        elif kind == "absolute":
+            mask = grads_n > value
+        else:  # the reference leaves dup_mask undefined for any other value (its own default "percentile" included)
+            raise ValueError(f"dup_threshold_type must be 'percentile_top' or 'absolute', got {kind!r}")
+        n = self.dup_gaussians(optimizers, mask)
+        self.reset_absgrads()
+        return n
+
+    def cull_gaussians_not_projecting(self, optimizers, min_projecting_fraction=0.1):  # edge_gs.py:578-601
+        return self.cull_gaussians(optimizers, self.not_projecting_mask(min_projecting_fraction))
+
+    def cull_wayward(self, optimizers, *args, **kwargs):
+        """No-op, like the reference: edge_gs.py:498-542 computes a mask and never applies it."""
+        return 0
 
     # ------------------------------------------------------------------ visibility filter (section 8f-4)
     def not_projecting_mask(self, min_projecting_fraction=0.1) -> torch.Tensor:
