@@ -38,6 +38,7 @@ class GraphedRasterStep:
         self.comm_stream = torch.cuda.Stream(device=dev) if allreduce else None
         self.chunked = False
         self.native_comm = None   # parallel.NativeComm: ranged backward + collectives as one C call
+        self.python_ranges = False  # True: drive the ranged backward + torch.distributed collectives from Python (A/B)
         # opt-in: the one all-reduce per step through libedgegs' own communicator, enqueued straight on the compute
         # stream (torch.distributed routes through an internal stream; measured identical at 2 GPUs: 0.379 ms)
         self.native_allreduce = native_allreduce
@@ -102,7 +103,7 @@ class GraphedRasterStep:
         torch.cuda.synchronize()
         self.chunked = (self._distributed() and self.allreduce_chunks > 1
                         and self.model.current_pipeline() != "tiles" and stage_cb is None)
-        if (self._distributed() and self.native_comm is None and not getattr(self, "python_ranges", False)
+        if (self._distributed() and self.native_comm is None and not self.python_ranges
                 and (self.chunked or self.native_allreduce)):
             from .parallel import NativeComm
             self.native_comm = NativeComm(self.model.means.device, self.allreduce_group)
