@@ -12,16 +12,19 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_C", "libedgegs.so")
 
-EG_ST_NISECT, EG_ST_OVERFLOW, EG_ST_BADCOLOR, EG_ST_MAXTILE, EG_ST_REDO, EG_ST_STOPPED, EG_ST_WORDS = 0, 1, 2, 3, 4, 5, 8
+EG_ST_NISECT, EG_ST_OVERFLOW, EG_ST_BADCOLOR, EG_ST_MAXTILE, EG_ST_REDO, EG_ST_STOPPED, EG_ST_NKEYS, EG_ST_WORDS = 0, 1, 2, 3, 4, 5, 6, 8
 EG_GT_NONE, EG_GT_F32, EG_GT_U8 = 0, 1, 2
 EG_CNT_STRIDE = 32
 EG_FLAG_LAZY_SORT = 1
 EG_FLAG_COMPACT_KEYS = 2
 EG_FLAG_NO_EMIT = 4
+EG_FLAG_CULL_TILES = 8
+EG_FLAG_FRONT_SORT = 16
 
 EXPORTS = ["eg_last_error", "eg_abi_version", "eg_tile_grid", "eg_project_fwd", "eg_bin", "eg_raster_fwd",
            "eg_raster_bwd", "eg_project_bwd", "eg_splat_bwd", "eg_make_seed", "eg_splat_fwd", "eg_splat_resolve", "eg_emit_flagged",
-           "eg_comm_unique_id", "eg_comm_init", "eg_comm_destroy", "eg_comm_allreduce", "eg_splat_bwd_allreduce", "eg_reg_fwd_bwd", "eg_knn_workspace_bytes", "eg_knn", "eg_adam_step",
+           "eg_comm_unique_id", "eg_comm_init", "eg_comm_destroy", "eg_comm_allreduce", "eg_allreduce_symm", "eg_allreduce_flag_words",
+           "eg_grad_layout", "eg_tile_capacity_for", "eg_workspace_sizes_for", "eg_workspace_bytes", "eg_reg_fwd_bwd", "eg_knn_workspace_bytes", "eg_knn", "eg_adam_step",
            "eg_projecting_fraction"]
 
 
@@ -31,6 +34,15 @@ class EgConfig(Structure):
                 ("antialiased", c_int32), ("raw_params", c_int32), ("isect_capacity", c_int64),
                 ("tile_capacity", c_int32), ("flags", c_int32)]
 
+
+class EgWorkspaceSizes(Structure):
+    _fields_ = [(k, ctypes.c_size_t) for k in
+                ("rec", "gint", "head", "tile_counts", "stop_list", "tile_offsets", "keys", "flatten_ids", "cmask", "logT",
+                 "wpix", "render0", "last_depth", "last_gid", "grad2d", "grads", "total")] + [
+                    ("tile_capacity", c_int32), ("compact_keys", c_int32)]
+
+
+EG_PIPE = {"splat": 0, "tiles+splat": 1, "tiles": 2}
 
 _lib = None
 
@@ -56,18 +68,23 @@ def load(build_if_missing: bool = True):
     lib.eg_tile_grid.argtypes = [c_int, c_int, c_int, POINTER(c_int), POINTER(c_int)]
     lib.eg_project_fwd.argtypes = [cfgp] + [P] * 13
     lib.eg_bin.argtypes = [cfgp] + [P] * 7
-    lib.eg_raster_fwd.argtypes = [cfgp] + [P] * 10 + [c_int] + [P] * 8
-    lib.eg_raster_bwd.argtypes = [cfgp] + [P] * 6 + [c_int, P, P, c_float, P, P, P]
+    lib.eg_raster_fwd.argtypes = [cfgp] + [P] * 10 + [c_int] + [P] * 11
+    lib.eg_raster_bwd.argtypes = [cfgp] + [P] * 7 + [c_int, P, P, c_float, P, P, P]
     lib.eg_project_bwd.argtypes = [cfgp] + [P] * 9 + [c_int] + [P] * 7
     lib.eg_splat_bwd.argtypes = [cfgp] + [P] * 9 + [c_float] + [P] * 4 + [c_int, c_int] + [P] * 7
     lib.eg_splat_fwd.argtypes = [cfgp] + [P] * 5
-    lib.eg_splat_resolve.argtypes = [cfgp, P, P, c_int] + [P] * 8
+    lib.eg_splat_resolve.argtypes = [cfgp, P, P, c_int] + [P] * 10
     lib.eg_emit_flagged.argtypes = [cfgp] + [P] * 7
     lib.eg_comm_unique_id.argtypes = [P]
     lib.eg_comm_init.argtypes = [P, c_int, c_int, POINTER(c_void_p)]
     lib.eg_comm_destroy.argtypes = [P]
     lib.eg_comm_allreduce.argtypes = [P, c_int64, P, P]
-    lib.eg_splat_bwd_allreduce.argtypes = [cfgp] + [P] * 9 + [c_float] + [P] * 6 + [c_int, P, P, P]
+    lib.eg_allreduce_symm.argtypes = [P, P, P, c_int64, c_int, c_int, c_int, P]
+    lib.eg_allreduce_flag_words.argtypes = [c_int]
+    lib.eg_grad_layout.argtypes = [c_int, POINTER(c_int64)]
+    lib.eg_tile_capacity_for.argtypes = [c_int64, c_int, c_int]
+    lib.eg_workspace_sizes_for.argtypes = [cfgp, c_int, c_int, POINTER(EgWorkspaceSizes)]
+    lib.eg_workspace_bytes.argtypes = [cfgp, c_int]
     lib.eg_make_seed.argtypes = [c_int64, P, P, c_int, P, P, P]
     lib.eg_reg_fwd_bwd.argtypes = [c_int, P, P, P, P, c_int, c_int, c_int, c_float, c_float, P, P, P, P, P]
     lib.eg_knn_workspace_bytes.argtypes = [c_int]
@@ -77,6 +94,7 @@ def load(build_if_missing: bool = True):
     for name in EXPORTS[2:]:
         getattr(lib, name).restype = c_int
     lib.eg_knn_workspace_bytes.restype = ctypes.c_size_t
+    lib.eg_workspace_bytes.restype = ctypes.c_size_t
     _lib = lib
     return lib
 

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_C")
 LIB = os.path.join(OUT_DIR, "libedgegs.so")
-SOURCES = ["eg_api.cu", "eg_project_fwd.cu", "eg_bin.cu", "eg_raster_fwd.cu", "eg_raster_bwd.cu", "eg_splat_bwd.cu", "eg_splat_fwd.cu", "eg_comm.cu",
+SOURCES = ["eg_api.cu", "eg_project_fwd.cu", "eg_bin.cu", "eg_raster_fwd.cu", "eg_raster_bwd.cu", "eg_splat_bwd.cu", "eg_splat_fwd.cu", "eg_comm.cu", "eg_allreduce.cu",
            "eg_project_bwd.cu", "eg_reg.cu", "eg_knn.cu", "eg_adam.cu", "eg_visibility.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]

@@ -1,0 +1,145 @@
+// eg_allreduce.cu -- the view-sharded step's gradient exchange as ONE kernel of this library over NVLink 5 /
+// NVSwitch (no NCCL on the data path).
+//
+// The reference is single-GPU (train_gaussians.py:311); the sharding is SURVEY.md section 8e's: parameters
+// replicated, one view per GPU per step, the per-view gradients of the flat buffer means | scales | quats |
+// opacities (eg_grad_layout) summed over the ranks.  Every rank holds that buffer at the same offset of a SYMMETRIC
+// allocation (peer-mapped on every rank, and bound to an NVSwitch multicast object where the fabric has one).
+//
+//   barrier   every CTA b of every rank signals flag[b][my rank] on each peer and waits for its own flags --
+//             the peers' backward kernels (same stream, earlier) have then written their gradients;
+//   reduce    rank r owns the r-th slice.  Multicast path: multimem.ld_reduce.add.v4.f32 pulls the slice through
+//             the switch, which sums the G copies in flight (one 16-byte response instead of G), and
+//             multimem.st.v4.f32 writes the sum back to ALL ranks' buffers in one store.  Per GPU and direction
+//             that is one buffer length on the links instead of 2 (G-1)/G lengths for a ring, and two latencies
+//             instead of 2 (G-1).  Peer path (no multicast object): plain 128-bit loads from the G peer buffers in
+//             rank order, 128-bit stores to all of them;
+//   barrier   the slices written by the peers are visible before anything on this stream reads the buffer.
+//
+// Flags are toggled 0 -> 1 -> 0 with compare-and-swap (the waiter consumes what the signaller produced), so the
+// kernel is re-entrant without epochs or host resets and can be captured in a CUDA graph -- the whole iteration,
+// exchange included, is then one graph replay.
+#include "eg_common.cuh"
+
+namespace {
+
+constexpr int AR_THREADS = 512;
+constexpr int AR_MAX_RANKS = 16;
+constexpr int AR_UNROLL = 4;
+
+struct ArPeers {
+    float *buf[AR_MAX_RANKS];       // peer-mapped gradient buffers, by rank
+    uint32_t *flags[AR_MAX_RANKS];  // peer-mapped flag areas, by rank: [grid][AR_MAX_RANKS] words
+};
+
+__device__ __forceinline__ uint32_t cas_release_sys(uint32_t *addr, uint32_t cmp, uint32_t val) {
+    uint32_t old;
+    asm volatile("atom.global.release.sys.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(addr), "r"(cmp), "r"(val) : "memory");
+    return old;
+}
+__device__ __forceinline__ uint32_t cas_acquire_sys(uint32_t *addr, uint32_t cmp, uint32_t val) {
+    uint32_t old;
+    asm volatile("atom.global.acquire.sys.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(addr), "r"(cmp), "r"(val) : "memory");
+    return old;
+}
+
+// CTA-level barrier with CTA `blockIdx.x` of every other rank.  Threads 0 .. world-1 each handle one peer.
+__device__ __forceinline__ void rank_barrier(const ArPeers &peers, const int rank, const int world) {
+    __syncthreads();  // this CTA's earlier stores are ordered before the release below (cumulativity)
+    if ((int)threadIdx.x < world && (int)threadIdx.x != rank) {
+        const int peer = threadIdx.x;
+        uint32_t *put = peers.flags[peer] + (size_t)blockIdx.x * AR_MAX_RANKS + rank;  // my slot in the peer's area
+        while (cas_release_sys(put, 0u, 1u) != 0u) {}                                   // (free again once consumed)
+        uint32_t *get = peers.flags[rank] + (size_t)blockIdx.x * AR_MAX_RANKS + peer;   // the peer's slot in mine
+        while (cas_acquire_sys(get, 1u, 0u) != 1u) {}
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ float4 mc_ld_reduce(const float *mc_addr) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc_addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mc_st(float *mc_addr, const float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+                 ::"l"(mc_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// n4 = number of float4 elements of the whole buffer; rank r owns the float4 range [r * per, min(n4, (r+1) * per))
+template <bool MULTICAST>
+__global__ void __launch_bounds__(AR_THREADS) allreduce_kernel(const ArPeers peers, float *__restrict__ mc_buf,
+                                                               const long long n4, const int rank, const int world) {
+    rank_barrier(peers, rank, world);
+    const long long per = (n4 + world - 1) / world;
+    const long long lo = (long long)rank * per, hi = (lo + per < n4) ? lo + per : n4;
+    const long long stride = (long long)gridDim.x * AR_THREADS;
+    if (MULTICAST) {
+        float4 *mc4 = reinterpret_cast<float4 *>(mc_buf);
+        // AR_UNROLL independent 16-byte switch reductions in flight per thread: the slice is a few MB and one
+        // round trip through the switch takes microseconds, so the bytes in flight are what sets the rate
+        for (long long i0 = lo + (long long)blockIdx.x * AR_THREADS + threadIdx.x; i0 < hi; i0 += AR_UNROLL * stride) {
+            float4 v[AR_UNROLL];
+#pragma unroll
+            for (int u = 0; u < AR_UNROLL; ++u)
+                if (i0 + u * stride < hi) v[u] = mc_ld_reduce(reinterpret_cast<const float *>(mc4 + i0 + u * stride));
+#pragma unroll
+            for (int u = 0; u < AR_UNROLL; ++u)
+                if (i0 + u * stride < hi) mc_st(reinterpret_cast<float *>(mc4 + i0 + u * stride), v[u]);
+        }
+    } else {
+        for (long long i = lo + (long long)blockIdx.x * AR_THREADS + threadIdx.x; i < hi; i += stride) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 v[AR_MAX_RANKS];
+#pragma unroll
+            for (int r = 0; r < AR_MAX_RANKS; ++r)
+                if (r < world) v[r] = __ldcg(reinterpret_cast<const float4 *>(peers.buf[r]) + i);  // all loads in flight
+#pragma unroll
+            for (int r = 0; r < AR_MAX_RANKS; ++r)
+                if (r < world) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
+#pragma unroll
+            for (int r = 0; r < AR_MAX_RANKS; ++r)
+                if (r < world) __stcg(reinterpret_cast<float4 *>(peers.buf[r]) + i, acc);
+        }
+    }
+    __threadfence_system();
+    rank_barrier(peers, rank, world);
+}
+
+}  // namespace
+
+extern "C" int eg_allreduce_flag_words(int grid) { return (grid > 0 ? grid : 0) * AR_MAX_RANKS; }
+
+extern "C" int eg_allreduce_symm(float *const *peer_bufs, float *mc_buf, uint32_t *const *peer_flags, int64_t count,
+                                 int rank, int world, int grid, void *stream) {
+    if (peer_bufs == nullptr || peer_flags == nullptr || world < 1 || world > AR_MAX_RANKS || rank < 0 || rank >= world) {
+        eg_set_error("eg_allreduce_symm: bad arguments (world %d, rank %d; at most %d ranks)", world, rank, AR_MAX_RANKS);
+        return 1;
+    }
+    if (count < 0 || (count & 3) != 0) {
+        eg_set_error("eg_allreduce_symm: count must be a multiple of 4 floats (eg_grad_layout pads to that)");
+        return 1;
+    }
+    if (world == 1 || count == 0) return 0;
+    if (grid <= 0) grid = 64;
+    ArPeers peers;
+    for (int r = 0; r < AR_MAX_RANKS; ++r) {
+        peers.buf[r] = r < world ? peer_bufs[r] : nullptr;
+        peers.flags[r] = r < world ? peer_flags[r] : nullptr;
+        if (r < world && (peers.buf[r] == nullptr || peers.flags[r] == nullptr || ((uintptr_t)peers.buf[r] & 15))) {
+            eg_set_error("eg_allreduce_symm: peer pointer %d missing or not 16-byte aligned", r);
+            return 1;
+        }
+    }
+    if (mc_buf != nullptr && ((uintptr_t)mc_buf & 15)) {
+        eg_set_error("eg_allreduce_symm: multicast pointer not 16-byte aligned");
+        return 1;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (mc_buf != nullptr)
+        allreduce_kernel<true><<<grid, AR_THREADS, 0, s>>>(peers, mc_buf, count / 4, rank, world);
+    else
+        allreduce_kernel<false><<<grid, AR_THREADS, 0, s>>>(peers, nullptr, count / 4, rank, world);
+    return eg_check_launch("eg_allreduce_symm");
+}

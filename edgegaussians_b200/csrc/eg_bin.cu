@@ -6,7 +6,8 @@
 // Here eg_project_fwd has already appended every (depth_bits<<32 | id) key to a fixed-capacity bucket
 // of its tile (one atomic per intersection), so what is left is
 //   scan_kernel : exclusive scan of the T tile counts -> tile_offsets (== gsplat isect_offsets),
-//                 n_isects and the largest tile count, kept on the device (status words);
+//                 the number of emitted keys and the largest tile count, kept on the device (status words;
+//                 gsplat's n_isects = sum of tiles_per_gauss is accumulated by eg_project_fwd);
 // and the sort happens per tile on chip inside eg_raster_fwd.  The key is unique, so the result is
 // deterministic and equals gsplat's stable sort order (tile, depth bits, Gaussian id).
 #include "eg_common.cuh"
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(int32_t *__restrict_
         for (int w = 0; w < SCAN_THREADS / 32; ++w) m = max(m, warp_max[w]);
         const int32_t total = carry_s;
         offsets[T] = total;
-        status[EG_ST_NISECT] = total;
+        status[EG_ST_NKEYS] = total;  // emitted keys (== n_isects unless EG_FLAG_CULL_TILES dropped unreachable tiles)
         status[EG_ST_MAXTILE] = m;
         if ((long long)total > capacity || (!compact && m > tile_capacity)) status[EG_ST_OVERFLOW] = 1;
     }
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(int32_t *__restrict_
 __global__ void __launch_bounds__(256) emit_kernel(int n, const float4 *__restrict__ rec,
                                                    const int2 *__restrict__ gint, int32_t *__restrict__ counts,
                                                    unsigned long long *__restrict__ keys, long long capacity,
-                                                   int tw, int th) {
+                                                   int tw, int th, int cull) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n) return;
     const int2 gi = __ldg(gint + g);
@@ -98,11 +99,20 @@ __global__ void __launch_bounds__(256) emit_kernel(int n, const float4 *__restri
     uint32_t x0, y0, x1, y1;
     eg_tile_rect(r0.x, r0.y, gi.x, tw, th, x0, y0, x1, y1);
     const unsigned long long key = ((unsigned long long)__float_as_uint(r0.w) << 32) | (unsigned int)g;
-    for (uint32_t i = y0; i < y1; ++i)
-        for (uint32_t j = x0; j < x1; ++j) {
+    float hu = 1e30f, hv = 1e30f, tau = 0.0f;
+    float4 r1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cull) {  // the same tile set eg_project_fwd counted (EG_FLAG_CULL_TILES)
+        r1 = __ldg(rec + 2 * g + 1);
+        if (!eg_extent(r0.z, r1.x, r1.y, r1.z, hu, hv, tau)) return;
+    }
+    for (uint32_t i = y0; i < y1; ++i) {
+        int j0 = (int)x0, j1 = (int)x1 - 1;
+        if (cull && !eg_tile_row_cols(r0.x, r0.y, r1.x, r1.y, r1.z, tau, hu, hv, (int)i, (int)x0, (int)x1, j0, j1)) continue;
+        for (int j = j0; j <= j1; ++j) {
             const long long pos = atomicAdd(counts + (size_t)(i * tw + j) * EG_CNT_STRIDE + 1, 1);
             if (pos < capacity) keys[pos] = key;
         }
+    }
 }
 
 }  // namespace
@@ -127,7 +137,7 @@ extern "C" int eg_bin(const eg_config *cfg, int32_t *tile_counts, int32_t *tile_
         }
         emit_kernel<<<(cfg->n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
             cfg->n, (const float4 *)rec, (const int2 *)gint, tile_counts, (unsigned long long *)keys,
-            (long long)cfg->isect_capacity, tw, th);
+            (long long)cfg->isect_capacity, tw, th, (cfg->flags & EG_FLAG_CULL_TILES) ? 1 : 0);
         return eg_check_launch("eg_bin/emit");
     }
     return 0;

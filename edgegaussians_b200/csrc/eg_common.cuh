@@ -62,6 +62,16 @@ __device__ __forceinline__ void eg_red_add_v4(float *addr, float a, float b, flo
                  : "memory");
 }
 
+// v_quats[g] = vq: one 128-bit store when the tensor is 16-byte aligned (always the case inside the padded flat gradient
+// buffer, eg_grad_layout), four scalar stores otherwise (a caller-supplied [N,4] tensor at an odd offset)
+__device__ __forceinline__ void eg_store_quat_grad(float *__restrict__ v_quats, int g, const float (&vq)[4]) {
+    if ((reinterpret_cast<uintptr_t>(v_quats) & 15) == 0) {
+        reinterpret_cast<float4 *>(v_quats)[g] = make_float4(vq[0], vq[1], vq[2], vq[3]);
+    } else {
+        v_quats[4 * g] = vq[0]; v_quats[4 * g + 1] = vq[1]; v_quats[4 * g + 2] = vq[2]; v_quats[4 * g + 3] = vq[3];
+    }
+}
+
 // Packed fp32x2 arithmetic (Blackwell FFMA2 / FADD2 / FMUL2: two IEEE-rn fp32 operations per issued instruction,
 // operands in even-aligned register pairs).  Element-wise results are bit-identical to the scalar .rn forms.
 typedef unsigned long long eg_f2;
@@ -141,4 +151,50 @@ __device__ __forceinline__ bool eg_extent(float o, float A, float B, float C, fl
     hx = sqrtf(k * C) * 1.0001f + 1e-3f;
     hy = sqrtf(k * A) * 1.0001f + 1e-3f;
     return true;
+}
+
+// Tile columns of tile row `ty` that the alpha >= 1/255 footprint of a Gaussian can reach (EG_FLAG_CULL_TILES).
+// The footprint is the ellipse  sigma(u, v) = (A u^2 + C v^2) / 2 + B u v <= tau  around the mean, tau = ln(255 o)
+// (+ the safety margin of eg_extent); the pixel-centre rows of the tile row cut a horizontal strip out of it, whose
+// u-extent is attained at the strip's ends or at the ellipse's left / right extreme points.  CONSERVATIVE: only used
+// to skip (tile, Gaussian) pairs in which the exact per-pixel alpha test of the raster kernels could never pass.
+// hu, hv = eg_extent's half extents, (x0, x1) the tile-column range of gsplat's rectangle.  Returns false when the
+// row holds no tile; else [j0, j1] (inclusive).
+__device__ __forceinline__ bool eg_tile_row_cols(float mx, float my, float A, float B, float C, float tau, float hu,
+                                                 float hv, int ty, int x0, int x1, int &j0, int &j1) {
+    j0 = x0;
+    j1 = x1 - 1;
+    if (!(hu < 1e29f)) return j1 >= j0;  // degenerate conic: eg_extent gave up, keep the whole row
+    const float va = (float)(ty * EG_TILE) + 0.5f - my, vb = va + (float)(EG_TILE - 1);
+    if (vb < -hv || va > hv) return false;
+    const float v1 = fmaxf(va, -hv), v2 = fminf(vb, hv);
+    const float det = A * C - B * B, iA = 1.0f / A;
+    const float s1 = sqrtf(fmaxf(0.0f, 2.0f * tau * A - det * v1 * v1)), s2 = sqrtf(fmaxf(0.0f, 2.0f * tau * A - det * v2 * v2));
+    float umax = fmaxf((-B * v1 + s1) * iA, (-B * v2 + s2) * iA);
+    float umin = fminf((-B * v1 - s1) * iA, (-B * v2 - s2) * iA);
+    const float vr = -B * hu / C;  // v of the right-most point (u = +hu); the left-most one is at -vr
+    if (vr >= v1 && vr <= v2) umax = hu;
+    if (-vr >= v1 && -vr <= v2) umin = -hu;
+    umax = umax + fabsf(umax) * 1e-4f + 0.02f;
+    umin = umin - fabsf(umin) * 1e-4f - 0.02f;
+    // pixel columns whose centre px + 0.5 lies in [mx + umin, mx + umax]
+    const float pa = ceilf(mx + umin - 0.5f), pb = floorf(mx + umax - 0.5f);
+    if (!(pb >= pa)) return false;
+    const int ja = (int)fmaxf(pa, 0.0f) >> 4, jb = (int)fminf(fmaxf(pb, -1.0f), 1e9f) >> 4;
+    j0 = max(j0, ja);
+    j1 = min(j1, jb);
+    return j1 >= j0 && pb >= 0.0f;
+}
+
+// Coefficient of |clamp(render) - gt| at one pixel in the fused projection loss (and of that pixel's backward seed):
+// loss_params == NULL -> 1 ("whole", edge_gs.py:290-296); else loss_params = (w_edge, w_bg, w_sel, threshold) on the
+// device: w_edge where gt >= threshold (the reference's edge mask, edge_gs.py:154-159), w_bg elsewhere, plus w_sel
+// where sel_mask != 0 -- "weighted" (edge_gs.py:177-193,316-319) and "bg_edge_ratio" (edge_gs.py:298-314) are both
+// of this form, see edge_gs.py::loss_spec.
+__device__ __forceinline__ float eg_loss_coef(const float *__restrict__ loss_params,
+                                              const unsigned char *__restrict__ sel_mask, float g, long long pix) {
+    if (loss_params == nullptr) return 1.0f;
+    float c = g >= __ldg(loss_params + 3) ? __ldg(loss_params) : __ldg(loss_params + 1);
+    if (sel_mask != nullptr && __ldg(sel_mask + pix) != 0) c += __ldg(loss_params + 2);
+    return c;
 }

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(128) project_bwd_kernel(
     }
     v_means[3 * g] = vm[0]; v_means[3 * g + 1] = vm[1]; v_means[3 * g + 2] = vm[2];
     v_scales[3 * g] = vs[0]; v_scales[3 * g + 1] = vs[1]; v_scales[3 * g + 2] = vs[2];
-    reinterpret_cast<float4 *>(v_quats)[g] = make_float4(vq[0], vq[1], vq[2], vq[3]);
+    eg_store_quat_grad(v_quats, g, vq);
     v_opacities[g] = vo;
 }
 

@@ -142,18 +142,24 @@ __global__ void __launch_bounds__(256, EG_PF_MINBLOCKS) project_fwd_kernel(
     rec[2 * g] = r0;
     rec[2 * g + 1] = r1;
     gint[g] = make_int2(radius_i, ntiles);
-    // K2 emission: append (depth_bits << 32 | id) to the bucket of every tile of the rectangle
-    const unsigned long long key = ((unsigned long long)__float_as_uint(r0.w) << 32) | (unsigned int)g;
-    const uint32_t w = x1 - x0;
-    if (cfg.flags & EG_FLAG_NO_EMIT) {
-        // Gaussian-major forward: no tile lists at all; only the intersection count is kept (one atomic per warp)
+    // status[EG_ST_NISECT] = sum of tiles_per_gauss (gsplat's n_isects), whatever is emitted below: one atomic per warp
+    {
         const unsigned am = __activemask();
         const int nt = __reduce_add_sync(am, ntiles);
         if ((int)(threadIdx.x & 31) == __ffs(am) - 1 && nt > 0) atomicAdd(status + EG_ST_NISECT, nt);
-    } else if (cfg.flags & EG_FLAG_COMPACT_KEYS) {  // count only; eg_bin emits after the scan
-        for (uint32_t i = y0; i < y1; ++i)
-            for (uint32_t j = x0; j < x1; ++j) atomicAdd(tile_counts + (size_t)(i * tw + j) * EG_CNT_STRIDE, 1);
-    } else if (ntiles > 0 && ntiles <= 12) {
+    }
+    if (cfg.flags & EG_FLAG_NO_EMIT) return;  // Gaussian-major forward: no tile lists at all
+    if (ntiles <= 0) return;
+    // K2 emission: append (depth_bits << 32 | id) to the bucket of every tile of the rectangle -- with
+    // EG_FLAG_CULL_TILES only of the tiles the alpha >= 1/255 footprint can reach (fused step: the others would
+    // fail the alpha test at every pixel; elongated Gaussians touch a fraction of their bounding square)
+    const unsigned long long key = ((unsigned long long)__float_as_uint(r0.w) << 32) | (unsigned int)g;
+    const uint32_t w = x1 - x0;
+    const bool cull = (cfg.flags & EG_FLAG_CULL_TILES) != 0;
+    const bool count_only = (cfg.flags & EG_FLAG_COMPACT_KEYS) != 0;  // eg_bin emits after the scan
+    float hu = 1e30f, hv = 1e30f, tau = 0.0f;
+    if (cull && !eg_extent(r0.z, r1.x, r1.y, r1.z, hu, hv, tau)) return;  // opacity' < 1/255: never composited
+    if (!cull && !count_only && ntiles <= 12) {
         // common case: issue all the (independent) atomics first so that they overlap, then the stores
         int pos[12];
 #pragma unroll
@@ -168,13 +174,16 @@ __global__ void __launch_bounds__(256, EG_PF_MINBLOCKS) project_fwd_kernel(
                 const uint32_t i = y0 + (uint32_t)q / w, j = x0 + (uint32_t)q % w;
                 if (pos[q] < cfg.tile_capacity) keys[(size_t)(i * tw + j) * (size_t)cfg.tile_capacity + pos[q]] = key;
             }
-    } else {
-        for (uint32_t i = y0; i < y1; ++i)
-            for (uint32_t j = x0; j < x1; ++j) {
-                const size_t t = (size_t)(i * tw + j);
-                const int pos = atomicAdd(tile_counts + t * EG_CNT_STRIDE, 1);
-                if (pos < cfg.tile_capacity) keys[t * (size_t)cfg.tile_capacity + pos] = key;
-            }
+        return;
+    }
+    for (uint32_t i = y0; i < y1; ++i) {
+        int j0 = (int)x0, j1 = (int)x1 - 1;
+        if (cull && !eg_tile_row_cols(r0.x, r0.y, r1.x, r1.y, r1.z, tau, hu, hv, (int)i, (int)x0, (int)x1, j0, j1)) continue;
+        for (int j = j0; j <= j1; ++j) {
+            const size_t t = (size_t)(i * tw + j);
+            const int pos = atomicAdd(tile_counts + t * EG_CNT_STRIDE, 1);
+            if (!count_only && pos < cfg.tile_capacity) keys[t * (size_t)cfg.tile_capacity + pos] = key;
+        }
     }
 }
 

@@ -40,8 +40,8 @@ __device__ __forceinline__ void acc_flush(const PairAcc &a, float *__restrict__ 
 
 __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
     const eg_config cfg, int tw, const float4 *__restrict__ rec, const int32_t *__restrict__ tile_offsets,
-    const int32_t *__restrict__ flatten_ids, const uint4 *__restrict__ cmask, const float *__restrict__ alpha,
-    const float *__restrict__ v_render, int vr_ch, const float *__restrict__ v_alpha,
+    const int32_t *__restrict__ flatten_ids, const uint4 *__restrict__ cmask, const int32_t *__restrict__ tile_done,
+    const float *__restrict__ alpha, const float *__restrict__ v_render, int vr_ch, const float *__restrict__ v_alpha,
     const float *__restrict__ wpix, float seed_scale, float *__restrict__ grad2d,
     const int32_t *__restrict__ status) {
     __shared__ __align__(16) float4 s_px[EG_TILE * EG_TILE];  // per pixel: seed * T_final (0 outside the image),
@@ -59,7 +59,9 @@ __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
     const int tile = blockIdx.x;
     const int tile_y = tile / tw, tile_x = tile - tile_y * tw;
     const int start = tile_offsets[tile];
-    const int L = tile_offsets[tile + 1] - start;
+    // EG_FLAG_FRONT_SORT: the forward stopped after tile_done[tile] entries (everything behind is invisible and its
+    // flatten_ids / cmask are undefined)
+    const int L = tile_done != nullptr ? min(tile_done[tile], tile_offsets[tile + 1] - start) : tile_offsets[tile + 1] - start;
     if (L <= 0) return;
     const int X0 = tile_x * EG_TILE, Y0 = tile_y * EG_TILE;
 
@@ -210,7 +212,7 @@ __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
 }  // namespace
 
 extern "C" int eg_raster_bwd(const eg_config *cfg, const float *rec, const int32_t *tile_offsets,
-                             const int32_t *flatten_ids, const uint32_t *cmask, const float *alpha,
+                             const int32_t *flatten_ids, const uint32_t *cmask, const int32_t *tile_done, const float *alpha,
                              const float *v_render, int v_render_channels, const float *v_alpha, const float *wpix,
                              float seed_scale, float *grad2d, const int32_t *status, void *stream) {
     if (cfg == nullptr || cfg->tile_size != EG_TILE) {
@@ -228,7 +230,7 @@ extern "C" int eg_raster_bwd(const eg_config *cfg, const float *rec, const int32
     int tw, th;
     eg_tile_grid(cfg->width, cfg->height, cfg->tile_size, &tw, &th);
     raster_bwd_kernel<<<tw * th, RB_THREADS, 0, (cudaStream_t)stream>>>(
-        *cfg, tw, (const float4 *)rec, tile_offsets, flatten_ids, (const uint4 *)cmask, alpha, v_render,
+        *cfg, tw, (const float4 *)rec, tile_offsets, flatten_ids, (const uint4 *)cmask, tile_done, alpha, v_render,
         v_render_channels, v_alpha, wpix, seed_scale, grad2d, status);
     return eg_check_launch("eg_raster_bwd");
 }

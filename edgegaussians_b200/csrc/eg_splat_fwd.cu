@@ -254,6 +254,8 @@ __global__ void __launch_bounds__(256) splat_resolve_kernel(const eg_config cfg,
                                                             float *__restrict__ render0, float *__restrict__ alpha_out,
                                                             int32_t *__restrict__ tile_stop,
                                                             int32_t *__restrict__ stop_list,
+                                                            const float *__restrict__ loss_params,
+                                                            const unsigned char *__restrict__ sel_mask,
                                                             int32_t *__restrict__ status) {
     __shared__ float s_red[8];
     if (status[EG_ST_OVERFLOW]) return;
@@ -287,10 +289,11 @@ __global__ void __launch_bounds__(256) splat_resolve_kernel(const eg_config cfg,
                 if (GT_KIND == EG_GT_F32) gv = __ldg(reinterpret_cast<const float *>(gt) + pix);
                 else gv = __fdiv_rn((float)__ldg(reinterpret_cast<const unsigned char *>(gt) + pix), 255.0f);
                 const float d = fminf(fmaxf(out, 0.0f), 1.0f) - gv;
-                absd += fabsf(d);
+                const float coef = eg_loss_coef(loss_params, sel_mask, gv, pix);
+                absd += coef * fabsf(d);
                 const float sgn = (d > 0.0f) ? 1.0f : ((d < 0.0f) ? -1.0f : 0.0f);
                 const float pass = (out >= 0.0f && out <= 1.0f) ? 1.0f : 0.0f;
-                if (wpix) wpix[pix] = sgn * pass * T;
+                if (wpix) wpix[pix] = sgn * pass * T * coef;
             }
         }
     }
@@ -318,6 +321,8 @@ __global__ void __launch_bounds__(256) splat_resolve4_kernel(const eg_config cfg
                                                              float *__restrict__ render0, float *__restrict__ alpha_out,
                                                              int32_t *__restrict__ tile_stop,
                                                              int32_t *__restrict__ stop_list,
+                                                             const float *__restrict__ loss_params,
+                                                             const unsigned char *__restrict__ sel_mask,
                                                              int32_t *__restrict__ status) {
     __shared__ float s_red[8];
     __shared__ int s_flag[4];
@@ -326,6 +331,12 @@ __global__ void __launch_bounds__(256) splat_resolve4_kernel(const eg_config cfg
     const int row = tid >> 4, c4 = tid & 15, k = c4 >> 2;
     const int ngx = (tw + 3) >> 2, n_groups = ngx * th;
     float absd = 0.0f;
+    // coefficients of the fused loss (eg_loss_coef): 1 everywhere unless loss_params is given
+    const bool weighted = loss_params != nullptr;
+    float w_edge = 1.0f, w_bg = 1.0f, w_sel = 0.0f, w_thr = 0.0f;
+    if (weighted) {
+        w_edge = __ldg(loss_params); w_bg = __ldg(loss_params + 1); w_sel = __ldg(loss_params + 2); w_thr = __ldg(loss_params + 3);
+    }
     for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
         const int gy = grp / ngx, gx = grp - gy * ngx;
         const int tile_x = gx * 4 + k;
@@ -361,14 +372,19 @@ __global__ void __launch_bounds__(256) splat_resolve4_kernel(const eg_config cfg
         } else if (inside) {
             float o4[4], w4[4];
             const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+            uchar4 sel = make_uchar4(0, 0, 0, 0);
+            if (weighted && sel_mask != nullptr) sel = __ldg(reinterpret_cast<const uchar4 *>(sel_mask + pix));
+            const unsigned char sl[4] = {sel.x, sel.y, sel.z, sel.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 o4[i] = 1.0f - T[i];
                 const float d = fminf(fmaxf(o4[i], 0.0f), 1.0f) - gv[i];
-                absd += fabsf(d);
+                float coef = 1.0f;
+                if (weighted) coef = (gv[i] >= w_thr ? w_edge : w_bg) + (sl[i] ? w_sel : 0.0f);
+                absd += coef * fabsf(d);
                 const float sgn = (d > 0.0f) ? 1.0f : ((d < 0.0f) ? -1.0f : 0.0f);
                 const float pass = (o4[i] >= 0.0f && o4[i] <= 1.0f) ? 1.0f : 0.0f;
-                w4[i] = sgn * pass * T[i];
+                w4[i] = sgn * pass * T[i] * coef;
             }
             const float4 ov = make_float4(o4[0], o4[1], o4[2], o4[3]);
             if (alpha_out) *reinterpret_cast<float4 *>(alpha_out + pix) = ov;
@@ -408,8 +424,17 @@ __global__ void __launch_bounds__(256) emit_flagged_kernel(const eg_config cfg, 
         uint32_t x0, y0, x1, y1;
         eg_tile_rect(r0.x, r0.y, gi.x, tw, th, x0, y0, x1, y1);
         const unsigned long long key = ((unsigned long long)__float_as_uint(r0.w) << 32) | (unsigned int)g;
-        for (uint32_t i = y0; i < y1; ++i)
-            for (uint32_t j = x0; j < x1; ++j) {
+        const bool cull = (cfg.flags & EG_FLAG_CULL_TILES) != 0;  // only the tiles the footprint can reach
+        float hu = 1e30f, hv = 1e30f, tau = 0.0f;
+        float4 r1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cull) {
+            r1 = __ldg(rec + 2 * g + 1);
+            if (!eg_extent(r0.z, r1.x, r1.y, r1.z, hu, hv, tau)) continue;
+        }
+        for (uint32_t i = y0; i < y1; ++i) {
+            int j0 = (int)x0, j1 = (int)x1 - 1;
+            if (cull && !eg_tile_row_cols(r0.x, r0.y, r1.x, r1.y, r1.z, tau, hu, hv, (int)i, (int)x0, (int)x1, j0, j1)) continue;
+            for (int j = j0; j <= j1; ++j) {
                 const size_t t = (size_t)i * tw + j;
                 if (__ldg(tile_stop + t) == 0) continue;
                 const int pos = atomicAdd(tile_cnt + t, 1);
@@ -419,6 +444,7 @@ __global__ void __launch_bounds__(256) emit_flagged_kernel(const eg_config cfg, 
                     atomicMax(status + EG_ST_MAXTILE, pos + 1);
                 }
             }
+        }
     }
 }
 
@@ -456,7 +482,7 @@ extern "C" int eg_splat_fwd(const eg_config *cfg, const float *rec, const int32_
 
 extern "C" int eg_splat_resolve(const eg_config *cfg, float *logT, const void *gt, int gt_kind, double *loss_sum,
                                 float *wpix, float *render0, float *alpha, int32_t *tile_stop, int32_t *stop_list,
-                                int32_t *status, void *stream) {
+                                const float *loss_params, const uint8_t *sel_mask, int32_t *status, void *stream) {
     if (cfg == nullptr || cfg->tile_size != EG_TILE) {
         eg_set_error("eg_splat_resolve: tile_size must be %d", EG_TILE);
         return 1;
@@ -466,23 +492,30 @@ extern "C" int eg_splat_resolve(const eg_config *cfg, float *logT, const void *g
         return 1;
     }
     if (gt == nullptr) gt_kind = EG_GT_NONE;
+    if ((gt_kind == EG_GT_NONE || loss_params == nullptr) && sel_mask != nullptr) {
+        eg_set_error("eg_splat_resolve: sel_mask needs gt and loss_params");
+        return 1;
+    }
+    if (gt_kind == EG_GT_NONE) loss_params = nullptr;
     int tw, th;
     eg_tile_grid(cfg->width, cfg->height, cfg->tile_size, &tw, &th);
     cudaStream_t s = (cudaStream_t)stream;
     const int n_tiles = tw * th;
     auto al16 = [](const void *p) { return ((uintptr_t)p & 15) == 0; };
     const bool vec = cfg->width % 4 == 0 && al16(logT) && al16(wpix) && al16(render0) && al16(alpha) &&
-                     (gt_kind == EG_GT_U8 ? ((uintptr_t)gt & 3) == 0 : al16(gt));
+                     (gt_kind == EG_GT_U8 ? ((uintptr_t)gt & 3) == 0 : al16(gt)) && ((uintptr_t)sel_mask & 3) == 0;
     const int n_units = vec ? ((tw + 3) / 4) * th : n_tiles;
     const int grid = n_units < 148 * 8 ? n_units : 148 * 8;
 #define EG_RS_LAUNCH(KIND)                                                                                          \
     do {                                                                                                            \
         if (vec)                                                                                                    \
             splat_resolve4_kernel<KIND><<<grid, 256, 0, s>>>(*cfg, tw, th, logT, gt, loss_sum, wpix, render0,       \
-                                                             alpha, tile_stop, stop_list, status);                  \
+                                                             alpha, tile_stop, stop_list, loss_params, sel_mask,    \
+                                                             status);                                               \
         else                                                                                                        \
             splat_resolve_kernel<KIND><<<grid, 256, 0, s>>>(*cfg, tw, n_tiles, logT, gt, loss_sum, wpix, render0,   \
-                                                            alpha, tile_stop, stop_list, status);                   \
+                                                            alpha, tile_stop, stop_list, loss_params, sel_mask,     \
+                                                            status);                                                \
     } while (0)
     switch (gt_kind) {
         case EG_GT_NONE: EG_RS_LAUNCH(EG_GT_NONE); break;

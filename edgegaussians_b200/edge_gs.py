@@ -29,6 +29,7 @@ import torch
 from . import _lib
 from .cameras import BaseCamera
 from .engine import TILE, SplatState, get_engine, tile_capacity_for, tile_grid, use_compact_keys, _p, _stream
+from .layout import grad_numel, split_grads
 from .losses import MaskedL1Loss, WeightedL1Loss
 from .rasterization import rasterization
 
@@ -67,7 +68,7 @@ def random_quat_tensor(N, generator: Optional[torch.Generator] = None):
 class RasterStepWorkspace:
     """Persistent device buffers of the fused iteration for fixed (N, W, H, capacity)."""
 
-    def __init__(self, N: int, W: int, H: int, capacity: int, device, max_tile: int = 0):
+    def __init__(self, N: int, W: int, H: int, capacity: int, device, max_tile: int = 0, grads=None):
         tw, th = tile_grid(W, H)
         T = tw * th
         f32, i32 = torch.float32, torch.int32
@@ -94,7 +95,13 @@ class RasterStepWorkspace:
         # per-pixel cut-off of the backward for pixels that hit the transmittance stop (eg_splat_bwd)
         self.last_depth = torch.empty((H, W), dtype=i32, device=device)
         self.last_gid = torch.empty((H, W), dtype=i32, device=device)
-        self.grads = torch.zeros(11 * N, dtype=f32, device=device)  # means | scales | quats | opacities
+        # fused-loss coefficients (eg_loss_coef): (w_edge, w_bg, w_sel, threshold) on the device, so a captured graph
+        # keeps working when they change; sel_mask marks the pixels sampled by the "bg_edge_ratio" strategy
+        self.loss_params = torch.zeros(4, dtype=f32, device=device)
+        # means | scales | quats | opacities, every segment 16-byte aligned (layout.grad_layout); `grads` may be
+        # supplied by the caller (the view-sharded step hands in a symmetric-memory buffer, parallel.SymmetricGrads)
+        self.grads = grads if grads is not None else torch.zeros(grad_numel(N), dtype=f32, device=device)
+        assert self.grads.numel() == grad_numel(N) and self.grads.data_ptr() % 16 == 0
         self._lazy = {}
 
     def _get(self, name, make):
@@ -122,6 +129,10 @@ class RasterStepWorkspace:
         return self._get("cmask", lambda: torch.empty((self.capacity, 8), dtype=torch.int32, device=self.device))
 
     @property
+    def sel_mask(self):  # "bg_edge_ratio": the sampled pixels (u8 [H,W]), refreshed before every step that uses it
+        return self._get("sel_mask", lambda: torch.zeros((self.H, self.W), dtype=torch.uint8, device=self.device))
+
+    @property
     def grad2d(self):
         return self._get("grad2d", lambda: torch.zeros((self.N, 8), dtype=torch.float32, device=self.device))
 
@@ -141,6 +152,12 @@ class EdgeGaussianSplatting(torch.nn.Module):
         self._auto_pipeline = "splat"
         self.crop_box = None
         self._ws: Optional[RasterStepWorkspace] = None
+        self._resize_version = 0        # bumped whenever N changes: graphs / workspaces built for the old N are stale
+        self._external_grads = None     # flat gradient buffer supplied from outside (parallel.SymmetricExchange)
+        self.cull_tiles = True          # fused step: emit keys only to the tiles a footprint can reach (EG_FLAG_CULL_TILES)
+        self.front_sort = True          # fused step: depth-sliced sort with early stop (EG_FLAG_FRONT_SORT)
+        self.absgrads = torch.zeros(0, device=device)
+        self.absgrads_normalize_factor = 1.0
         self.config = EdgeGaussianSplattingConfig()
         self.viewcams: List[BaseCamera] = []
         self.edge_masks: List[torch.Tensor] = []
@@ -164,6 +181,7 @@ class EdgeGaussianSplatting(torch.nn.Module):
         self.absgrads_normalize_factor = 1.0
         self.gauss_params = torch.nn.ParameterDict({"means": means, "scales": scales, "quats": quats, "opacities": opacities})
         self.step = 0
+        self._after_resize()
 
     populate_params = poplutate_params
 
@@ -175,6 +193,7 @@ class EdgeGaussianSplatting(torch.nn.Module):
                                                     "opacities": mk(torch.as_tensor(opacities).reshape(-1, 1))})
         self.absgrads = torch.zeros(self.num_points, device=dev)
         self.absgrads_normalize_factor = 1.0
+        self._after_resize()
         if viewcams is not None:
             self.viewcams = viewcams
 
@@ -204,6 +223,7 @@ class EdgeGaussianSplatting(torch.nn.Module):
     def load_state_dict(self, state_dict):  # edge_gs.py:625-633
         self.gauss_params = torch.nn.ParameterDict({
             k: torch.nn.Parameter(state_dict[f"gauss_params.{k}"].to(self.device)) for k in ["means", "scales", "quats", "opacities"]})
+        self._after_resize()
 
     def export_as_ply(self, ply_path):  # edge_gs.py:635-642
         from .io_utils import write_gaussian_params_as_ply
@@ -300,7 +320,13 @@ class EdgeGaussianSplatting(torch.nn.Module):
 
     def _after_resize(self):
         self._ws = None
+        self._external_grads = None
         self._packed_views_key = None
+        self._resize_version += 1   # GraphedRasterStep re-calibrates and re-captures when it sees a new version
+        if self.absgrads.shape[0] != self.num_points:
+            # the reference resets the statistic when its length no longer matches (edge_gs.py:607-611); the fused
+            # kernels write absgrads[g] for every g < N, so the length must be right BEFORE the next step
+            self.reset_absgrads()
 
     def reset_opacities(self):  # edge_gs.py:425-429 (clamps the stored logits, as the reference does)
         self.opacities.data = torch.clamp(self.opacities.data, max=self.config.reset_opacity_value)
@@ -406,22 +432,84 @@ class EdgeGaussianSplatting(torch.nn.Module):
         ws = self._ws
         eng = get_engine(self.means.device)
         want = int(capacity) if capacity is not None else max(eng._ensure_capacity(N), ws.capacity if ws else 0)
+        ext = self._external_grads
         if (ws is None or (ws.N, ws.W, ws.H) != (N, W, H) or ws.capacity < want
+                or (ext is not None and ws.grads.data_ptr() != ext.data_ptr())
                 or (not ws.compact_keys and ws.tile_capacity < tile_capacity_for(0, ws.T, eng.max_tile))):
-            ws = RasterStepWorkspace(N, W, H, want, self.means.device, eng.max_tile)
+            ws = RasterStepWorkspace(N, W, H, want, self.means.device, eng.max_tile, grads=ext)
             self._ws = ws
         return ws
 
+    # -- fused projection losses (a8): every strategy of edge_gs.py:288-324 is  scale * sum_p c_p |clamp(render) - gt|
+    def loss_spec(self, strategy: str, image_index=None, bg_edge_pixel_ratio: float = 1.0, n_pixels: Optional[int] = None):
+        """(params, n_sel, scale) of the fused loss for a strategy of compute_projection_loss:
+        params = (w_edge, w_bg, w_sel, threshold) or None ("whole"), n_sel = number of pixels "bg_edge_ratio"
+        samples, loss = scale * loss_sum.  Needs the edge masks of compute_image_masks for the masked strategies
+        (their pixel counts are read once per view and cached: no host sync per step)."""
+        if strategy == "whole":
+            return None, 0, 1.0 / float(n_pixels)
+        idx = int(image_index)
+        if not hasattr(self, "_mask_counts"):
+            self._mask_counts = {}
+        if idx not in self._mask_counts:
+            m = self.edge_masks[idx]
+            self._mask_counts[idx] = (int(m.sum()), int(m.numel()))
+        n_edge, P = self._mask_counts[idx]
+        n_bg = P - n_edge
+        thr = float(self.config.edge_detection_threshold)
+        if strategy == "weighted":      # WeightedL1Loss: mean(w * |d|), w = n_bg / P on edge pixels, n_edge / P elsewhere
+            # the reference forms the weights as float32 quotients of integer tensors (edge_gs.py:183-190)
+            w_e = float(torch.tensor(n_bg, dtype=torch.int64) / torch.tensor(P, dtype=torch.int64))
+            w_b = float(torch.tensor(n_edge, dtype=torch.int64) / torch.tensor(P, dtype=torch.int64))
+            return (w_e, w_b, 0.0, thr), 0, 1.0 / float(P)
+        if strategy == "bg_edge_ratio":  # MaskedL1 over the edge pixels + MaskedL1 over the sampled pixels
+            n_sel = min(int(bg_edge_pixel_ratio * n_edge), n_bg)
+            w_e = 1.0 / n_edge if n_edge > 0 else float("nan")   # mean over an empty selection is nan in the reference
+            w_s = 1.0 / n_sel if n_sel > 0 else float("nan")
+            return (w_e, 0.0, w_s, thr), n_sel, 1.0
+        raise ValueError(f"Unknown projection loss strategy: {strategy}")
+
+    def sample_bg_pixels(self, image_index, n_sel: int, generator=None) -> torch.Tensor:
+        """Flat pixel ids the "bg_edge_ratio" strategy adds to the loss, with the reference's quirk kept
+        (edge_gs.py:303-310): a random n_sel-subset of range(n_bg), unravelled as FLAT pixel ids -- i.e. arbitrary
+        pixels among the first n_bg raster positions, not background pixels.  Drawn on the parameters' device
+        (``generator``: a generator of that device, or a CPU one whose permutation is then copied)."""
+        n_edge, P = self._mask_counts[int(image_index)]
+        n_bg = P - n_edge
+        dev = self.means.device
+        if generator is not None and generator.device.type != dev.type:
+            return torch.randperm(n_bg, generator=generator)[:n_sel].to(dev)
+        return torch.randperm(n_bg, generator=generator, device=dev)[:n_sel]
+
+    def set_loss(self, ws: RasterStepWorkspace, strategy: str, image_index=None, bg_edge_pixel_ratio: float = 1.0,
+                 generator=None, sel_ids: Optional[torch.Tensor] = None):
+        """Stage the fused-loss inputs of the NEXT step in the workspace's device buffers (async device work only:
+        legal between graph replays).  Returns the loss scale."""
+        params, n_sel, scale = self.loss_spec(strategy, image_index, bg_edge_pixel_ratio, ws.W * ws.H)
+        ws.loss_scale = scale
+        if params is None:
+            return scale
+        ws.loss_params.copy_(torch.tensor(params, dtype=torch.float32), non_blocking=True)
+        if strategy == "bg_edge_ratio":
+            ids = sel_ids if sel_ids is not None else self.sample_bg_pixels(image_index, n_sel, generator)
+            sel = ws.sel_mask.view(-1)
+            sel.zero_()
+            sel[ids.to(sel.device)] = 1
+        return scale
+
     def enqueue_raster_step(self, viewmat, K, W, H, gt, *, loss_weight=1.0, accumulate_absgrad=True, capacity=None,
-                            want_render=False, stage_cb=None, lazy_sort=None, pipeline=None,
-                            parts="all") -> RasterStepWorkspace:
+                            want_render=False, stage_cb=None, lazy_sort=None, pipeline=None, parts="all",
+                            loss_mode: str = "whole", view_slot=None) -> RasterStepWorkspace:
         """Enqueue one fused forward+backward iteration on the current stream. No host sync, no
         allocation after the first call for a given (N, W, H): CUDA-graph capturable.
 
-        Results (device): ws.loss_sum[0] / (W*H) = "whole" L1 loss; ws.grads = gradients of
+        Results (device): ws.loss_sum[0] * ws.loss_scale = the projection loss; ws.grads = gradients of
         loss_weight * loss w.r.t. (means | log-scales | quats | logit-opacities), also installed as
         ``.grad`` views on the parameters; self.absgrads += ||means2d.absgrad|| when
         ``accumulate_absgrad``; ws.status = (n_isects, overflow, ...).
+
+        ``loss_mode``: "whole" (edge_gs.py:290-296), or "weighted" / "bg_edge_ratio" (edge_gs.py:298-319) -- the
+        masked strategies read their coefficients from ws.loss_params / ws.sel_mask, staged by :meth:`set_loss`.
 
         ``pipeline`` (default: :meth:`current_pipeline`), all three give gsplat's result:
           "splat"        Gaussian-major forward (eg_splat_fwd/resolve, exact per-tile fallback) + eg_splat_bwd;
@@ -429,16 +517,22 @@ class EdgeGaussianSplatting(torch.nn.Module):
           "tiles"        eg_raster_fwd with contribution masks + eg_raster_bwd + eg_project_bwd.
 
         ``parts="forward"`` stops after the forward (loss, backward seed); the backward is then issued with
-        :meth:`enqueue_backward_range` (Gaussian ranges, for the chunked gradient all-reduce of parallel.py)."""
+        :meth:`enqueue_backward_range`."""
         lib = get_engine(self.means.device).lib
         ws = self._workspace(W, H, capacity)
         N = ws.N
+        if self.absgrads.shape[0] != N:
+            self.reset_absgrads()   # the kernels index absgrads by Gaussian: never run them on a stale length
         pipeline = pipeline or self.current_pipeline()
         if pipeline not in ("splat", "tiles+splat", "tiles"):
             raise ValueError(f"unknown pipeline {pipeline!r}")
         if pipeline == "splat" and ws.compact_keys:
             pipeline = "tiles+splat"  # the fallback of the Gaussian-major forward needs per-tile buckets
         flags = (_lib.EG_FLAG_COMPACT_KEYS if ws.compact_keys else 0)
+        if self.cull_tiles:
+            flags |= _lib.EG_FLAG_CULL_TILES
+        if self.front_sort:
+            flags |= _lib.EG_FLAG_FRONT_SORT
         if pipeline == "splat":
             flags |= _lib.EG_FLAG_NO_EMIT
         elif self._use_lazy(lazy_sort):
@@ -452,7 +546,21 @@ class EdgeGaussianSplatting(torch.nn.Module):
         means, quats, scales, opac = self.means.data, self.quats.data, self.scales.data, self.opacities.data
         cb = stage_cb if stage_cb is not None else (lambda name: None)
         chk = _lib.check
-        seed = float(loss_weight) / float(W * H)
+        if loss_mode == "whole":
+            ws.loss_scale = 1.0 / float(W * H)
+            lparams, lsel = None, None
+        elif loss_mode in ("weighted", "bg_edge_ratio"):
+            if getattr(ws, "loss_scale", None) is None:
+                raise RuntimeError("call set_loss() before a step with a masked loss strategy")
+            lparams = _p(ws.loss_params)
+            lsel = _p(ws.sel_mask) if loss_mode == "bg_edge_ratio" else None
+            if loss_mode == "weighted":
+                ws.loss_scale = 1.0 / float(W * H)
+            else:
+                ws.loss_scale = 1.0
+        else:
+            raise ValueError(f"Unknown projection loss strategy: {loss_mode}")
+        seed = float(loss_weight) * ws.loss_scale
         g = ws.grads
         absg = _p(self.absgrads) if accumulate_absgrad else None
         render0 = _p(ws.render0) if want_render else None
@@ -466,14 +574,16 @@ class EdgeGaussianSplatting(torch.nn.Module):
             chk(lib.eg_splat_fwd(c, _p(ws.rec), _p(ws.gint), _p(ws.logT), _p(ws.status), s), "eg_splat_fwd")
             cb("splat_fwd")
             chk(lib.eg_splat_resolve(c, _p(ws.logT), _p(gt), gt_kind, _p(ws.loss_sum), _p(ws.wpix), render0, None,
-                                     _p(ws.tile_stop), _p(ws.stop_list), _p(ws.status), s), "eg_splat_resolve")
+                                     _p(ws.tile_stop), _p(ws.stop_list), lparams, lsel, _p(ws.status), s),
+                "eg_splat_resolve")
             cb("splat_resolve")
             # exact redo of the tiles in which a pixel may have hit gsplat's stop rule (both return at once if none)
             chk(lib.eg_emit_flagged(c, _p(ws.rec), _p(ws.gint), _p(ws.tile_stop), _p(ws.tile_cnt), _p(ws.keys),
                                     _p(ws.status), s), "eg_emit_flagged")
             chk(lib.eg_raster_fwd(c, _p(ws.rec), None, _p(ws.keys), _p(ws.flatten_ids), None, render0, None, None, None,
                                   _p(gt), gt_kind, _p(ws.loss_sum), _p(ws.wpix), _p(ws.last_depth), _p(ws.last_gid),
-                                  _p(ws.stop_list), _p(ws.tile_cnt), _p(ws.status), s), "eg_raster_fwd")
+                                  _p(ws.stop_list), _p(ws.tile_cnt), None, lparams, lsel, _p(ws.status), s),
+                "eg_raster_fwd")
             cb("stop_fallback")
         else:
             ws.zero_block.zero_()   # + the padded tile counters
@@ -485,10 +595,12 @@ class EdgeGaussianSplatting(torch.nn.Module):
                            _p(ws.keys), s), "eg_bin")
             cb("bin")
             tiles_bwd = pipeline == "tiles"
+            # tile_cnt doubles as tile_done here (the flagged-tile fallback that owns it belongs to the other pipeline)
             chk(lib.eg_raster_fwd(c, _p(ws.rec), _p(ws.tile_offsets), _p(ws.keys), _p(ws.flatten_ids), None, render0,
                                   None, None, _p(ws.cmask) if tiles_bwd else None, _p(gt), gt_kind, _p(ws.loss_sum),
                                   _p(ws.wpix), None if tiles_bwd else _p(ws.last_depth),
-                                  None if tiles_bwd else _p(ws.last_gid), None, None, _p(ws.status), s), "eg_raster_fwd")
+                                  None if tiles_bwd else _p(ws.last_gid), None, None, _p(ws.tile_cnt), lparams, lsel,
+                                  _p(ws.status), s), "eg_raster_fwd")
             cb("raster_fwd")
         ws.pipeline = pipeline
         ws.n_kernels = {"splat": 6, "tiles+splat": 4, "tiles": 5}[pipeline]   # launches of this library per iteration
@@ -498,45 +610,35 @@ class EdgeGaussianSplatting(torch.nn.Module):
                 raise ValueError("parts='forward' needs a pipeline with the Gaussian-major backward")
             return ws
         if pipeline == "tiles":
-            chk(lib.eg_raster_bwd(c, _p(ws.rec), _p(ws.tile_offsets), _p(ws.flatten_ids), _p(ws.cmask), None, None, 0,
-                                  None, _p(ws.wpix), seed, _p(ws.grad2d), _p(ws.status), s), "eg_raster_bwd")
+            chk(lib.eg_raster_bwd(c, _p(ws.rec), _p(ws.tile_offsets), _p(ws.flatten_ids), _p(ws.cmask), _p(ws.tile_cnt),
+                                  None, None, 0, None, _p(ws.wpix), seed, _p(ws.grad2d), _p(ws.status), s), "eg_raster_bwd")
             cb("raster_bwd")
+            gm, gs, gq, go = split_grads(g, N)
             chk(lib.eg_project_bwd(c, _p(means), _p(quats), _p(scales), _p(opac), _p(viewmat), _p(K), _p(ws.rec),
-                                   _p(ws.gint), _p(ws.grad2d), 1, None, _p(g[0:3 * N]), _p(g[6 * N:10 * N]),
-                                   _p(g[3 * N:6 * N]), _p(g[10 * N:11 * N]), absg, s), "eg_project_bwd")
+                                   _p(ws.gint), _p(ws.grad2d), 1, None, _p(gm), _p(gq), _p(gs), _p(go), absg, s),
+                "eg_project_bwd")
             cb("project_bwd")
         else:
             self.enqueue_backward_range(ws, 0, N)
             cb("splat_bwd")
         return ws
 
+    def loss_from_workspace(self, ws: RasterStepWorkspace, loss_mode: str = "whole") -> torch.Tensor:
+        """The projection loss of the step that just ran, as a 0-dim device tensor (no sync)."""
+        return (ws.loss_sum[0] * ws.loss_scale).float()
+
     def enqueue_backward_range(self, ws: RasterStepWorkspace, g_begin: int, g_end: int) -> None:
         """eg_splat_bwd for the Gaussians [g_begin, g_end) of the step whose forward was just enqueued: their
         slices of ws.grads (and of self.absgrads) are final when this launch completes."""
         cfg, viewmat, K, seed, accumulate_absgrad = ws.bwd_args
         lib = get_engine(self.means.device).lib
-        N, g = ws.N, ws.grads
+        gm, gs, gq, go = split_grads(ws.grads, ws.N)
         means, quats, scales, opac = self.means.data, self.quats.data, self.scales.data, self.opacities.data
         _lib.check(lib.eg_splat_bwd(ctypes.byref(cfg), _p(means), _p(quats), _p(scales), _p(opac), _p(viewmat), _p(K),
                                     _p(ws.rec), _p(ws.gint), _p(ws.wpix), seed, _p(ws.last_depth), _p(ws.last_gid),
                                     _p(ws.tile_stop) if ws.pipeline == "splat" else None, _p(ws.status),
-                                    int(g_begin), int(g_end), None, _p(g[0:3 * N]), _p(g[6 * N:10 * N]),
-                                    _p(g[3 * N:6 * N]), _p(g[10 * N:11 * N]),
+                                    int(g_begin), int(g_end), None, _p(gm), _p(gq), _p(gs), _p(go),
                                     _p(self.absgrads) if accumulate_absgrad else None, _stream()), "eg_splat_bwd")
-
-    def enqueue_backward_allreduce(self, ws: RasterStepWorkspace, comm, n_ranges: int) -> None:
-        """The whole backward of the step whose forward was just enqueued, in ``n_ranges`` Gaussian ranges, with the
-        gradients of each finished range all-reduced over the ranks of ``comm`` (parallel.NativeComm) on its side
-        stream while the next range is computed -- one C call (eg_splat_bwd_allreduce)."""
-        cfg, viewmat, K, seed, accumulate_absgrad = ws.bwd_args
-        lib = get_engine(self.means.device).lib
-        means, quats, scales, opac = self.means.data, self.quats.data, self.scales.data, self.opacities.data
-        _lib.check(lib.eg_splat_bwd_allreduce(
-            ctypes.byref(cfg), _p(means), _p(quats), _p(scales), _p(opac), _p(viewmat), _p(K), _p(ws.rec), _p(ws.gint),
-            _p(ws.wpix), seed, _p(ws.last_depth), _p(ws.last_gid),
-            _p(ws.tile_stop) if ws.pipeline == "splat" else None, _p(ws.status), _p(ws.grads),
-            _p(self.absgrads) if accumulate_absgrad else None, int(n_ranges), comm.handle,
-            ctypes.c_void_p(comm.stream.cuda_stream), _stream()), "eg_splat_bwd_allreduce")
 
     # ------------------------------------------------------------------ pipeline policy
     def current_pipeline(self) -> str:
@@ -573,35 +675,47 @@ class EdgeGaussianSplatting(torch.nn.Module):
             self._lazy_on = False
 
     def install_grads(self, ws: RasterStepWorkspace):
-        N, g = ws.N, ws.grads
-        self.means.grad = g[0:3 * N].view(N, 3)
-        self.scales.grad = g[3 * N:6 * N].view(N, 3)
-        self.quats.grad = g[6 * N:10 * N].view(N, 4)
-        self.opacities.grad = g[10 * N:11 * N].view(N, 1)
+        gm, gs, gq, go = split_grads(ws.grads, ws.N)
+        self.means.grad, self.scales.grad, self.quats.grad, self.opacities.grad = gm, gs, gq, go.view(ws.N, 1)
 
-    def raster_step(self, idx_or_camera, gt, *, loss_weight=1.0, sync=True):
-        """Fused equivalent of train_gaussians.py:81-102 for the "whole" L1 strategy:
-        model(idx) -> compute_projection_loss -> (lambda * loss).backward() -> update_absgrads().
+    def raster_step(self, idx_or_camera, gt, *, loss_weight=1.0, sync=True, strategy: str = "whole",
+                    bg_edge_pixel_ratio: float = 1.0, generator=None, sel_ids=None):
+        """Fused equivalent of train_gaussians.py:81-102:
+        model(idx) -> compute_projection_loss(strategy) -> (lambda * loss).backward() -> update_absgrads().
         ``gt`` is the [H,W] edge map on the device: float32 in [0,1] or the raw uint8 image (the /255 of
-        train_gaussians.py:87 is then fused).  Returns the loss as a 0-dim device tensor.
+        train_gaussians.py:87 is then fused).  ``strategy`` / ``bg_edge_pixel_ratio`` as compute_projection_loss
+        (edge_gs.py:288); the masked strategies need an image index and compute_image_masks.  ``sel_ids``: the flat
+        pixel ids "bg_edge_ratio" samples (default: drawn like the reference does, see sample_bg_pixels).
+        Returns the loss as a 0-dim device tensor.
 
         ``sync=True`` validates the intersection capacity on the host (waits only for the status
         words) and transparently re-runs with larger buffers when needed."""
-        cam = self.viewcams[int(idx_or_camera)] if not isinstance(idx_or_camera, BaseCamera) else idx_or_camera
+        is_cam = isinstance(idx_or_camera, BaseCamera)
+        cam = idx_or_camera if is_cam else self.viewcams[int(idx_or_camera)]
         viewmat, K = cam.viewmat.reshape(4, 4), cam.K.reshape(3, 3)
         W, H = cam.width, cam.height
+        if strategy != "whole" and is_cam:
+            raise ValueError("the masked loss strategies need the view's index (edge_masks[image_index])")
+        staged = False
         while True:
-            ws = self.enqueue_raster_step(viewmat, K, W, H, gt, loss_weight=loss_weight)
+            if strategy != "whole" and not staged:
+                self.set_loss(self._workspace(W, H), strategy, idx_or_camera, bg_edge_pixel_ratio, generator, sel_ids)
+                staged = True
+            ws = self.enqueue_raster_step(viewmat, K, W, H, gt, loss_weight=loss_weight, loss_mode=strategy)
             if not sync:
                 break
             hs = ws.status.cpu()
             self.note_status(hs, ws.T)
             if not int(hs[_lib.EG_ST_OVERFLOW]):
                 break
-            # roll back the abs-grad accumulation is unnecessary: overflowed runs are no-ops in raster kernels
-            get_engine(self.means.device).note_status(int(hs[_lib.EG_ST_NISECT]), self.max_tile_load(ws, hs))
+            # rolling back the abs-grad accumulation is unnecessary: overflowed runs are no-ops in the raster kernels
+            get_engine(self.means.device).note_status(max(int(hs[_lib.EG_ST_NISECT]), int(hs[_lib.EG_ST_NKEYS])),
+                                                      self.max_tile_load(ws, hs))
+            staged = False   # the workspace is rebuilt with larger buffers: stage the loss inputs again
+            if sel_ids is None and strategy == "bg_edge_ratio":
+                sel_ids = torch.nonzero(ws.sel_mask.view(-1)).view(-1)   # keep the same sample for the re-run
         self.install_grads(ws)
         self.absgrads_normalize_factor += 1
         self.step += 1
         self.last_size = (H, W)
-        return (ws.loss_sum[0] / float(W * H)).float()
+        return self.loss_from_workspace(ws, strategy)

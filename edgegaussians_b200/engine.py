@@ -16,6 +16,7 @@ from typing import Optional
 import torch
 
 from . import _lib
+from .layout import grad_numel, split_grads
 from ._lib import (EG_GT_F32, EG_GT_NONE, EG_GT_U8, EG_ST_BADCOLOR, EG_ST_MAXTILE, EG_ST_NISECT, EG_ST_OVERFLOW,
                    EG_ST_WORDS, EgConfig)
 
@@ -39,15 +40,15 @@ KEY_BUCKET_BYTES_MAX = 1 << 30  # above this, tile buckets are replaced by compa
 
 def use_compact_keys(n_tiles: int, tile_capacity: int) -> bool:
     """Fixed-capacity buckets cost T * tile_capacity * 8 B; a view where a few tiles hold most intersections
-    (camera far away) would blow that up, so such views use the two-pass compact layout instead."""
+    (camera far away) would blow that up, so such views use the two-pass compact layout instead
+    (same rule as eg_workspace_sizes_for)."""
     return n_tiles * tile_capacity * 8 > KEY_BUCKET_BYTES_MAX
 
 
 def tile_capacity_for(isect_capacity: int, n_tiles: int, max_tile: int = 0) -> int:
-    """Keys per tile bucket: 4x the mean tile load implied by the intersection capacity, at least
-    1.25x the largest tile seen so far, rounded up to a multiple of 64."""
-    want = max(256, 4 * isect_capacity // max(n_tiles, 1), int(max_tile * 1.25) + 1)
-    return (want + 63) // 64 * 64
+    """Keys per tile bucket (eg_tile_capacity_for: 4x the mean tile load implied by the intersection capacity, at
+    least 1.25x the largest tile seen so far, rounded up to a multiple of 64)."""
+    return int(_lib.load().eg_tile_capacity_for(int(isect_capacity), int(n_tiles), int(max_tile)))
 
 
 @dataclass
@@ -198,8 +199,8 @@ class Engine:
         _lib.check(self.lib.eg_raster_fwd(ctypes.byref(st.cfg), _p(st.rec), _p(st.tile_offsets), _p(st.keys),
                                           _p(st.flatten_ids), _p(st.isect_ids), _p(st.render0), _p(st.alpha),
                                           _p(st.last_ids), _p(st.cmask), _p(gt), gt_kind, _p(st.loss_sum), _p(st.wpix),
-                                          _p(st.last_depth), _p(st.last_gid), None, None, _p(st.status), _stream()),
-                   "eg_raster_fwd")
+                                          _p(st.last_depth), _p(st.last_gid), None, None, None, None, None, _p(st.status),
+                                          _stream()), "eg_raster_fwd")
         return st
 
     # ------------------------------------------------------------------ backward
@@ -227,22 +228,19 @@ class Engine:
         if st.cmask is None:
             raise RuntimeError("raster_bwd needs the contribution masks of the forward (raster_fwd(want_cmask=True))")
         _lib.check(self.lib.eg_raster_bwd(ctypes.byref(st.cfg), _p(st.rec), _p(st.tile_offsets), _p(st.flatten_ids),
-                                          _p(st.cmask), _p(st.alpha), _p(v_render), ch, _p(v_alpha), _p(wpix),
+                                          _p(st.cmask), None, _p(st.alpha), _p(v_render), ch, _p(v_alpha), _p(wpix),
                                           float(seed_scale), _p(grad2d), _p(st.status), _stream()), "eg_raster_bwd")
         return grad2d
 
     def project_bwd(self, st: SplatState, means, quats, scales, opacities, viewmat, K, grad2d, *, v_depths=None,
                     out: Optional[torch.Tensor] = None, absgrad_accum: Optional[torch.Tensor] = None):
         """K7. Returns (v_means [N,3], v_quats [N,4], v_scales [N,3], v_opacities [N]) as views of one
-        flat fp32 buffer laid out means|scales|quats|opacities (11*N floats) -- the buffer that is
+        flat fp32 buffer laid out means|scales|quats|opacities (layout.grad_layout) -- the buffer that is
         all-reduced in the view-sharded multi-GPU step."""
         N = st.N
         if out is None:
-            out = torch.empty(11 * N, dtype=torch.float32, device=st.rec.device)
-        v_means = out[0:3 * N].view(N, 3)
-        v_scales = out[3 * N:6 * N].view(N, 3)
-        v_quats = out[6 * N:10 * N].view(N, 4)
-        v_opac = out[10 * N:11 * N]
+            out = torch.zeros(grad_numel(N), dtype=torch.float32, device=st.rec.device)
+        v_means, v_scales, v_quats, v_opac = split_grads(out, N)
         _lib.check(self.lib.eg_project_bwd(ctypes.byref(st.cfg), _p(means), _p(quats), _p(scales), _p(opacities),
                                            _p(viewmat), _p(K), _p(st.rec), _p(st.gint), _p(grad2d), 0, _p(v_depths),
                                            _p(v_means), _p(v_quats), _p(v_scales), _p(v_opac), _p(absgrad_accum),
@@ -278,12 +276,9 @@ class Engine:
             _lib.check(self.lib.eg_make_seed(st.height * st.width, _p(st.alpha), _p(v_render), ch, _p(v_alpha),
                                              _p(wpix), _stream()), "eg_make_seed")
         if out is None:
-            out = torch.empty(11 * N, dtype=torch.float32, device=dev)
+            out = torch.zeros(grad_numel(N), dtype=torch.float32, device=dev)
         grad2d = torch.empty((N, 8), dtype=torch.float32, device=dev) if want_grad2d else None
-        v_means = out[0:3 * N].view(N, 3)
-        v_scales = out[3 * N:6 * N].view(N, 3)
-        v_quats = out[6 * N:10 * N].view(N, 4)
-        v_opac = out[10 * N:11 * N]
+        v_means, v_scales, v_quats, v_opac = split_grads(out, N)
         _lib.check(self.lib.eg_splat_bwd(ctypes.byref(st.cfg), _p(means), _p(quats), _p(scales), _p(opacities),
                                          _p(viewmat), _p(K), _p(st.rec), _p(st.gint), _p(wpix), float(seed_scale),
                                          _p(st.last_depth), _p(st.last_gid), None, _p(st.status), 0, -1, _p(grad2d), _p(v_means),

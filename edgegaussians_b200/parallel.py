@@ -3,7 +3,7 @@
 The reference is strictly single-GPU, one view per step (train_gaussians.py:71,311).  The path shards
 naturally by VIEW: parameters are replicated, rank r renders view ``perm[step * G + r]`` and the
 per-view gradients (additive over views) are summed with ONE all-reduce over the flat fp32 gradient
-buffer laid out  means | scales | quats | opacities  (11 N floats) -- optionally followed by the [N]
+buffer laid out  means | scales | quats | opacities  (layout.grad_layout: 11 x N rounded up to a multiple of 4 floats) -- optionally followed by the [N]
 abs-grad statistics.  One process per GPU, ``torch.distributed`` (NCCL on GPUs, gloo in CPU tests).
 """
 from __future__ import annotations
@@ -12,6 +12,8 @@ from typing import List, Optional, Sequence
 
 import torch
 import torch.distributed as dist
+
+from .layout import grad_layout, grad_numel, split_grads
 
 
 def view_permutation(n_views: int, epoch: int, seed: int = 0) -> List[int]:
@@ -34,8 +36,8 @@ def steps_per_epoch(n_views: int, world_size: int) -> int:
 
 def flat_grad_views(flat: torch.Tensor, n: int):
     """(v_means [N,3], v_scales [N,3], v_quats [N,4], v_opacities [N,1]) views of the flat buffer."""
-    return (flat[0:3 * n].view(n, 3), flat[3 * n:6 * n].view(n, 3), flat[6 * n:10 * n].view(n, 4),
-            flat[10 * n:11 * n].view(n, 1))
+    vm, vs, vq, vo = split_grads(flat, n)
+    return vm, vs, vq, vo.view(n, 1)
 
 
 def allreduce_gradients(flat: torch.Tensor, absgrad_increment: Optional[torch.Tensor] = None, group=None,
@@ -50,39 +52,57 @@ def allreduce_gradients(flat: torch.Tensor, absgrad_increment: Optional[torch.Te
         flat.div_(dist.get_world_size(group))
 
 
-def gaussian_ranges(n: int, chunks: int, align: int = 128) -> List[tuple]:
-    """Split [0, n) into at most ``chunks`` contiguous ranges whose boundaries are multiples of ``align`` (the
-    Gaussians one CTA of eg_splat_bwd owns)."""
-    chunks = max(1, int(chunks))
-    per = -(-n // chunks)
-    per = -(-per // align) * align
-    return [(b, min(n, b + per)) for b in range(0, n, per)]
+class SymmetricExchange:
+    """The gradient exchange of the view-sharded step through libedgegs' own kernel (eg_allreduce_symm).
 
+    Owns a SYMMETRIC fp32 buffer of ``numel`` floats (``.buf``; the fused step writes its gradients straight into
+    it -- it is handed to the workspace as ``ws.grads``) plus the flag area of the in-kernel rank barriers.
+    torch.distributed._symmetric_memory supplies the allocation, the peer mappings and the NVSwitch multicast
+    mapping (plumbing); the data path is one kernel of this library: switch-side ``multimem.ld_reduce`` of this
+    rank's slice + ``multimem.st`` broadcast (or 128-bit peer loads / stores where the fabric has no multicast
+    object).  ``allreduce_()`` only enqueues that kernel on the current stream: no host sync, CUDA-graph capturable.
+    Collective: every rank of the group constructs it at the same point."""
 
-def range_slices(flat: torch.Tensor, n: int, g0: int, g1: int):
-    """The four slices of the flat gradient buffer (means | scales | quats | opacities) that hold the
-    Gaussians [g0, g1)."""
-    return [flat[3 * g0:3 * g1], flat[3 * n + 3 * g0:3 * n + 3 * g1], flat[6 * n + 4 * g0:6 * n + 4 * g1],
-            flat[10 * n + g0:10 * n + g1]]
+    def __init__(self, numel: int, device: torch.device, group=None, grid: int = 0, multicast: bool = True):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self.lib = _lib.load()
+        group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.numel = int(numel)
+        assert self.numel % 4 == 0, "the flat gradient buffer is padded to 16 bytes (layout.grad_numel)"
+        self.grid = int(grid) if grid > 0 else 64
+        self.buf = symm_mem.empty(self.numel, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        self._hdl = symm_mem.rendezvous(self.buf, group)
+        n_flags = int(self.lib.eg_allreduce_flag_words(self.grid))
+        self.flags = symm_mem.empty(n_flags, dtype=torch.int32, device=device)
+        self.flags.zero_()
+        self._fhdl = symm_mem.rendezvous(self.flags, group)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)   # every rank's flags are zero before the first kernel signals anybody
 
+        def ptrs(hdl, local):
+            # the handle reports the BASE of each rank's block; the tensor may sit at an offset inside it
+            delta = local.data_ptr() - int(hdl.buffer_ptrs[self.rank])
+            return (ctypes.c_void_p * self.world)(*[int(p) + delta for p in hdl.buffer_ptrs]), delta
+        (self._bufs, delta), (self._flagp, _) = ptrs(self._hdl, self.buf), ptrs(self._fhdl, self.flags)
+        mc = int(getattr(self._hdl, "multicast_ptr", 0) or 0) if multicast else 0
+        if mc:
+            mc += delta
+        self.multicast_ptr = mc
+        self.kind = "multimem (switch-side reduction)" if mc else "peer loads/stores"
 
-def allreduce_range(flat: torch.Tensor, n: int, g0: int, g1: int, group=None) -> None:
-    """Sum the gradients of the Gaussians [g0, g1) over all ranks in place (issued on the current stream).  The
-    Gaussian-major backward finishes its gradients range by range, so the collective of one range runs while
-    the next range is still being computed.  On NCCL the four slices go out as one grouped launch."""
-    if not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return
-    parts = range_slices(flat, n, g0, g1)
-    if flat.is_cuda and hasattr(dist, "_coalescing_manager"):
-        try:
-            with dist._coalescing_manager(group=group, device=flat.device):
-                for t in parts:
-                    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-            return
-        except (RuntimeError, TypeError, NotImplementedError):
-            pass
-    for t in parts:
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    def allreduce_(self, count: Optional[int] = None) -> None:
+        """In-place sum of the first ``count`` floats (default: all) over the ranks, enqueued on the current stream."""
+        import ctypes
+        from . import _lib
+        n = self.numel if count is None else int(count)
+        _lib.check(self.lib.eg_allreduce_symm(self._bufs, ctypes.c_void_p(self.multicast_ptr or None), self._flagp, n,
+                                              self.rank, self.world, self.grid,
+                                              ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                   "eg_allreduce_symm")
 
 
 class NativeComm:

@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define EG_ABI_VERSION 8
+#define EG_ABI_VERSION 9
 #define EG_CNT_STRIDE 32
 
 enum {
@@ -59,6 +59,7 @@ enum {
     EG_ST_MAXTILE = 3,  /* largest per-tile intersection count                                                 */
     EG_ST_REDO = 4,     /* tiles composited a second time in sorted order (lazy sort / splat fallback)         */
     EG_ST_STOPPED = 5,  /* tiles in which some pixel hit gsplat's transmittance stop (T * (1 - alpha) <= 1e-4) */
+    EG_ST_NKEYS = 6,    /* keys emitted into the tile lists (eg_bin): == EG_ST_NISECT unless EG_FLAG_CULL_TILES   */
     EG_ST_WORDS = 8
 };
 
@@ -69,7 +70,19 @@ enum { EG_GT_NONE = 0, EG_GT_F32 = 1, EG_GT_U8 = 2 };
  * pixel came near gsplat's transmittance stop threshold -- when none does, the blend result cannot depend on
  * the order.  flatten_ids is then unordered inside such tiles (cmask stays aligned with it).
  * status[EG_ST_REDO] counts the tiles that had to be redone. */
-enum { EG_FLAG_LAZY_SORT = 1, EG_FLAG_COMPACT_KEYS = 2, EG_FLAG_NO_EMIT = 4 };
+enum { EG_FLAG_LAZY_SORT = 1, EG_FLAG_COMPACT_KEYS = 2, EG_FLAG_NO_EMIT = 4, EG_FLAG_CULL_TILES = 8,
+       EG_FLAG_FRONT_SORT = 16 };
+/* EG_FLAG_CULL_TILES (fused training step only): eg_project_fwd / eg_bin emit a Gaussian's key only to the tiles
+ * its alpha >= 1/255 footprint can reach (a conservative ellipse / tile-row test) instead of to every tile of
+ * gsplat's bounding rectangle: the dropped (tile, Gaussian) pairs would fail the alpha test at every pixel, so the
+ * render and the gradients are unchanged, but an elongated Gaussian's lists shrink by 2-3x.  tiles_per_gauss and
+ * status[EG_ST_NISECT] stay gsplat's; tile_offsets / flatten_ids then describe the culled lists
+ * (status[EG_ST_NKEYS] entries).
+ * EG_FLAG_FRONT_SORT (fused training step only; ignored when isect_ids or last_ids are requested): eg_raster_fwd
+ * sorts a long tile list front to back in depth slices of at most 2048 keys (histogram of the depth bits, slice by
+ * slice selection) and stops as soon as every pixel of the tile has hit the transmittance stop -- the exact
+ * gsplat order for everything that is composited, no work for what lies behind.  tile_done[t] = number of list
+ * entries that were processed; flatten_ids / cmask are defined for those entries only. */
 /* EG_FLAG_NO_EMIT: eg_project_fwd neither counts nor emits tile intersections (Gaussian-major forward); it
  * accumulates status[EG_ST_NISECT] = sum of tiles_per_gauss itself (no eg_bin in that pipeline). */
 /* EG_FLAG_COMPACT_KEYS: keys is a compact [isect_capacity] array segmented by tile_offsets instead of T
@@ -97,6 +110,27 @@ const char *eg_last_error(void);
 int eg_abi_version(void);
 /* tile grid for an image: replaces gsplat's tile_width / tile_height arithmetic (rendering.py) */
 int eg_tile_grid(int width, int height, int tile_size, int *tile_w, int *tile_h);
+
+/* Sizing helpers (host arithmetic, no CUDA call): everything a caller needs to allocate the buffers of the fused
+ * iteration (SURVEY.md section 8b "scratch obtained via eg_workspace_bytes").
+ *   eg_grad_layout        offsets5 = float offsets of v_means | v_scales | v_quats | v_opacities in the flat gradient
+ *                         buffer and its total length; segment offsets use n rounded up to a multiple of 4, so every
+ *                         segment is 16-byte aligned for any n (the pad floats are never written);
+ *   eg_tile_capacity_for  keys per tile bucket for an intersection capacity (max_tile = largest tile load seen so
+ *                         far, 0 if unknown);
+ *   eg_workspace_sizes_for / eg_workspace_bytes   per-buffer / total bytes for cfg (n, width, height,
+ *                         isect_capacity; tile_capacity 0 = derive it) and a pipeline EG_PIPE_*. */
+enum { EG_PIPE_SPLAT = 0, EG_PIPE_TILES_SPLAT = 1, EG_PIPE_TILES = 2 };
+typedef struct eg_workspace_sizes {
+    size_t rec, gint, head /* status | loss_sum | tile_stop | tile_cnt */, tile_counts, stop_list, tile_offsets, keys,
+        flatten_ids, cmask, logT, wpix, render0, last_depth, last_gid, grad2d, grads, total;
+    int32_t tile_capacity;
+    int32_t compact_keys; /* 1: EG_FLAG_COMPACT_KEYS layout (buckets would exceed 1 GiB) */
+} eg_workspace_sizes;
+int eg_grad_layout(int n, int64_t *offsets5);
+int eg_tile_capacity_for(int64_t isect_capacity, int n_tiles, int max_tile);
+int eg_workspace_sizes_for(const eg_config *cfg, int pipeline, int max_tile, eg_workspace_sizes *out);
+size_t eg_workspace_bytes(const eg_config *cfg, int pipeline);
 
 /* K1 (+ K2 pass 1): projection forward + per-tile intersection counts.
  * Replaces gsplat fully_fused_projection fwd + isect_tiles pass 1 behind edge_gs.py:250-268.
@@ -131,19 +165,30 @@ int eg_bin(const eg_config *cfg, int32_t *tile_counts, int32_t *tile_offsets, in
  * status[EG_ST_STOPPED] tiles listed in stop_list (eg_splat_resolve) are processed by a small persistent grid,
  * their keys are the first tile_cnt[t] entries of bucket t (eg_emit_flagged), always sorted; tile_offsets is then
  * unused, flatten_ids needs T * tile_capacity entries, last_depth / last_gid are required.
+ * tile_done [T] i32 (optional): number of list entries of each tile that were processed -- all of them unless
+ * EG_FLAG_FRONT_SORT stopped early; flatten_ids / cmask are defined for those entries only (eg_raster_bwd takes it).
+ * loss_params (DEVICE, 4 floats: w_edge, w_bg, w_sel, threshold) / sel_mask [P] u8, both optional, need gt: the
+ * per-pixel coefficient c_p of the fused loss, loss_sum[0] += sum_p c_p |clamp(render0) - gt|, wpix[p] *= c_p:
+ *   c_p = (gt_p >= threshold ? w_edge : w_bg) + (sel_mask[p] ? w_sel : 0);   NULL loss_params: c_p = 1.
+ * That covers the reference's three strategies (edge_gs.py:288-324): "whole" (NULL), "weighted" (w_edge = n_bg / P,
+ * w_bg = n_edge / P, loss = loss_sum / P), "bg_edge_ratio" (w_edge = 1 / n_edge, w_bg = 0, sel_mask = the sampled
+ * pixels, w_sel = 1 / n_sel, loss = loss_sum); the scalars live on the device so a captured graph can be re-used
+ * when they change.
  * Any of render0 / alpha / last_ids / isect_ids / cmask / gt / loss_sum / wpix / last_* / tile_* may be NULL. */
 int eg_raster_fwd(const eg_config *cfg, const float *rec, const int32_t *tile_offsets, uint64_t *keys,
                   int32_t *flatten_ids, int64_t *isect_ids, float *render0, float *alpha,
                   int32_t *last_ids, uint32_t *cmask, const void *gt, int gt_kind, double *loss_sum,
                   float *wpix, uint32_t *last_depth, int32_t *last_gid, const int32_t *stop_list,
-                  const int32_t *tile_cnt, int32_t *status, void *stream);
+                  const int32_t *tile_cnt, int32_t *tile_done, const float *loss_params, const uint8_t *sel_mask,
+                  int32_t *status, void *stream);
 
 /* K6: compositing backward with abs-grad.  Replaces gsplat rasterize_to_pixels bwd.
  * The seed of pixel p is  w_p = (sum_ch v_render[p,ch] + v_alpha[p]) * (1 - alpha[p])  when
  * v_render/v_alpha/alpha are given (generic autograd path; v_render has `v_render_channels`
- * interleaved channels), or  w_p = seed_scale * wpix[p]  (fused-loss path). */
+ * interleaved channels), or  w_p = seed_scale * wpix[p]  (fused-loss path).  tile_done [T] (optional, written by
+ * eg_raster_fwd): only the first tile_done[t] entries of tile t's list are walked. */
 int eg_raster_bwd(const eg_config *cfg, const float *rec, const int32_t *tile_offsets,
-                  const int32_t *flatten_ids, const uint32_t *cmask, const float *alpha,
+                  const int32_t *flatten_ids, const uint32_t *cmask, const int32_t *tile_done, const float *alpha,
                   const float *v_render, int v_render_channels, const float *v_alpha,
                   const float *wpix, float seed_scale, float *grad2d, const int32_t *status,
                   void *stream);
@@ -165,7 +210,7 @@ int eg_project_bwd(const eg_config *cfg, const float *means, const float *quats,
  *   eg_splat_fwd      logT [P] fp32 (zero on entry) += log2(1 - alpha) of every (pixel, Gaussian) pair that passes
  *                     gsplat's tile-rectangle / sigma / alpha tests (red.global.add.v4.f32, no tile lists);
  *   eg_splat_resolve  per 16x16 tile: T = 2^logT, render = alpha = 1 - T, fused clamp + "whole" L1 loss + backward
- *                     seed exactly as eg_raster_fwd (loss_sum, wpix), logT re-zeroed.  A tile in which some
+ *                     seed exactly as eg_raster_fwd (loss_sum, wpix, loss_params, sel_mask), logT re-zeroed.  A tile in which some
  *                     pixel's T is within 0.1 % of gsplat's stop threshold 1e-4 is NOT resolved: tile_stop[t] = 1,
  *                     its id is appended to stop_list [T] and status[EG_ST_STOPPED] += 1 (tile_stop zeroed by
  *                     the caller);
@@ -175,8 +220,8 @@ int eg_project_bwd(const eg_config *cfg, const float *means, const float *quats,
 int eg_splat_fwd(const eg_config *cfg, const float *rec, const int32_t *gint, float *logT, const int32_t *status,
                  void *stream);
 int eg_splat_resolve(const eg_config *cfg, float *logT, const void *gt, int gt_kind, double *loss_sum, float *wpix,
-                     float *render0, float *alpha, int32_t *tile_stop, int32_t *stop_list, int32_t *status,
-                     void *stream);
+                     float *render0, float *alpha, int32_t *tile_stop, int32_t *stop_list, const float *loss_params,
+                     const uint8_t *sel_mask, int32_t *status, void *stream);
 int eg_emit_flagged(const eg_config *cfg, const float *rec, const int32_t *gint, const int32_t *tile_stop,
                     int32_t *tile_cnt, uint64_t *keys, int32_t *status, void *stream);
 
@@ -191,8 +236,7 @@ int eg_emit_flagged(const eg_config *cfg, const float *rec, const int32_t *gint,
  *                   status[EG_ST_STOPPED] != 0, and, when tile_stop [T] i32 is given (eg_splat_resolve), only
  *                   inside the tiles it flags (the planes are undefined elsewhere).
  *   g_begin, g_end  only the Gaussians [g_begin, g_end) are processed (g_end < 0: all) -- every Gaussian has one
- *                   owner, so the view-sharded multi-GPU step launches the backward in Gaussian ranges and
- *                   all-reduces the gradients of a finished range while the next one is being computed.
+ *                   owner, so the gradients of a range are final as soon as its launch has drained.
  *   grad2d_out [N,8] optional: the 2D gradients (layout of grad2d above), WRITTEN.
  * Gradient outputs are WRITTEN (layout as eg_project_bwd); absgrad_accum [N] (may be NULL) += ||absgrad||_2. */
 int eg_splat_bwd(const eg_config *cfg, const float *means, const float *quats, const float *scales,
@@ -203,25 +247,27 @@ int eg_splat_bwd(const eg_config *cfg, const float *means, const float *quats, c
                  float *v_quats, float *v_scales, float *v_opacities, float *absgrad_accum, void *stream);
 
 /* View-sharded multi-GPU step (no reference counterpart: the reference is single-GPU, train_gaussians.py:311; the
- * sharding is SURVEY.md section 8e's): a communicator over the ranks' GPUs and the backward + exchange as ONE call.
- * NCCL is resolved at run time (dlopen libnccl.so.2), the library does not link against it.
- *   eg_comm_unique_id  rank 0: 128-byte rendezvous id (host memory), to be broadcast to the other ranks by the caller
- *   eg_comm_init       collective over all ranks, on the calling thread's current CUDA device
- *   eg_splat_bwd_allreduce  eg_splat_bwd over [0, N) in n_ranges (<= 16) Gaussian ranges on `stream`; the gradients
- *                      of each finished range (its slices of grads = means | scales | quats | opacities, 11 N
- *                      floats, WRITTEN then summed over ranks in place) are all-reduced on `comm_stream` while the
- *                      next range is computed; `stream` finally waits for the last collective.  absgrad_accum
- *                      stays per rank (sum it where it is consumed, edge_gs.py:544-576). */
+ * sharding is SURVEY.md section 8e's: parameters replicated, one view per GPU per step, per-view gradients summed).
+ *
+ * eg_allreduce_symm -- the exchange as ONE kernel of this library over NVLink / NVSwitch: in-place fp32 sum of
+ *   `count` floats (a multiple of 4; eg_grad_layout pads to that) that every rank holds at the same offset of a
+ *   SYMMETRIC allocation.  peer_bufs [world] (HOST array of device pointers): the buffer as mapped into this
+ *   process for every rank (peer_bufs[rank] = the local one).  mc_buf: the same buffer through an NVSwitch multicast
+ *   mapping, or NULL -- with it each rank reduces its 1/world slice with multimem.ld_reduce (summed inside the
+ *   switch) and broadcasts it with multimem.st; without it, 128-bit peer loads / stores.  peer_flags [world] (HOST
+ *   array): per rank a zero-initialised symmetric area of eg_allreduce_flag_words(grid) u32 used by the in-kernel
+ *   rank barriers (self-resetting: no host work between calls; capturable in a CUDA graph).  Every rank must
+ *   enqueue the call with the same count / grid; `grid` <= 0 picks the default.
+ * eg_comm_* -- the same sum through NCCL (resolved at run time with dlopen, no link dependency), kept as the A/B
+ *   baseline: eg_comm_unique_id on rank 0 (128-byte id in host memory, broadcast by the caller), eg_comm_init
+ *   collectively on the calling thread's current device, eg_comm_allreduce in place on `stream`. */
+int eg_allreduce_flag_words(int grid);
+int eg_allreduce_symm(float *const *peer_bufs, float *mc_buf, uint32_t *const *peer_flags, int64_t count, int rank,
+                      int world, int grid, void *stream);
 int eg_comm_unique_id(void *id128);
 int eg_comm_init(const void *id128, int rank, int world, void **comm_out);
 int eg_comm_destroy(void *comm);
-/* in-place fp32 sum over the ranks, enqueued directly on `stream` (no side stream, no event hops) */
 int eg_comm_allreduce(float *buf, int64_t count, void *comm, void *stream);
-int eg_splat_bwd_allreduce(const eg_config *cfg, const float *means, const float *quats, const float *scales,
-                           const float *opacities, const float *viewmat, const float *K, const float *rec,
-                           const int32_t *gint, const float *wpix, float seed_scale, const uint32_t *last_depth,
-                           const int32_t *last_gid, const int32_t *tile_stop, const int32_t *status, float *grads,
-                           float *absgrad_accum, int n_ranges, void *comm, void *comm_stream, void *stream);
 
 /* Per-pixel seed of the gsplat-shaped autograd path:
  *   wpix[p] = (sum_ch v_render[p,ch] + v_alpha[p]) * (1 - alpha[p])      (v_render / v_alpha may be NULL) */

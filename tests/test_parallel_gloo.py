@@ -11,6 +11,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from edgegaussians_b200 import parallel
+from edgegaussians_b200.layout import grad_layout, grad_numel, split_grads
 
 
 def _free_port():
@@ -21,7 +22,10 @@ def _free_port():
 
 def _fake_view_grad(view, n):
     g = torch.Generator().manual_seed(1234 + view)
-    return torch.randn(11 * n, generator=g, dtype=torch.float32)
+    flat = torch.zeros(grad_numel(n))
+    for t in split_grads(flat, n):      # the pad floats between the segments are never written
+        t.copy_(torch.randn(t.shape, generator=g, dtype=torch.float32))
+    return flat
 
 
 def _worker(rank, world, port, n, n_views, out_dir):
@@ -30,18 +34,13 @@ def _worker(rank, world, port, n, n_views, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         perm = parallel.view_permutation(n_views, epoch=3, seed=7)
-        total = torch.zeros(11 * n)
+        total = torch.zeros(grad_numel(n))
         absg = torch.zeros(n)
         for step in range(parallel.steps_per_epoch(n_views, world)):
             view = parallel.views_for_step(perm, step, world)[rank]
-            flat = _fake_view_grad(view, n) if view is not None else torch.zeros(11 * n)
+            flat = _fake_view_grad(view, n) if view is not None else torch.zeros(grad_numel(n))
             inc = torch.full((n,), float(view + 1)) if view is not None else torch.zeros(n)
-            if step % 2 == 0:
-                parallel.allreduce_gradients(flat, inc)
-            else:  # the chunked form the Gaussian-major backward uses: range by range
-                for g0, g1 in parallel.gaussian_ranges(n, 3, align=8):
-                    parallel.allreduce_range(flat, n, g0, g1)
-                dist.all_reduce(inc)
+            parallel.allreduce_gradients(flat, inc)
             total += flat
             absg += inc
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), total=total.numpy(), absg=absg.numpy(), perm=np.array(perm))
@@ -68,19 +67,16 @@ def test_views_for_step_and_layout():
     assert parallel.views_for_step(perm, 0, 2) == [4, 2]
     assert parallel.views_for_step(perm, 2, 2) == [1, None]
     assert parallel.steps_per_epoch(5, 2) == 3 and parallel.steps_per_epoch(8, 8) == 1
-    n = 5
-    flat = torch.arange(11 * n, dtype=torch.float32)
-    vm, vs, vq, vo = parallel.flat_grad_views(flat, n)
-    assert vm.shape == (n, 3) and vs.shape == (n, 3) and vq.shape == (n, 4) and vo.shape == (n, 1)
-    assert vs[0, 0] == 3 * n and vq[0, 0] == 6 * n and vo[0, 0] == 10 * n
-    vm[0, 0] = -1.0
-    assert flat[0] == -1.0                                          # views, not copies
-    assert parallel.gaussian_ranges(1000, 4) == [(0, 256), (256, 512), (512, 768), (768, 1000)]
-    assert parallel.gaussian_ranges(100, 4) == [(0, 100)] and parallel.gaussian_ranges(37, 3, align=8) == [(0, 16), (16, 32), (32, 37)]
-    covered = torch.zeros(11 * n)
-    for g0, g1 in parallel.gaussian_ranges(n, 2, align=2):
-        for t in parallel.range_slices(covered, n, g0, g1):
-            t += 1
-    assert bool((covered == 1).all())                               # the ranges tile the flat buffer exactly once
+    for n in (5, 8, 37, 1001):            # odd N included: every segment stays 16-byte aligned
+        om, os_, oq, oo, total = grad_layout(n)
+        assert (om, total) == (0, grad_numel(n)) and total % 4 == 0
+        assert all(o % 4 == 0 for o in (os_, oq, oo)) and os_ >= 3 * n and oq - os_ >= 3 * n and oo - oq >= 4 * n and total - oo >= n
+        flat = torch.arange(total, dtype=torch.float32)
+        vm, vs, vq, vo = parallel.flat_grad_views(flat, n)
+        assert vm.shape == (n, 3) and vs.shape == (n, 3) and vq.shape == (n, 4) and vo.shape == (n, 1)
+        assert vs[0, 0] == os_ and vq[0, 0] == oq and vo[0, 0] == oo
+        vm[0, 0] = -1.0
+        assert flat[0] == -1.0                                      # views, not copies
+        assert (vq.data_ptr() - flat.data_ptr()) % 16 == 0          # the float4 gradient stores of the kernels
     assert parallel.view_permutation(10, 1, 3) == parallel.view_permutation(10, 1, 3)
     assert parallel.view_permutation(10, 1, 3) != parallel.view_permutation(10, 2, 3)
