@@ -3,13 +3,17 @@
 
 Metric (BASELINE.json): train iters/sec (fwd+bwd raster) @ 500k Gaussians x 1600x1200, with the
 achieved fraction of the B200 HBM roofline.  One "step" = one view: activations + projection +
-tile binning + per-tile sort + compositing + "whole" L1 edge-map loss + both backward kernels +
-abs-grad accumulation; the optimizer step and KNN are excluded.
+(tile binning + per-tile sort) + compositing + "whole" L1 edge-map loss + backward + abs-grad
+accumulation (+ the gradient exchange when N > 1); the optimizer step, the
+regularisers and KNN are excluded from the step and reported separately (`aux_ms`).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--regime both|init|trained]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
-Prints ONE JSON line on rank 0 (contract in the task statement).  Synthetic data (synth-v1).
+Prints ONE JSON line on rank 0 (contract in the task statement).  Synthetic data (synth-v1).  The headline
+`value` is the init regime (reference initialisation: isotropic 0.004, opacity 0.08); the default run also
+measures the trained regime (5:1 anisotropy, opacity U(0.05, 0.9)) and reports both under `regimes`, each
+with its own roofline and its own full-size parity check against the CPU oracle.
 """
 from __future__ import annotations
 
@@ -41,23 +45,24 @@ def parse_args():
     ap.add_argument("--n", type=int, default=500_000, help="Gaussians")
     ap.add_argument("--width", type=int, default=1600)
     ap.add_argument("--height", type=int, default=1200)
-    ap.add_argument("--regime", default="init", choices=["init", "trained"])
+    ap.add_argument("--regime", default="both", choices=["both", "init", "trained"])
     ap.add_argument("--views", type=int, default=8, help="distinct synthetic views cycled per rank")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed iterations")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle (no parity block, no cpu_baseline)")
+    ap.add_argument("--no-aux", action="store_true", help="skip the optimizer / regulariser / KNN timings")
     ap.add_argument("--no-lazy-sort", action="store_true", help="always sort every tile (gsplat order) in the tile pipelines")
+    ap.add_argument("--no-cull", action="store_true", help="emit keys to every tile of gsplat's rectangle (no footprint culling)")
+    ap.add_argument("--no-front-sort", action="store_true", help="sort whole tile lists (no depth-sliced early stop)")
+    ap.add_argument("--morton", action="store_true", help="Morton-order the Gaussians once before the run (as after a densify)")
     ap.add_argument("--pipeline", default="auto", choices=["auto", "splat", "tiles+splat", "tiles"],
                     help="fused-step pipeline (edge_gs.enqueue_raster_step); auto = what training would run")
-    ap.add_argument("--allreduce-chunks", type=int, default=1,
-                    help="N > 1: Gaussian ranges of the backward whose all-reduce overlaps the next range")
-    ap.add_argument("--native-allreduce", action="store_true",
-                    help="N > 1: all-reduce through the library's own communicator (eg_comm_allreduce) instead of torch.distributed")
-    ap.add_argument("--cpu-budget-s", type=float, default=25.0)
+    ap.add_argument("--exchange", default="auto", choices=["auto", "symm", "symm-p2p", "nccl", "native-nccl"],
+                    help="N > 1: gradient exchange -- the library's symmetric-memory kernel (default) or NCCL (A/B)")
     return ap.parse_args()
 
 
 def algorithmic_bytes(N, I, P):
-    """A = 228 N + 92 I + 20 P, split per stage."""
+    """A = 228 N + 92 I + 20 P, split per stage (I = gsplat's n_isects)."""
     stages = {
         "project_fwd": 76 * N,
         "bin": 12 * I,
@@ -73,36 +78,39 @@ def algorithmic_bytes(N, I, P):
     return stages, total
 
 
-def workload_name(args):
-    return f"{args.n} Gaussians x {args.width}x{args.height}, 1 view/iter/GPU, regime={args.regime}"
+def workload_name(args, regime="init"):
+    return f"{args.n} Gaussians x {args.width}x{args.height}, 1 view/iter/GPU, regime={regime}"
 
 
 def ncu_traffic_bytes(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full
-    summary (profiles/r1_splat_ncu_full_summary.txt, written by scripts/summarise_profiles.py); None if absent."""
-    path = os.path.join(ROOT, "profiles", "r1_splat_ncu_full_summary.txt")
-    if not os.path.exists(path):
-        return None
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the newest committed
+    `ncu --set full` summary under profiles/ (written by scripts/summarise_profiles.py from a capture of this
+    same bench command); None if no capture of that kernel is committed."""
+    pdir = os.path.join(ROOT, "profiles")
+    cands = sorted((f for f in os.listdir(pdir) if f.endswith("ncu_full_summary.txt")), reverse=True) if os.path.isdir(pdir) else []
     mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    cur, rd, wr, best = None, None, None, None
-    for line in open(path):
-        parts = line.split()
-        if not parts:
-            continue
-        if parts[0] == "Kernel" and len(parts) > 2:
-            cur, rd, wr = line, None, None
-        elif parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and cur and kernel in cur:
-            try:
-                val = float(parts[1].replace(",", "")) * mult.get(parts[2], 1.0)
-            except (ValueError, IndexError):
+    for fn in cands:
+        cur, rd, wr, best = None, None, None, None
+        for line in open(os.path.join(pdir, fn)):
+            parts = line.split()
+            if not parts:
                 continue
-            if parts[0].startswith("dram__bytes_read"):
-                rd = val
-            else:
-                wr = val
-            if rd is not None and wr is not None:
-                best = rd + wr
-    return best
+            if parts[0] == "Kernel" and len(parts) > 2:
+                cur, rd, wr = line, None, None
+            elif parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and cur and kernel in cur:
+                try:
+                    val = float(parts[1].replace(",", "")) * mult.get(parts[2], 1.0)
+                except (ValueError, IndexError):
+                    continue
+                if parts[0].startswith("dram__bytes_read"):
+                    rd = val
+                else:
+                    wr = val
+                if rd is not None and wr is not None:
+                    best = rd + wr
+        if best is not None:
+            return best, fn
+    return None, None
 
 
 def load_peaks():
@@ -159,57 +167,86 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------
-def cpu_step_time(args, n_sample, reps, threads=None):
-    """Time the CPU oracle's full iteration (projection .. loss .. backward) on synth-v1."""
+# CPU legs (the oracle is test infrastructure: it is only ever the checker or the reported baseline)
+# ----------------------------------------------------------------------------------------------
+def cpu_all_cores():
+    """Use every host core, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
+    from oracle import oracle
+    oracle.build()
+    oracle.set_num_threads(os.cpu_count() or 1)
+    return oracle.num_threads()
+
+
+def cpu_full_step(args, regime, view):
+    """One full-size iteration of the CPU oracle on synth-v1 (same inputs as the GPU rank-0 slot `view`).
+    Returns (result dict, seconds)."""
     from edgegaussians_b200 import synth
     from oracle import oracle
-    if threads:
-        oracle.set_num_threads(threads)
-    m, q, s, o = synth.make_gaussians(n_sample, args.regime, 0)
-    vms, Ks = synth.make_cameras(max(args.views, 2), args.width, args.height)
-    gt = synth.make_edge_map(args.width, args.height, 0)
-    times = []
-    for r in range(reps):
-        t0 = time.perf_counter()
-        oracle.edge_step(m, q, s, o, vms[r % len(vms)], Ks[r % len(vms)], args.width, args.height, gt)
-        times.append(time.perf_counter() - t0)
-    return times, oracle.num_threads()
+    m, q, s, o = synth.make_gaussians(args.n, regime, 0)
+    vms, Ks = synth.make_cameras(args.views * max(args.gpus, 1), args.width, args.height)
+    gt = synth.make_edge_map_u8(args.width, args.height, view).astype(np.float32) / np.float32(255.0)
+    t0 = time.perf_counter()
+    ref = oracle.edge_step(m, q, s, o, vms[view], Ks[view], args.width, args.height, gt)
+    return ref, time.perf_counter() - t0
 
 
 def run_reference(args):
-    """--impl reference: the reference path's CPU implementation (the oracle port: the reference's own
-    splat lives in CUDA-only gsplat, absent here) on all host cores."""
+    """--impl reference: the reference path's CPU implementation (the oracle port: the reference's own splat lives in
+    CUDA-only gsplat, absent here) on ALL host cores, full size, no sub-sampling.  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import oracle
-    oracle.build()
-    cores = oracle.num_threads()
-    budget = 150.0
-    t_probe, _ = cpu_step_time(args, min(args.n, 50_000), 1)
-    est_full = t_probe[0] * args.n / min(args.n, 50_000)
-    total_steps = args.steps + args.warmup
-    frac = min(1.0, budget / max(est_full * total_steps, 1e-9))
-    n_sample = max(1000, int(args.n * frac))
-    times, cores = cpu_step_time(args, n_sample, total_steps)
+    cores = cpu_all_cores()
+    regime = "init" if args.regime == "both" else args.regime
+    n_views = args.views * max(args.gpus, 1)
+    times = []
+    for i in range(args.warmup + args.steps):
+        _, dt = cpu_full_step(args, regime, i % n_views)
+        times.append(dt)
+        if sum(times) > 240.0 and i + 1 >= args.warmup + 3:   # bounded wall time; says so in `sample`
+            break
     timed = times[args.warmup:]
     t_step = sum(timed) / len(timed)
-    scale = args.n / n_sample
-    value = 1.0 / (t_step * scale)
+    value = 1.0 / t_step
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * t_step * scale, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(timed),
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic (synth-v1)",
-        "config": {"workload": workload_name(args)},
+        "config": {"workload": workload_name(args, regime)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{n_sample} of {args.n} Gaussians per step at full resolution, time scaled x{scale:.2f} (linear in N)"},
+                         "sample": f"{len(timed)} full-size iterations ({args.n} Gaussians, {args.width}x{args.height}), "
+                                   f"no sub-sampling, {cores} threads (os.cpu_count() = {os.cpu_count()})"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
+def parity_block(ref, loss, grads_flat, absgrad, n_isects, N):
+    """Full-size parity of one GPU iteration against the CPU oracle on identical inputs: tolerances of
+    tests/test_gpu_parity.py (gradients |d| <= 1e-3 |ref| + 2e-5 max|ref|, at most max(2, 5e-4 n) violations)."""
+    from edgegaussians_b200.layout import split_grads
+    gm, gs, gq, go = split_grads(grads_flat, N)
+    out = {"loss_gpu": float(loss), "loss_oracle": float(ref["loss"]), "loss_abs_err": abs(float(loss) - float(ref["loss"])),
+           "n_isects_gpu": int(n_isects), "n_isects_oracle": int(ref["state"]["n_isects"]),
+           "n_isects_equal": int(n_isects) == int(ref["state"]["n_isects"]), "grad_violations": {}, "grad_max_rel_err": {}}
+    ok = out["n_isects_equal"] and out["loss_abs_err"] <= 1e-5
+    for key, got in (("v_means", gm), ("v_log_scales", gs), ("v_quats", gq), ("v_logit_opacities", go), ("absgrad_norm", absgrad)):
+        exp = ref[key].reshape(-1)
+        got = got.reshape(-1)
+        scale = float(np.abs(exp).max())
+        err = np.abs(got - exp)
+        floor = 1e-7 if key == "v_quats" else 0.0   # isotropic Gaussians: the quaternion gradient is a cancellation to ~0
+        bad = int((err > 1e-3 * np.abs(exp) + 2e-5 * scale + floor).sum())
+        out["grad_violations"][key] = bad
+        out["grad_max_rel_err"][key] = float(err.max() / (scale + 1e-30))
+        ok = ok and bad <= max(2, int(5e-4 * err.size))
+    out["ok"] = bool(ok)
+    return out
+
+
 # ----------------------------------------------------------------------------------------------
-def run_b200(args):
+def bench_regime(args, regime, ctx):
+    """Everything measured for one regime on this rank; rank 0 returns the summary dict."""
     import torch
     import torch.distributed as dist
     from edgegaussians_b200 import synth
@@ -217,62 +254,110 @@ def run_b200(args):
     from edgegaussians_b200.edge_gs import EdgeGaussianSplatting
     from edgegaussians_b200.graph_step import GraphedRasterStep
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        import datetime
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
-
+    world, rank, dev = ctx["world"], ctx["rank"], ctx["dev"]
     N, W, H, V = args.n, args.width, args.height, args.views
     P = W * H
-    m, q, s, o = synth.make_gaussians(N, args.regime, 0)
+    m, q, s, o = synth.make_gaussians(N, regime, 0)
     vms, Ks = synth.make_cameras(V * world, W, H)
-    my_views = [rank + world * i for i in range(V)]            # view-sharded: rank r renders views r, r+G, ...
+    # view-sharded: at step i rank r renders view i * G + r (slot i of that rank)
+    my_views = [i * world + rank for i in range(V)]
     gts_u8 = [synth.make_edge_map_u8(W, H, v) for v in my_views]
     model = EdgeGaussianSplatting(device=dev)
     cams = [OpenCVCamera.from_matrices(H, W, Ks[v], vms[v]).to(dev) for v in my_views]
     model.set_params(m, s, q, o, viewcams=cams)
     model.lazy_sort = False if args.no_lazy_sort else "auto"
     model.pipeline = args.pipeline
+    model.cull_tiles = not args.no_cull
+    model.front_sort = not args.no_front_sort
+    perm = None
+    if args.morton:
+        perm = model.sort_gaussians_morton()   # once, like after a densify; parity below maps back through `perm`
 
-    step = GraphedRasterStep(model, W, H, n_slots=V, gt_dtype=torch.uint8, allreduce=world > 1,
-                             allreduce_chunks=args.allreduce_chunks, native_allreduce=args.native_allreduce)
+    step = GraphedRasterStep(model, W, H, n_slots=V, gt_dtype=torch.uint8, allreduce=world > 1, exchange=args.exchange)
     host_vm = [torch.from_numpy(vms[v]).pin_memory() for v in my_views]
     host_K = [torch.from_numpy(Ks[v]).pin_memory() for v in my_views]
     host_gt = [torch.from_numpy(g).pin_memory() for g in gts_u8]
     for i in range(V):
         step.set_view(i, host_vm[i], host_K[i], host_gt[i])
     torch.cuda.synchronize()
-    n_isects_max = step.calibrate()
+    step.calibrate()
     for i in range(V):
         step.capture(i)
     ws = step.ws
-    grads = ws.grads
 
-    flush_buf = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush_buf = ctx["flush_buf"]
 
     def flush():
         if flush_buf is not None:
             flush_buf.fill_(1)
 
     def one_step(i):
-        step.replay(i % V)   # includes the NCCL all-reduce of the gradient buffer when world > 1
+        step.replay(i % V)   # includes the gradient exchange when world > 1
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---------------- parity at full size: this rank-0 iteration against the CPU oracle ----------------
+    parity, cpu_s, cpu_cores = None, None, None
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu_cores = cpu_all_cores()
+        ws_e = step._enqueue(0, accumulate_absgrad=False)   # eager, no exchange: one view on one GPU
+        torch.cuda.synchronize()
+        hs = ws_e.status.cpu()
+        grads_host = ws_e.grads.cpu().numpy().copy()
+        loss_gpu = float(step.loss())
+        # abs-grad norm of this view alone
+        absg = torch.zeros(N, device=dev)
+        saved = model.absgrads
+        model.absgrads = absg
+        step._enqueue(0, accumulate_absgrad=True)
+        torch.cuda.synchronize()
+        model.absgrads = saved
+        ref, cpu_s = cpu_full_step(args, regime, my_views[0])
+        absg_h = absg.cpu().numpy()
+        if perm is not None:   # the model holds the Gaussians in Morton order: undo it for the comparison
+            from edgegaussians_b200.layout import grad_layout
+            inv = np.empty(N, np.int64)
+            inv[perm.cpu().numpy()] = np.arange(N)
+            offs = grad_layout(N)
+            g2 = grads_host.copy()
+            for off, w in zip(offs[:4], (3, 3, 4, 1)):
+                g2[off:off + w * N] = grads_host[off:off + w * N].reshape(N, w)[inv].reshape(-1)
+            grads_host, absg_h = g2, absg_h[inv]
+        parity = parity_block(ref, loss_gpu, grads_host, absg_h, int(hs[0]), N)
+        parity["stopped_tiles"] = int(hs[5])
+    barrier()
+
+    # ---------------- N > 1: the exchanged buffer equals the sum of the ranks' single-GPU gradients ----------------
+    sum_check = None
+    if world > 1:
+        one_step(0)
+        torch.cuda.synchronize()
+        exchanged = ws.grads.clone()
+        barrier()
+        if rank == 0:
+            acc = torch.zeros_like(exchanged, dtype=torch.float64)
+            tmp_gt = [synth.make_edge_map_u8(W, H, r) for r in range(world)]   # slot 0 of rank r is view r
+            for r in range(world):
+                step.set_view(0, torch.from_numpy(vms[r]), torch.from_numpy(Ks[r]), torch.from_numpy(tmp_gt[r]), non_blocking=False)
+                w_r = step._enqueue(0, accumulate_absgrad=False)
+                torch.cuda.synchronize()
+                acc += w_r.grads.double()
+            step.set_view(0, host_vm[0], host_K[0], host_gt[0], non_blocking=False)
+            scale = float(acc.abs().max())
+            err = (exchanged.double() - acc).abs()
+            bad = int((err > 1e-5 * acc.abs() + 1e-6 * scale).sum())
+            sum_check = {"ranks": world, "max_abs_err": float(err.max()), "max_abs": scale, "violations": bad,
+                         "ok": bad == 0, "tolerance": "|d| <= 1e-5 |sum| + 1e-6 max|sum|"}
+        barrier()
+
     # ---------------- device-resident timing (`value`) ----------------
     for i in range(args.warmup):
         flush(); one_step(i)
     barrier()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(ctx["local"])
     if rank == 0:
         sampler.start()
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
@@ -298,8 +383,7 @@ def run_b200(args):
     hot_ms = e0.elapsed_time(e1)
     # the timed region lasts only tens of milliseconds: keep the same load running (untimed) for about a second so
     # that the nvidia-smi sampler (100 ms period) sees the clocks / throttle reasons this workload runs at
-    # (a fixed iteration COUNT agreed by all ranks: every step holds a collective, so a time-based loop would
-    # run a different number of all-reduces per rank and dead-lock)
+    # (a fixed iteration COUNT agreed by all ranks: every step holds a collective)
     n_cont = torch.tensor([max(32, min(20000, int(1200.0 * args.steps / max(total_ms, 1e-3))))], device=dev)
     if world > 1:
         dist.broadcast(n_cont, src=0)
@@ -309,12 +393,11 @@ def run_b200(args):
             torch.cuda.synchronize()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    n_isects = int(ws.status[0])
     overflow = int(ws.status[1])
 
     # ---------------- per-kernel breakdown (events between stages, eager launches) ----------------
-    names, acc = None, {}
-    isect_sum = 0
+    names, acc_t = None, {}
+    isect_sum = keys_sum = 0
     reps = min(args.steps, 16)
     for i in range(reps):
         evs = {}
@@ -324,22 +407,32 @@ def run_b200(args):
             e.record()
             evs[name] = e
         flush()  # also lets the host run ahead of the device so events see no launch gaps
-        step._enqueue(i % V, stage_cb=cb)
+        step._enqueue(i % V, stage_cb=cb, accumulate_absgrad=False)
+        ex0 = ex1 = None
+        if step.exchange is not None:
+            # exchange kernel alone (all ranks enter together: its own in-kernel barriers line the ranks up)
+            ex0, ex1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ex0.record(); step.exchange.allreduce_(); ex1.record()
         torch.cuda.synchronize()
         if names is None:
             names = [k for k in evs if k != "begin"]   # stage order as enqueued (dicts keep insertion order)
-            acc = {k: 0.0 for k in names}
+            acc_t = {k: 0.0 for k in names}
+            if ex0 is not None:
+                acc_t["exchange"] = 0.0
         prev = "begin"
         for k in names:
-            acc[k] += evs[prev].elapsed_time(evs[k])
+            acc_t[k] += evs[prev].elapsed_time(evs[k])
             prev = k
+        if ex0 is not None:
+            acc_t["exchange"] += ex0.elapsed_time(ex1)
         isect_sum += int(ws.status[0])
-    kern_ms = {k: acc[k] / reps for k in names}
+        keys_sum += int(ws.status[6])
+    kern_ms = {k: acc_t[k] / reps for k in acc_t}
     I_mean = isect_sum / reps
 
     # ---------------- end-to-end through the public API with host buffers (`e2e`) ----------------
     loss_host = torch.zeros(1, dtype=torch.float64).pin_memory()
-    copy_stream = torch.cuda.Stream()
+    copy_stream = ctx["copy_stream"]
     h2d = host_gt[0].numel() * host_gt[0].element_size() + 16 * 4 + 9 * 4
     d2h = 8
 
@@ -370,70 +463,193 @@ def run_b200(args):
             done[slot] = e
         torch.cuda.synchronize()
 
+    n_e2e = 4 * args.steps   # a longer region than the device-timed one: wall-clock timing needs it
     e2e_loop(max(2, args.warmup))
     barrier()
     t0 = time.perf_counter()
-    e2e_loop(args.steps)
+    e2e_loop(n_e2e)
     barrier()
     t_e2e = time.perf_counter() - t0
-    # restore slot contents for any later use
-    for i in range(V):
+    for i in range(V):   # restore slot contents
         step.set_view(i, host_vm[i], host_K[i], host_gt[i])
     torch.cuda.synchronize()
 
     # ---------------- reductions over ranks ----------------
-    vals = torch.tensor([total_ms, t_e2e * 1e3], dtype=torch.float64, device=dev)
+    vals = torch.tensor([total_ms, t_e2e * 1e3, hot_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms = float(vals[0]), float(vals[1])
+    total_ms, e2e_ms, hot_ms = float(vals[0]), float(vals[1]), float(vals[2])
+    if rank != 0:
+        return None
 
+    peak, peak_src = load_peaks()
+    stages, A = algorithmic_bytes(N, I_mean, P)
+    ms_per_step = total_ms / args.steps
+    value = world * args.steps / (total_ms * 1e-3)
+    kernels = [k for k in names if k != "memset"]
+    dom = max(kernels, key=lambda k: kern_ms[k])
+    achieved = stages[dom] / (kern_ms[dom] * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic_bytes(dom + "_kernel") if regime == "init" else (None, None)
+    n_launch = ws.n_kernels + (1 if step.exchange is not None else 0)
+    out = {
+        "workload": workload_name(args, regime), "value": value, "unit": UNIT, "ms_per_step": ms_per_step,
+        "n_isects": I_mean, "isect_per_gaussian": I_mean / N, "keys_emitted": keys_sum / reps, "overflow": overflow,
+        "pipeline": ws.pipeline, "stopped_tiles": int(ws.status[5]),
+        "tile_sort": ("n/a" if ws.pipeline == "splat" else "lazy (only tiles near the transmittance stop threshold)" if model._use_lazy() else
+                      ("front-to-back depth slices, early stop" if model.front_sort else "every tile")),
+        "tile_culling": bool(model.cull_tiles), "morton_order": bool(args.morton),
+        "execution": f"CUDA graph replay per iteration (1 memset + {n_launch} kernels; stages: {', '.join(kernels)}"
+                     + (", exchange" if step.exchange is not None else "") + ")",
+        "exchange": step.exchange_name(),
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": stages[dom], "kernel_ms": kern_ms[dom]},
+        "roofline_step": {"algorithmic_bytes": A, "achieved": A / (ms_per_step * 1e-3) / 1e9,
+                          "frac": A / (ms_per_step * 1e-3) / 1e9 / peak, "formula": "228 N + 92 I + 20 P"},
+        "kernel_ms": kern_ms,
+        "e2e": {"value": world * n_e2e / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": n_e2e, "l2": "not flushed (back-to-back steps, as in training)",
+                "api": "GraphedRasterStep.set_view(pinned host) + replay + loss readback"},
+        "value_no_l2_flush": world * args.steps / (hot_ms * 1e-3),
+        "gpu_launches": n_launch * args.steps,
+        "clocks": clocks, "wall_s_timed_region": t_wall,
+    }
+    if parity is not None:
+        out["parity"] = parity
+        out["cpu_baseline"] = {"value": 1.0 / cpu_s, "unit": UNIT, "cores": cpu_cores, "kind": "port",
+                               "sample": f"1 full-size iteration ({N} Gaussians, {W}x{H}, regime={regime}) of the C/OpenMP oracle, "
+                                         f"{cpu_s:.2f} s, no sub-sampling; the same run is the parity check"}
+    if sum_check is not None:
+        out["exchange_sum_check"] = sum_check
+    return out
+
+
+def aux_timings(args, ctx):
+    """Optimizer step, regularisers and KNN at N Gaussians: this library's kernels next to the reference's own code
+    (torch.optim.Adam x 4 on the same GPU -- the reference's optimizer, utils/train_utils.py:48-65; the numpy ports of
+    compute_direction_loss / compute_ratio_loss pinned to the reference's outputs; sklearn NearestNeighbors exactly as
+    k_nearest_sklearn calls it, edge_gs.py:135-151).  SURVEY.md section 8d: reported separately from the step."""
+    import torch
+    from edgegaussians_b200 import synth
+    from edgegaussians_b200.edge_gs import EdgeGaussianSplatting
+    from edgegaussians_b200.knn import knn_indices
+    from edgegaussians_b200.optim import NAMES, FusedAdamGroup
+    from edgegaussians_b200.regularisers import _run as reg_run
+    dev, N = ctx["dev"], args.n
+    m, q, s, o = synth.make_gaussians(N, "trained", 0)
+    model = EdgeGaussianSplatting(device=dev)
+    model.set_params(m, s, q, o)
+    out = {"n": N}
+
+    def timed(fn, reps=10):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    # ---- Adam: one launch (eg_adam_multi) vs the reference's four torch.optim.Adam on the same GPU
+    for k in NAMES:
+        model.gauss_params[k].grad = torch.randn_like(model.gauss_params[k]) * 1e-3
+    group = FusedAdamGroup(model, {k: 1e-3 for k in NAMES})
+    out["adam_ms"] = timed(lambda: group.step(zero_grad=False))
+    ref_params = [torch.nn.Parameter(model.gauss_params[k].detach().clone()) for k in NAMES]
+    for p in ref_params:
+        p.grad = torch.randn_like(p) * 1e-3
+    opts = [torch.optim.Adam([p], lr=1e-3) for p in ref_params]
+
+    def torch_adam():
+        for op in opts:
+            op.step()
+    out["adam_ms_reference_torch_x4_gpu"] = timed(torch_adam)
+    # ---- KNN (k = 5 as configs/DTU.json:72)
+    k = 5
+    pts = model.means.data
+    out["knn_ms"] = timed(lambda: knn_indices(pts, k), reps=3)
+    nn_idx = knn_indices(pts, k)
+    # ---- regularisers fwd + bwd in one pass
+    out["reg_fwd_bwd_ms"] = timed(lambda: reg_run(model.means.data, model.quats.data, model.scales.data, nn_idx, k, False, 1.0, 1.0))
+    if not args.no_cpu_baseline:
+        from oracle import reference_ports as ports
+        try:
+            from sklearn.neighbors import NearestNeighbors
+            t0 = time.perf_counter()
+            nn_model = NearestNeighbors(n_neighbors=k + 2, algorithm="auto", metric="euclidean").fit(m)
+            _, ind = nn_model.kneighbors(m)
+            out["knn_s_reference_sklearn_cpu"] = time.perf_counter() - t0
+            ref_idx = ind[:, 2:]
+            out["knn_mismatch_rows_vs_sklearn"] = int((nn_idx.cpu().numpy() != ref_idx).any(axis=1).sum())
+        except Exception as e:  # sklearn missing on the box: the timing is informational
+            out["knn_s_reference_sklearn_cpu"] = f"unavailable: {e}"
+            ref_idx = nn_idx.cpu().numpy()
+        t0 = time.perf_counter()
+        ports.direction_loss(m, q, s, ref_idx, k)
+        ports.ratio_loss(s)
+        out["reg_fwd_bwd_s_reference_port_cpu"] = time.perf_counter() - t0
+        out["cpu_cores"] = os.cpu_count()
+    return out
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
+    ctx = {"world": world, "rank": rank, "local": local, "dev": dev,
+           "flush_buf": None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev),
+           "copy_stream": torch.cuda.Stream()}
+    regimes = ["init", "trained"] if args.regime == "both" else [args.regime]
+    results = {}
+    for regime in regimes:
+        results[regime] = bench_regime(args, regime, ctx)
+        torch.cuda.synchronize()
+    aux = None
+    if rank == 0 and world == 1 and not args.no_aux:
+        try:
+            aux = aux_timings(args, ctx)
+        except Exception as e:   # informational block: never takes the headline down
+            aux = {"failed": repr(e)}
     if rank == 0:
-        peak, peak_src = load_peaks()
-        stages, A = algorithmic_bytes(N, I_mean, P)
-        ms_per_step = total_ms / args.steps
-        value = world * args.steps / (total_ms * 1e-3)
-        kernels = [k for k in names if k != "memset"]
-        dom = max(kernels, key=lambda k: kern_ms[k])
-        achieved = stages[dom] / (kern_ms[dom] * 1e-3) / 1e9
+        head = results[regimes[0]]
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic (synth-v1: uniform Gaussians in [-1,1]^3, Fibonacci-sphere cameras, random-segment edge maps)",
-            "config": {"workload": workload_name(args), "views_cycled_per_gpu": V,
-                       "n_isects": I_mean, "isect_per_gaussian": I_mean / N, "overflow": overflow,
-                       "l2": "flushed between timed iterations (256 MiB fill)" if flush_buf is not None else "not flushed",
-                       "pipeline": ws.pipeline + {"splat": " (Gaussian-major forward + backward; tiles near the transmittance stop threshold redone sorted)",
-                                                  "tiles+splat": " (tile binning + per-tile sort/compositing, Gaussian-major backward)",
-                                                  "tiles": " (tile binning + per-tile sort/compositing, tile-major backward)"}[ws.pipeline],
-                       "stopped_tiles": int(ws.status[5]),
-                       "tile_sort": ("n/a" if ws.pipeline == "splat" else "lazy (only tiles near the transmittance stop threshold)" if model._use_lazy() else "every tile"),
-                       "execution": f"CUDA graph replay per iteration (1 memset + {ws.n_kernels} kernels; stages: {', '.join(kernels)})" + ((", + NCCL all-reduce of the 11N fp32 gradient buffer " + (f"in {step.allreduce_chunks} Gaussian ranges on a side stream, overlapped with the backward of the next range" if step.chunked else ("issued on the compute stream after the replay (libedgegs communicator)" if step.native_comm is not None else "issued after the replay (torch.distributed)"))) if world > 1 else ""),
+            "config": {"workload": head["workload"], "views_cycled_per_gpu": args.views,
+                       "n_isects": head["n_isects"], "isect_per_gaussian": head["isect_per_gaussian"], "overflow": head["overflow"],
+                       "l2": "flushed between timed iterations (256 MiB fill)" if ctx["flush_buf"] is not None else "not flushed",
+                       "pipeline": head["pipeline"], "stopped_tiles": head["stopped_tiles"], "tile_sort": head["tile_sort"],
+                       "execution": head["execution"], "exchange": head["exchange"],
                        "parallelism": f"view-sharded dp{world}" if world > 1 else "single GPU"},
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": ncu_traffic_bytes(dom + "_kernel"), "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": stages[dom], "kernel_ms": kern_ms[dom]},
-            "roofline_step": {"algorithmic_bytes": A, "achieved": A / (ms_per_step * 1e-3) / 1e9,
-                              "frac": A / (ms_per_step * 1e-3) / 1e9 / peak, "formula": "228 N + 92 I + 20 P"},
-            "kernel_ms": kern_ms,
-            "e2e": {"value": world * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "api": "GraphedRasterStep.set_view(pinned host) + replay + loss readback"},
-            "value_no_l2_flush": world * args.steps / (hot_ms * 1e-3),
-            "gpu_launches": ws.n_kernels * args.steps,
-            "clocks": clocks,
-            "wall_s_timed_region": t_wall,
+            "roofline": head["roofline"], "roofline_step": head["roofline_step"], "kernel_ms": head["kernel_ms"],
+            "e2e": head["e2e"], "value_no_l2_flush": head["value_no_l2_flush"], "gpu_launches": head["gpu_launches"],
+            "clocks": head["clocks"], "wall_s_timed_region": head["wall_s_timed_region"],
         }
-        if not args.no_cpu_baseline and world == 1:
-            try:
-                t_probe, cores = cpu_step_time(args, min(N, 50_000), 1)
-                est = t_probe[0] * N / min(N, 50_000)
-                n_s = max(1000, int(N * min(1.0, args.cpu_budget_s / max(2 * est, 1e-9))))
-                ts, cores = cpu_step_time(args, n_s, 2)
-                t_cpu = min(ts) * N / n_s
-                line["cpu_baseline"] = {"value": 1.0 / t_cpu, "unit": UNIT, "cores": cores, "kind": "port",
-                                        "sample": f"{n_s} of {N} Gaussians at full resolution, best of 2, time scaled linearly in N"}
-            except Exception as e:  # the oracle is only a reported baseline
-                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": f"failed: {e}"}
+        for k in ("parity", "cpu_baseline", "exchange_sum_check"):
+            if k in head:
+                line[k] = head[k]
+        line["regimes"] = {r: {k: v for k, v in res.items() if k not in ("clocks",)} for r, res in results.items()}
+        if aux is not None:
+            line["aux_ms"] = aux
         print(json.dumps(line), flush=True)
+        bad = [r for r, res in results.items() if ("parity" in res and not res["parity"]["ok"])
+               or ("exchange_sum_check" in res and not res["exchange_sum_check"]["ok"])]
+        if bad:
+            sys.stderr.write(f"bench.py: PARITY VIOLATION in regime(s) {bad}: the numbers above are invalid\n")
+            if world > 1:
+                dist.destroy_process_group()
+            sys.exit(3)
     if world > 1:
         dist.destroy_process_group()
 

@@ -24,7 +24,7 @@ EG_FLAG_FRONT_SORT = 16
 EXPORTS = ["eg_last_error", "eg_abi_version", "eg_tile_grid", "eg_project_fwd", "eg_bin", "eg_raster_fwd",
            "eg_raster_bwd", "eg_project_bwd", "eg_splat_bwd", "eg_make_seed", "eg_splat_fwd", "eg_splat_resolve", "eg_emit_flagged",
            "eg_comm_unique_id", "eg_comm_init", "eg_comm_destroy", "eg_comm_allreduce", "eg_allreduce_symm", "eg_allreduce_flag_words",
-           "eg_grad_layout", "eg_tile_capacity_for", "eg_workspace_sizes_for", "eg_workspace_bytes", "eg_reg_fwd_bwd", "eg_knn_workspace_bytes", "eg_knn", "eg_adam_step",
+           "eg_grad_layout", "eg_adam_multi", "eg_gather_rows", "eg_tile_capacity_for", "eg_workspace_sizes_for", "eg_workspace_bytes", "eg_reg_fwd_bwd", "eg_knn_workspace_bytes", "eg_knn", "eg_adam_step",
            "eg_projecting_fraction"]
 
 
@@ -43,6 +43,16 @@ class EgWorkspaceSizes(Structure):
 
 
 EG_PIPE = {"splat": 0, "tiles+splat": 1, "tiles": 2}
+
+
+class EgAdamSegment(Structure):
+    _fields_ = [("param", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p), ("grad_offset", c_int64),
+                ("count", c_int64)]
+
+
+class EgRowArray(Structure):
+    _fields_ = [("src", c_void_p), ("dst", c_void_p), ("width", c_int32), ("zero_from_row", c_int64)]
+
 
 _lib = None
 
@@ -91,6 +101,8 @@ def load(build_if_missing: bool = True):
     lib.eg_knn.argtypes = [c_int, P, c_int, c_int, P, P, ctypes.c_size_t, P]
     lib.eg_projecting_fraction.argtypes = [c_int, P, c_int, P, P, P, P, P, P, P]
     lib.eg_adam_step.argtypes = [c_int64, P, P, P, P] + [c_double] * 6 + [c_int, P]
+    lib.eg_adam_multi.argtypes = [c_int, POINTER(EgAdamSegment), P, P, c_double, c_double, c_double, c_int, P, P]
+    lib.eg_gather_rows.argtypes = [c_int64, P, c_int, POINTER(EgRowArray), P]
     for name in EXPORTS[2:]:
         getattr(lib, name).restype = c_int
     lib.eg_knn_workspace_bytes.restype = ctypes.c_size_t

@@ -308,15 +308,87 @@ class EdgeGaussianSplatting(torch.nn.Module):
     # Mirrors of edge_gs.py:384-488, 544-576.  Everything stays on the parameters' device (the reference detours
     # through numpy for the threshold); `optimizers` is the reference's dict name -> single-parameter Adam
     # (utils/train_utils.py:48-65).  Resizing N invalidates the fused step's workspace and graphs (rebuilt on use).
-    def _resize_optimizer(self, optimizer, new_param, resize):
-        """Re-key the optimizer to ``new_param``; ``resize`` maps each per-element state tensor to its new rows."""
-        old = optimizer.param_groups[0]["params"][0]
-        state = optimizer.state.pop(old, {})
-        for key in ("exp_avg", "exp_avg_sq"):
-            if key in state:
-                state[key] = resize(state[key])
-        optimizer.param_groups[0]["params"] = [new_param]
-        optimizer.state[new_param] = state
+    def _optimizer_moments(self, optimizers, name):
+        """(exp_avg, exp_avg_sq) of the parameter's optimizer, or None when it has not stepped yet."""
+        from .optim import FusedAdamGroup
+        if optimizers is None:
+            return None
+        if isinstance(optimizers, FusedAdamGroup):
+            return optimizers.moments[name]
+        opt = optimizers[name]
+        st = opt.state.get(opt.param_groups[0]["params"][0], {})
+        return (st["exp_avg"], st["exp_avg_sq"]) if "exp_avg" in st else None
+
+    def _install_resized(self, optimizers, new_params, new_moments):
+        """Re-key the optimizers to the resized parameters (edge_gs.py:395-411, 431-452)."""
+        from .optim import FusedAdamGroup
+        old = {name: self.gauss_params[name] for name in new_params}
+        for name, p in new_params.items():
+            self.gauss_params[name] = torch.nn.Parameter(p)
+        if optimizers is None:
+            return
+        if isinstance(optimizers, FusedAdamGroup):
+            optimizers.resize({k: new_moments[k] for k in new_params})
+            return
+        for name in new_params:
+            opt = optimizers[name]
+            state = opt.state.pop(old[name], {})
+            if new_moments.get(name) is not None:
+                state["exp_avg"], state["exp_avg_sq"] = new_moments[name]
+            opt.param_groups[0]["params"] = [self.gauss_params[name]]
+            opt.state[self.gauss_params[name]] = state
+
+    def _resize_rows(self, optimizers, idx: torch.Tensor, zero_moments_from: int, move_absgrads: bool):
+        """new[r] = old[idx[r]] for the four parameter tensors, both Adam moments of each (zero for rows
+        >= zero_moments_from: freshly duplicated Gaussians start with empty moments, edge_gs.py:441-449) and,
+        for a cull, the abs-grad statistic.  On a CUDA model all (up to 13) arrays move in ONE kernel
+        (eg_gather_rows); a model whose tensors the caller keeps on the CPU is resized with torch indexing."""
+        names = ["means", "scales", "quats", "opacities"]
+        n_out = int(idx.numel())
+        dev = self.means.device
+        moments = {k: self._optimizer_moments(optimizers, k) for k in names}
+        new_params, new_moments = {}, {}
+        if dev.type != "cuda":
+            idx = idx.to(dev)
+            for k in names:
+                new_params[k] = self.gauss_params[k].data[idx]
+                if moments[k] is not None:
+                    mv = []
+                    for t in moments[k]:
+                        r = t[idx]
+                        r[zero_moments_from:] = 0
+                        mv.append(r)
+                    new_moments[k] = tuple(mv)
+                else:
+                    new_moments[k] = None
+            new_abs = self.absgrads[idx] if move_absgrads else None
+        else:
+            lib = get_engine(dev).lib
+            idx32 = idx.to(device=dev, dtype=torch.int32).contiguous()
+            arrays = []
+            for k in names:
+                src = self.gauss_params[k].data.contiguous()
+                w = src.shape[1]
+                new_params[k] = torch.empty((n_out, w), dtype=torch.float32, device=dev)
+                arrays.append((src, new_params[k], w, -1))
+                if moments[k] is not None:
+                    mv = tuple(torch.empty((n_out, w), dtype=torch.float32, device=dev) for _ in range(2))
+                    for t, d in zip(moments[k], mv):
+                        arrays.append((t.contiguous(), d, w, zero_moments_from))
+                    new_moments[k] = mv
+                else:
+                    new_moments[k] = None
+            new_abs = None
+            if move_absgrads:
+                new_abs = torch.empty(n_out, dtype=torch.float32, device=dev)
+                arrays.append((self.absgrads.contiguous(), new_abs, 1, -1))
+            arr = (_lib.EgRowArray * len(arrays))()
+            for i, (src, dst, w, zf) in enumerate(arrays):
+                arr[i] = _lib.EgRowArray(src.data_ptr(), dst.data_ptr(), w, zf)
+            _lib.check(lib.eg_gather_rows(n_out, _p(idx32), len(arrays), arr, _stream()), "eg_gather_rows")
+        self._install_resized(optimizers, new_params, new_moments)
+        if new_abs is not None:
+            self.absgrads = new_abs
 
     def _after_resize(self):
         self._ws = None
@@ -332,32 +404,44 @@ class EdgeGaussianSplatting(torch.nn.Module):
         self.opacities.data = torch.clamp(self.opacities.data, max=self.config.reset_opacity_value)
 
     def cull_gaussians(self, optimizers, cull_mask, reset_rest=True):  # edge_gs.py:413-423
-        keep = ~cull_mask.to(self.means.device)
-        for name in list(self.gauss_params.keys()):
-            self.gauss_params[name] = torch.nn.Parameter(self.gauss_params[name].data[keep])
+        keep = ~cull_mask.to(self.means.device).reshape(-1)
+        idx = torch.nonzero(keep).reshape(-1)
+        self._resize_rows(optimizers, idx, zero_moments_from=int(idx.numel()), move_absgrads=True)
         if reset_rest:
             self.reset_opacities()
-        for name, params in self.get_gaussian_param_groups().items():
-            self._resize_optimizer(optimizers[name], params[0], lambda t: t[keep])
-        self.absgrads = self.absgrads[keep]
         self._after_resize()
         return int(cull_mask.sum())
 
     def dup_gaussians(self, optimizers, dup_mask):  # edge_gs.py:460-474
         mask = torch.as_tensor(dup_mask).to(self.means.device).reshape(-1)
         copies = self.config.dup_factor - 1
-        for name in list(self.gauss_params.keys()):
-            p = self.gauss_params[name].data
-            extra = torch.cat([p[mask]] * copies, dim=0) if copies > 0 else p[:0]
-            if name == "means":  # the copies are jittered; one randn_like over all of them, as in the reference
-                extra = extra + torch.randn_like(extra) * self.config.init_dup_rand_noise_scale
-            self.gauss_params[name] = torch.nn.Parameter(torch.cat([p, extra], dim=0))
-        n_new = copies * int(mask.sum())
-        for name, params in self.get_gaussian_param_groups().items():
-            self._resize_optimizer(optimizers[name], params[0],
-                                   lambda t: torch.cat([t, t.new_zeros((n_new,) + tuple(t.shape[1:]))], dim=0))
+        n_old = self.num_points
+        picked = torch.nonzero(mask).reshape(-1)
+        idx = torch.cat([torch.arange(n_old, device=picked.device)] + [picked] * copies)
+        self._resize_rows(optimizers, idx, zero_moments_from=n_old, move_absgrads=False)
+        if idx.numel() > n_old:  # the copies are jittered; one randn_like over all of them, as in the reference
+            extra = self.means.data[n_old:]
+            extra += torch.randn_like(extra) * self.config.init_dup_rand_noise_scale
         self._after_resize()
         return int(mask.sum())
+
+    def sort_gaussians_morton(self, optimizers=None, bits: int = 10) -> torch.Tensor:
+        """Re-order the Gaussians along a 3D Morton (Z-order) curve of their means -- parameters, Adam moments and
+        the abs-grad statistic move together (one eg_gather_rows launch).  No reference counterpart (the reference
+        keeps creation order); the order of the Gaussians has no effect on any result of the path.  Worth doing
+        once after every densification: a warp of the Gaussian-major kernels then owns 32 spatial neighbours, whose
+        footprints share cache lines and have similar sizes.  Returns the permutation (new[r] = old[perm[r]])."""
+        x = self.means.data
+        lo, hi = x.amin(0), x.amax(0)
+        q = ((x - lo) / (hi - lo).clamp_min(1e-12) * (2 ** bits - 1)).long().clamp_(0, 2 ** bits - 1)
+        code = torch.zeros(x.shape[0], dtype=torch.long, device=x.device)
+        for b in range(bits):
+            for a in range(3):
+                code |= ((q[:, a] >> b) & 1) << (3 * b + a)
+        perm = torch.argsort(code, stable=True)
+        self._resize_rows(optimizers, perm, zero_moments_from=int(perm.numel()), move_absgrads=True)
+        self._after_resize()
+        return perm
 
     def duplicate_all_existing_gaussians(self, optimizers):  # edge_gs.py:491-496
         return self.dup_gaussians(optimizers, torch.ones(self.num_points, dtype=torch.bool))
@@ -463,7 +547,8 @@ class EdgeGaussianSplatting(torch.nn.Module):
             w_b = float(torch.tensor(n_edge, dtype=torch.int64) / torch.tensor(P, dtype=torch.int64))
             return (w_e, w_b, 0.0, thr), 0, 1.0 / float(P)
         if strategy == "bg_edge_ratio":  # MaskedL1 over the edge pixels + MaskedL1 over the sampled pixels
-            n_sel = min(int(bg_edge_pixel_ratio * n_edge), n_bg)
+            # int(ratio * mask.sum()) with the reference's tensor arithmetic (edge_gs.py:302), then randperm(n_bg)[:num]
+            n_sel = min(int(bg_edge_pixel_ratio * torch.tensor(n_edge)), n_bg)
             w_e = 1.0 / n_edge if n_edge > 0 else float("nan")   # mean over an empty selection is nan in the reference
             w_s = 1.0 / n_sel if n_sel > 0 else float("nan")
             return (w_e, 0.0, w_s, thr), n_sel, 1.0

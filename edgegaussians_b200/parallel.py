@@ -168,9 +168,14 @@ class ViewShardedStep:
         model = self.model
         before = model.absgrads.clone()
         if view is None:
+            # idle rank of a ragged last step: zero gradients, but the same bookkeeping as the working ranks -- the
+            # abs-grad normaliser and the step counter feed the densification thresholds (edge_gs.py:544-576), which
+            # every rank must evaluate identically
             ws = model._ws
             ws.grads.zero_()
             loss = torch.zeros((), device=ws.grads.device)
+            model.absgrads_normalize_factor += 1
+            model.step += 1
         else:
             loss = model.raster_step(view, self.gts[view], loss_weight=loss_weight)
         ws = model._ws
@@ -180,3 +185,16 @@ class ViewShardedStep:
         if self.world > 1:
             dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=self.group)
         return loss
+
+
+def broadcast_parameters(model, group=None, src: int = 0) -> None:
+    """Make every rank's replica identical to rank ``src``'s after a step that draws random numbers per rank
+    (the jitter of duplicated Gaussians, edge_gs.py:466): parameters and abs-grad statistic.  Call it after
+    densification in a view-sharded run (the masks themselves are computed from all-reduced statistics and are
+    already identical)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    src_g = dist.get_global_rank(group, src) if group is not None else src
+    for p in model.gauss_params.values():
+        dist.broadcast(p.data, src=src_g, group=group)
+    dist.broadcast(model.absgrads, src=src_g, group=group)

@@ -314,6 +314,34 @@ int eg_adam_step(int64_t n, float *param, float *grad, float *exp_avg, float *ex
                  double beta1, double beta2, double eps, double bias_correction1, double bias_correction2,
                  int zero_grad, void *stream);
 
+/* a13 / section 8f-3: the reference's four Adams as ONE launch over the fused step's flat gradient buffer.
+ * segs [n_segs <= 8] (HOST structs): parameter tensor, its torch-layout moment tensors, where its gradients start in
+ * `grads` (eg_grad_layout) and its element count.  hyper [n_segs] (DEVICE, 24 bytes each: f64 lr | i64 completed
+ * steps | i64 enabled): what changes between steps lives on the device, so the launch can sit in a captured CUDA
+ * graph while schedulers rewrite the learning rates (train_utils.py:15-37) and the regulariser steps disable the
+ * opacity segment (train_gaussians.py:118-121); the kernel advances the step counts of the enabled segments itself.
+ * ticket: one zero-initialised u32 of device scratch.  zero_grad != 0 also clears the consumed gradients.
+ * Same arithmetic as eg_adam_step / torch.optim.Adam (bias corrections formed in double). */
+typedef struct eg_adam_segment {
+    float *param, *exp_avg, *exp_avg_sq;
+    int64_t grad_offset, count;
+} eg_adam_segment;
+int eg_adam_multi(int n_segs, const eg_adam_segment *segs, float *grads, void *hyper, double beta1, double beta2,
+                  double eps, int zero_grad, uint32_t *ticket, void *stream);
+
+/* Section 8f-3: densify / cull compaction as one kernel.  For every array a (at most 16; HOST structs):
+ *   dst[a][r, 0:width] = r < zero_from_row ? src[a][idx[r], 0:width] : 0      for r in [0, n_out)
+ * (zero_from_row < 0: never zero).  idx [n_out] i32 on the device.  A cull passes the surviving row ids; a
+ * duplication passes the old ids followed by the duplicated ones with zero_from_row = old N for the Adam moments
+ * (edge_gs.py:384-475: parameters, exp_avg, exp_avg_sq and the abs-grad statistic move together). */
+typedef struct eg_row_array {
+    const float *src;
+    float *dst;
+    int32_t width;
+    int64_t zero_from_row;
+} eg_row_array;
+int eg_gather_rows(int64_t n_out, const int32_t *idx, int n_arrays, const eg_row_array *arrays, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,3 +80,29 @@ def test_cameras_mirror_reference_golden(golden_dir):
     np.testing.assert_allclose(cam.get_viewmat()[0, :3, 3].numpy(), [0.1, 0.2, 0.3], atol=1e-7)
     cam.scale_translation(2.0)
     np.testing.assert_allclose(cam.get_viewmat()[0, :3, 3].numpy(), [0.2, 0.4, 0.6], atol=1e-7)
+
+
+def test_sizing_helpers_without_gpu():
+    """eg_grad_layout / eg_tile_capacity_for / eg_workspace_sizes_for: host arithmetic a
+    non-Python caller sizes its buffers with; the Python layer uses the same functions."""
+    from edgegaussians_b200 import _lib
+    from edgegaussians_b200.layout import grad_layout
+    lib = _lib.load()
+    offs = (ctypes.c_int64 * 5)()
+    for n in (0, 1, 3, 4, 1001, 500_000):
+        assert lib.eg_grad_layout(n, offs) == 0
+        assert tuple(offs) == grad_layout(n)
+        assert all(o % 4 == 0 for o in offs) and offs[4] >= 11 * n
+    assert lib.eg_tile_capacity_for(3_000_000, 7500, 0) == 1600 and lib.eg_tile_capacity_for(0, 7500, 0) == 256
+    assert lib.eg_tile_capacity_for(0, 7500, 1000) == 1280
+    cfg = _lib.EgConfig(n=500_000, width=1600, height=1200, tile_size=16, isect_capacity=3_000_000)
+    s = _lib.EgWorkspaceSizes()
+    for name, pipe in _lib.EG_PIPE.items():
+        assert lib.eg_workspace_sizes_for(ctypes.byref(cfg), pipe, 0, ctypes.byref(s)) == 0
+        assert s.rec == 500_000 * 32 and s.grads == grad_layout(500_000)[4] * 4 and s.wpix == 1600 * 1200 * 4
+        assert s.tile_capacity == 1600 and not s.compact_keys
+        assert s.total == lib.eg_workspace_bytes(ctypes.byref(cfg), pipe) > 0
+        assert (s.logT > 0) == (name == "splat") and (s.cmask > 0) == (name == "tiles")
+    cfg.tile_size = 8
+    assert lib.eg_workspace_sizes_for(ctypes.byref(cfg), 0, 0, ctypes.byref(s)) != 0
+    assert lib.eg_allreduce_flag_words(64) == 64 * 16

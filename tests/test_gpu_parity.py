@@ -147,14 +147,26 @@ def test_backward_parity(case, impl, monkeypatch):
 PIPELINES = ["splat", "tiles+splat", "tiles"]
 
 
+def _fused_check(name, model, ref, it=0, absgrads=True):
+    _check_grad(name, "v_means", model.means.grad.cpu().numpy(), ref["v_means"])
+    _check_grad(name, "v_quats", model.quats.grad.cpu().numpy(), ref["v_quats"], 1e-6 * np.abs(ref["v_means"]).max())
+    _check_grad(name, "v_log_scales", model.scales.grad.cpu().numpy(), ref["v_log_scales"])
+    _check_grad(name, "v_logit_opacities", model.opacities.grad.cpu().numpy()[:, 0], ref["v_logit_opacities"])
+    if absgrads:
+        _check_grad(name, "absgrads", model.absgrads.cpu().numpy(), (it + 1) * ref["absgrad_norm"])
+
+
 @pytest.mark.parametrize("pipeline", PIPELINES)
 @pytest.mark.parametrize("gt_dtype", ["f32", "u8"])
-@pytest.mark.parametrize("case", CASES[:5], ids=[c[0] for c in CASES[:5]])
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_fused_raster_step_parity(case, gt_dtype, pipeline):
     """raster_step == reference iteration (train_gaussians.py:81-102 with the "whole" L1 loss), for each of the
     three fused pipelines (Gaussian-major with its exact stop-rule fallback, tile forward + Gaussian-major
-    backward, all tile-major)."""
+    backward, all tile-major), with the fused step's default list handling (footprint culling of the tile lists,
+    depth-sliced front-to-back sort with early stop)."""
     name, N, W, H, regime, seed, bs, view = case
+    if name == "long-lists" and gt_dtype == "u8":
+        pytest.skip("one gt dtype is enough for the long-list stress case")
     m, q, s, o, sc, op, vm, K = _inputs(N, W, H, regime, seed, bs, view)
     gt_u8 = synth.make_edge_map_u8(W, H, seed)
     gt_f = (gt_u8.astype(np.float32) / np.float32(255.0)) if gt_dtype == "u8" else synth.make_edge_map(W, H, seed)
@@ -163,30 +175,119 @@ def test_fused_raster_step_parity(case, gt_dtype, pipeline):
     cam = OpenCVCamera.from_matrices(H, W, K, vm).to(DEV)
     model.set_params(m, s, q, o, viewcams=[cam])
     model.pipeline = pipeline
+    assert model.cull_tiles and model.front_sort
     gt = _t(gt_u8) if gt_dtype == "u8" else _t(gt_f)
     for it in range(2):  # second call reuses the workspace and must give the same gradients
         loss = model.raster_step(0, gt)
         assert model._ws.pipeline == pipeline
-        print(f"[{name}/{pipeline}] stopped tiles {int(model._ws.status[5])} / {model._ws.T}")
+        hs = model._ws.status.cpu()
+        print(f"[{name}/{pipeline}] stopped tiles {int(hs[5])} / {model._ws.T}, n_isects {int(hs[0])}, keys emitted {int(hs[6])}")
+        assert int(hs[0]) == ref["state"]["n_isects"]          # gsplat's count, whatever the lists hold
+        if pipeline != "splat":
+            assert 0 < int(hs[6]) <= int(hs[0])                  # culled lists are a subset
         assert abs(float(loss) - ref["loss"]) <= 2e-6 + 1e-5 * abs(ref["loss"]), (float(loss), ref["loss"])
-        _check_grad(name, "v_means", model.means.grad.cpu().numpy(), ref["v_means"])
-        _check_grad(name, "v_quats", model.quats.grad.cpu().numpy(), ref["v_quats"], 1e-6 * np.abs(ref["v_means"]).max())
-        _check_grad(name, "v_log_scales", model.scales.grad.cpu().numpy(), ref["v_log_scales"])
-        _check_grad(name, "v_logit_opacities", model.opacities.grad.cpu().numpy()[:, 0], ref["v_logit_opacities"])
-        _check_grad(name, "absgrads", model.absgrads.cpu().numpy(), (it + 1) * ref["absgrad_norm"])
+        _fused_check(name, model, ref, it)
     assert model.absgrads_normalize_factor == 3
 
 
+@pytest.mark.parametrize("pipeline", ["tiles+splat", "tiles"])
+@pytest.mark.parametrize("flags", [(False, False), (True, False), (False, True)], ids=["plain", "cull", "front"])
+@pytest.mark.parametrize("case", [CASES[2], CASES[4], CASES[5]], ids=[CASES[2][0], CASES[4][0], CASES[5][0]])
+def test_fused_step_list_options(case, flags, pipeline):
+    """The tile pipelines with footprint culling (EG_FLAG_CULL_TILES) and the depth-sliced front-to-back sort
+    (EG_FLAG_FRONT_SORT) switched on one at a time / both off: every combination is gsplat's result."""
+    name, N, W, H, regime, seed, bs, view = case
+    m, q, s, o, sc, op, vm, K = _inputs(N, W, H, regime, seed, bs, view)
+    gt_f = synth.make_edge_map(W, H, seed)
+    ref = oracle.edge_step(m, q, s, o, vm, K, W, H, gt_f, loss_scale=1.0)
+    model = EdgeGaussianSplatting(device=DEV)
+    model.set_params(m, s, q, o, viewcams=[OpenCVCamera.from_matrices(H, W, K, vm).to(DEV)])
+    model.pipeline = pipeline
+    model.cull_tiles, model.front_sort = flags
+    model.lazy_sort = False
+    loss = model.raster_step(0, _t(gt_f))
+    hs = model._ws.status.cpu()
+    assert int(hs[0]) == ref["state"]["n_isects"]
+    if not flags[0]:
+        assert int(hs[6]) == int(hs[0])                          # no culling: the lists are gsplat's
+    assert abs(float(loss) - ref["loss"]) <= 2e-6 + 1e-5 * abs(ref["loss"]), (float(loss), ref["loss"])
+    _fused_check(name, model, ref)
+
+
+@pytest.mark.parametrize("pipeline", PIPELINES)
+@pytest.mark.parametrize("N", [1, 7, 1001])
+def test_odd_gaussian_counts(N, pipeline):
+    """N not a multiple of 4 (any N after a cull or a duplication): the flat gradient buffer pads every segment to
+    16 bytes (eg_grad_layout), so the 128-bit quaternion-gradient stores stay aligned; fused and autograd paths."""
+    W, H = 160, 128
+    m, q, s, o = synth.make_gaussians(N, "trained", 11, base_scale=0.02)
+    m = (0.3 * m).astype(np.float32)
+    vms, Ks = synth.make_cameras(3, W, H)
+    vm, K = vms[1], Ks[1]
+    gt_f = synth.make_edge_map(W, H, 2)
+    ref = oracle.edge_step(m, q, s, o, vm, K, W, H, gt_f)
+    model = EdgeGaussianSplatting(device=DEV)
+    model.set_params(m, s, q, o, viewcams=[OpenCVCamera.from_matrices(H, W, K, vm).to(DEV)])
+    model.pipeline = pipeline
+    loss = model.raster_step(0, _t(gt_f))
+    torch.cuda.synchronize()
+    assert abs(float(loss) - ref["loss"]) <= 2e-6 + 1e-5 * abs(ref["loss"])
+    assert model.quats.grad.data_ptr() % 16 == 0
+    _fused_check(f"odd-{N}", model, ref)
+    if pipeline == "splat":   # the gsplat-shaped autograd op allocates its own (padded) gradient buffer
+        a = EdgeGaussianSplatting(device=DEV)
+        a.set_params(m, s, q, o, viewcams=[OpenCVCamera.from_matrices(H, W, K, vm).to(DEV)])
+        a.train()
+        la = a.compute_projection_loss(a(0)["rgb"][:, :, 0], _t(gt_f), strategy="whole")
+        la.backward()
+        torch.cuda.synchronize()
+        _check_grad(f"odd-{N}", "autograd v_quats", a.quats.grad.cpu().numpy(), ref["v_quats"], 1e-6 * np.abs(ref["v_means"]).max())
+        _check_grad(f"odd-{N}", "autograd v_means", a.means.grad.cpu().numpy(), ref["v_means"])
+
+
+#            name                       N        W     H     regime    (BASELINE.json configs 3, 4, 5 and the headline)
+BASELINE_SHAPES = [("cfg3-dtu-200k", 200_000, 1600, 1200, "init"),
+                   ("cfg4-replica-500k", 500_000, 1200, 680, "init"),
+                   ("cfg5-sweep-1M", 1_000_000, 1920, 1080, "init"),
+                   ("headline-500k-init", 500_000, 1600, 1200, "init"),
+                   ("headline-500k-trained", 500_000, 1600, 1200, "trained"),
+                   ("cfg3-dtu-200k-trained", 200_000, 1600, 1200, "trained")]
+
+
+@pytest.mark.parametrize("shape", BASELINE_SHAPES, ids=[c[0] for c in BASELINE_SHAPES])
+def test_baseline_config_shapes(shape):
+    """Parity where the numbers are claimed: the fused step (auto pipeline, as training and bench.py run it)
+    against the CPU oracle at the sizes of BASELINE.json's configs 3-5 and of the headline, uint8 edge map."""
+    name, N, W, H, regime = shape
+    m, q, s, o = synth.make_gaussians(N, regime, 0)
+    vms, Ks = synth.make_cameras(8, W, H)
+    vm, K = vms[3], Ks[3]
+    gt_u8 = synth.make_edge_map_u8(W, H, 3)
+    ref = oracle.edge_step(m, q, s, o, vm, K, W, H, gt_u8.astype(np.float32) / np.float32(255.0))
+    model = EdgeGaussianSplatting(device=DEV)
+    model.set_params(m, s, q, o, viewcams=[OpenCVCamera.from_matrices(H, W, K, vm).to(DEV)])
+    gt = _t(gt_u8)
+    loss = model.raster_step(0, gt)
+    if model.current_pipeline() != model._ws.pipeline:   # the auto policy moved after the first step: run what it chose
+        model.reset_absgrads()
+        loss = model.raster_step(0, gt)
+    hs = model._ws.status.cpu()
+    print(f"[{name}] pipeline {model._ws.pipeline}, n_isects {int(hs[0])} (I/N {int(hs[0]) / N:.2f}), keys {int(hs[6])}, "
+          f"stopped tiles {int(hs[5])} / {model._ws.T}")
+    assert int(hs[0]) == ref["state"]["n_isects"]
+    assert abs(float(loss) - ref["loss"]) <= 2e-6 + 1e-5 * abs(ref["loss"]), (float(loss), ref["loss"])
+    _fused_check(name, model, ref)
+
+
 def test_backward_in_gaussian_ranges_matches_single_launch():
-    """eg_splat_bwd over [0,N) in three Gaussian ranges (what the chunked multi-GPU all-reduce launches) writes
-    exactly the gradients of the single launch: every Gaussian has one owner, no atomics are involved."""
+    """eg_splat_bwd over [0,N) in three Gaussian ranges writes exactly the gradients of the single launch: every
+    Gaussian has one owner, no atomics are involved."""
     name, N, W, H, regime, seed, bs, view = CASES[1]
     m, q, s, o, sc, op, vm, K = _inputs(N, W, H, regime, seed, bs, view)
     model = EdgeGaussianSplatting(device=DEV)
     cam = OpenCVCamera.from_matrices(H, W, K, vm).to(DEV)
     model.set_params(m, s, q, o, viewcams=[cam])
     gt = _t(synth.make_edge_map_u8(W, H, seed))
-    from edgegaussians_b200 import parallel
     # one forward (its float reductions are order-dependent in the last bit), then both backward forms on its seed
     ws = model.enqueue_raster_step(cam.viewmat.reshape(4, 4), cam.K.reshape(3, 3), W, H, gt, accumulate_absgrad=False,
                                    parts="forward")
@@ -194,7 +295,8 @@ def test_backward_in_gaussian_ranges_matches_single_launch():
     full = ws.grads.clone()
     assert float(full.abs().max()) > 0
     ws.grads.fill_(float("nan"))
-    ranges = parallel.gaussian_ranges(N, 3)
+    per = -(-N // 3 // 128) * 128
+    ranges = [(b, min(N, b + per)) for b in range(0, N, per)]
     assert len(ranges) == 3 and ranges[0][0] == 0 and ranges[-1][1] == N
     for g0, g1 in reversed(ranges):
         model.enqueue_backward_range(ws, g0, g1)

@@ -95,3 +95,91 @@ def test_conservative_bounds_contain_every_passing_pair(regime, N, W, H, bs, see
     # the bounds are also TIGHT enough to be useful: less than ~40 % of the visited pixels fail the exact test
     print(f"[{regime}] passing pairs {n_pairs}, visited pixels {n_slots}, efficiency {n_pairs / max(n_slots, 1):.3f}")
     assert n_pairs >= 0.6 * n_slots
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# EG_FLAG_CULL_TILES: eg_tile_row_cols / eg_extent (edgegaussians_b200/csrc/eg_common.cuh) restated in numpy fp32.
+# The fused step emits a Gaussian's key only to the tiles this test keeps; it is only correct if no tile that holds a
+# passing (pixel, Gaussian) pair is dropped.
+# ---------------------------------------------------------------------------------------------------------------
+def _extent(o, A, B, C):
+    """eg_extent -> (hu, hv, tau) or None (opacity' < 1/255)"""
+    if not (o >= F(1.0 / 255.0)):
+        return None
+    tau = F(np.log(F(255.0) * o) * F(1.001) + F(0.02))
+    det = F(A * C - B * B)
+    if not (det > 0) or not (A > 0) or not (C > 0):
+        return F(1e30), F(1e30), tau
+    k = F(F(2.0) * tau / det)
+    return F(np.sqrt(F(k * C)) * F(1.0001) + F(1e-3)), F(np.sqrt(F(k * A)) * F(1.0001) + F(1e-3)), tau
+
+
+def _tile_row_cols(mx, my, A, B, C, tau, hu, hv, ty, x0, x1):
+    """eg_tile_row_cols -> (j0, j1) inclusive or None"""
+    j0, j1 = x0, x1 - 1
+    if not (hu < F(1e29)):
+        return (j0, j1) if j1 >= j0 else None
+    va = F(F(ty * 16) + F(0.5) - my)
+    vb = F(va + F(15.0))
+    if vb < -hv or va > hv:
+        return None
+    v1, v2 = max(va, -hv), min(vb, hv)
+    det, iA = F(A * C - B * B), F(F(1.0) / A)
+    s1 = F(np.sqrt(max(F(0.0), F(F(2.0) * tau * A - det * v1 * v1))))
+    s2 = F(np.sqrt(max(F(0.0), F(F(2.0) * tau * A - det * v2 * v2))))
+    umax = max(F((-B * v1 + s1) * iA), F((-B * v2 + s2) * iA))
+    umin = min(F((-B * v1 - s1) * iA), F((-B * v2 - s2) * iA))
+    vr = F(-B * hu / C)
+    if v1 <= vr <= v2:
+        umax = hu
+    if v1 <= -vr <= v2:
+        umin = -hu
+    umax = F(umax + abs(umax) * F(1e-4) + F(0.02))
+    umin = F(umin - abs(umin) * F(1e-4) - F(0.02))
+    pa, pb = np.ceil(F(mx + umin - F(0.5))), np.floor(F(mx + umax - F(0.5)))
+    if not (pb >= pa) or pb < 0:
+        return None
+    ja, jb = int(max(pa, 0.0)) >> 4, int(min(max(pb, -1.0), 1e9)) >> 4
+    j0, j1 = max(j0, ja), min(j1, jb)
+    return (j0, j1) if j1 >= j0 else None
+
+
+@pytest.mark.parametrize("regime,N,W,H,bs,seed", CASES + [("trained", 400, 320, 240, 0.02, 5)])
+def test_tile_culling_keeps_every_tile_with_a_passing_pair(regime, N, W, H, bs, seed):
+    m, q, s, o = synth.make_gaussians(N, regime, seed, base_scale=bs)
+    sc, op = activate(s, o)
+    vms, Ks = synth.make_cameras(3, W, H)
+    st = oracle.rasterization(m, q, sc, op, vms[seed % 3], Ks[seed % 3], W, H, forward_raster=False)
+    rects = tile_rects_from_state(st)
+    n_rect = n_kept = n_needed = 0
+    for g in np.nonzero(st["radii"] > 0)[0]:
+        A, B, C = (F(v) for v in st["conics"][g])
+        oo = F(st["opacities"][g])
+        mx, my = (F(v) for v in st["means2d"][g])
+        x0, y0, x1, y1 = (int(v) for v in rects[g])
+        if x1 <= x0 or y1 <= y0:
+            continue
+        n_rect += (x1 - x0) * (y1 - y0)
+        kept = np.zeros((y1 - y0, x1 - x0), bool)
+        ext = _extent(oo, A, B, C)
+        if ext is not None:
+            hu, hv, tau = ext
+            for ty in range(y0, y1):
+                cols = _tile_row_cols(mx, my, A, B, C, tau, hu, hv, ty, x0, x1)
+                if cols is not None:
+                    kept[ty - y0, cols[0] - x0:cols[1] - x0 + 1] = True
+        # tiles that hold a passing pair (fp64, with slack)
+        X0, X1, Y0, Y1 = 16 * x0, min(16 * x1, W), 16 * y0, min(16 * y1, H)
+        ys, xs = np.mgrid[Y0:Y1, X0:X1]
+        dx, dy = float(mx) - (xs + 0.5), float(my) - (ys + 0.5)
+        sigma = 0.5 * (float(A) * dx * dx + float(C) * dy * dy) + float(B) * dx * dy
+        passing = (sigma >= -1e-6) & (float(oo) * np.exp(-sigma) >= (1.0 / 255.0) * (1.0 - 1e-3))
+        needed = np.zeros_like(kept)
+        py, px = np.nonzero(passing)
+        needed[(py + Y0) // 16 - y0, (px + X0) // 16 - x0] = True
+        assert not (needed & ~kept).any(), f"Gaussian {g}: culled a tile that holds a passing pixel"
+        n_kept += int(kept.sum())
+        n_needed += int(needed.sum())
+    print(f"[{regime}] tiles in gsplat's rectangles {n_rect}, kept {n_kept}, with a passing pixel {n_needed}")
+    assert n_needed > 0 and n_kept <= n_rect
+    assert n_kept <= 1.35 * n_needed + 8        # and the test is tight: few kept tiles are empty
