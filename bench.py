@@ -235,10 +235,11 @@ def parity_block(ref, loss, grads_flat, absgrad, n_isects, N):
         got = got.reshape(-1)
         scale = float(np.abs(exp).max())
         err = np.abs(got - exp)
-        floor = 1e-7 if key == "v_quats" else 0.0   # isotropic Gaussians: the quaternion gradient is a cancellation to ~0
+        # isotropic Gaussians (init regime): the true quaternion gradient is a cancellation to ~0 of O(|v_means|) terms
+        floor = 1e-6 * float(np.abs(ref["v_means"]).max()) if key == "v_quats" else 0.0
         bad = int((err > 1e-3 * np.abs(exp) + 2e-5 * scale + floor).sum())
         out["grad_violations"][key] = bad
-        out["grad_max_rel_err"][key] = float(err.max() / (scale + 1e-30))
+        out["grad_max_rel_err"][key] = float(err.max() / (scale + floor + 1e-30))
         ok = ok and bad <= max(2, int(5e-4 * err.size))
     out["ok"] = bool(ok)
     return out
@@ -550,6 +551,13 @@ def aux_timings(args, ctx):
         e1.record(); torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps
 
+    # ---- KNN (k = 5 as configs/DTU.json:72)
+    k = 5
+    pts = model.means.data
+    out["knn_ms"] = timed(lambda: knn_indices(pts, k), reps=3)
+    nn_idx = knn_indices(pts, k)
+    # ---- regularisers fwd + bwd in one pass
+    out["reg_fwd_bwd_ms"] = timed(lambda: reg_run(model.means.data, model.quats.data, model.scales.data, nn_idx, k, False, 1.0, 1.0))
     # ---- Adam: one launch (eg_adam_multi) vs the reference's four torch.optim.Adam on the same GPU
     for k in NAMES:
         model.gauss_params[k].grad = torch.randn_like(model.gauss_params[k]) * 1e-3
@@ -564,13 +572,6 @@ def aux_timings(args, ctx):
         for op in opts:
             op.step()
     out["adam_ms_reference_torch_x4_gpu"] = timed(torch_adam)
-    # ---- KNN (k = 5 as configs/DTU.json:72)
-    k = 5
-    pts = model.means.data
-    out["knn_ms"] = timed(lambda: knn_indices(pts, k), reps=3)
-    nn_idx = knn_indices(pts, k)
-    # ---- regularisers fwd + bwd in one pass
-    out["reg_fwd_bwd_ms"] = timed(lambda: reg_run(model.means.data, model.quats.data, model.scales.data, nn_idx, k, False, 1.0, 1.0))
     if not args.no_cpu_baseline:
         from oracle import reference_ports as ports
         try:

@@ -30,5 +30,6 @@ def grad_numel(n: int) -> int:
 def split_grads(flat, n: int):
     """(v_means [N,3], v_scales [N,3], v_quats [N,4], v_opacities [N]) views of the flat buffer."""
     om, os_, oq, oo, _ = grad_layout(n)
-    return (flat[om:om + 3 * n].view(n, 3), flat[os_:os_ + 3 * n].view(n, 3), flat[oq:oq + 4 * n].view(n, 4),
+    # reshape of a contiguous slice is a view for torch tensors and numpy arrays alike
+    return (flat[om:om + 3 * n].reshape(n, 3), flat[os_:os_ + 3 * n].reshape(n, 3), flat[oq:oq + 4 * n].reshape(n, 4),
             flat[oo:oo + n])

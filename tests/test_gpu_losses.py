@@ -117,7 +117,7 @@ def test_fused_resolve_loss_matches_reference(golden_dir, strategy):
             ref = model.compute_projection_loss(out_t, torch.as_tensor(gt).to(DEV), i, strategy)
         ref.backward()
         loss, wpix, (lp, sel, scale) = _fused_loss(model, "resolve", out, gt, strategy, i, ratio, sel_ids, W, H)
-        assert loss == pytest.approx(float(ref), abs=2e-6)
+        assert loss == pytest.approx(float(ref.detach()), abs=2e-6)
         if np.array_equal(out, g["out"][i]):
             assert loss == pytest.approx(float(g[strategy][i]), abs=2e-6)
         # seed: wpix * scale = dL/d render * T
