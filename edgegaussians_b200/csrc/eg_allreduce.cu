@@ -19,13 +19,14 @@
 // Flags are toggled 0 -> 1 -> 0 with compare-and-swap (the waiter consumes what the signaller produced), so the
 // kernel is re-entrant without epochs or host resets and can be captured in a CUDA graph -- the whole iteration,
 // exchange included, is then one graph replay.
+#include <cstdlib>
+
 #include "eg_common.cuh"
 
 namespace {
 
 constexpr int AR_THREADS = 512;
-constexpr int AR_MAX_RANKS = 16;
-constexpr int AR_UNROLL = 4;
+constexpr int AR_MAX_RANKS = 8;
 
 struct ArPeers {
     float *buf[AR_MAX_RANKS];       // peer-mapped gradient buffers, by rank
@@ -67,8 +68,10 @@ __device__ __forceinline__ void mc_st(float *mc_addr, const float4 v) {
                  ::"l"(mc_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-// n4 = number of float4 elements of the whole buffer; rank r owns the float4 range [r * per, min(n4, (r+1) * per))
-template <bool MULTICAST>
+// n4 = number of float4 elements of the whole buffer; rank r owns the float4 range [r * per, min(n4, (r+1) * per)).
+// UNROLL independent 16-byte requests per peer are in flight per thread: one round trip over NVLink takes
+// microseconds, so the bytes in flight (threads x UNROLL x 16 B) are what sets the rate, not the instruction count.
+template <bool MULTICAST, int UNROLL>
 __global__ void __launch_bounds__(AR_THREADS) allreduce_kernel(const ArPeers peers, float *__restrict__ mc_buf,
                                                                const long long n4, const int rank, const int world) {
     rank_barrier(peers, rank, world);
@@ -77,30 +80,36 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_kernel(const ArPeers pee
     const long long stride = (long long)gridDim.x * AR_THREADS;
     if (MULTICAST) {
         float4 *mc4 = reinterpret_cast<float4 *>(mc_buf);
-        // AR_UNROLL independent 16-byte switch reductions in flight per thread: the slice is a few MB and one
-        // round trip through the switch takes microseconds, so the bytes in flight are what sets the rate
-        for (long long i0 = lo + (long long)blockIdx.x * AR_THREADS + threadIdx.x; i0 < hi; i0 += AR_UNROLL * stride) {
-            float4 v[AR_UNROLL];
+        for (long long i0 = lo + (long long)blockIdx.x * AR_THREADS + threadIdx.x; i0 < hi; i0 += UNROLL * stride) {
+            float4 v[UNROLL];
 #pragma unroll
-            for (int u = 0; u < AR_UNROLL; ++u)
+            for (int u = 0; u < UNROLL; ++u)
                 if (i0 + u * stride < hi) v[u] = mc_ld_reduce(reinterpret_cast<const float *>(mc4 + i0 + u * stride));
 #pragma unroll
-            for (int u = 0; u < AR_UNROLL; ++u)
+            for (int u = 0; u < UNROLL; ++u)
                 if (i0 + u * stride < hi) mc_st(reinterpret_cast<float *>(mc4 + i0 + u * stride), v[u]);
         }
     } else {
-        for (long long i = lo + (long long)blockIdx.x * AR_THREADS + threadIdx.x; i < hi; i += stride) {
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 v[AR_MAX_RANKS];
+        constexpr int PU = UNROLL >= 4 ? 2 : 1;  // elements per thread and iteration: PU x world loads in flight
+        for (long long i0 = lo + (long long)blockIdx.x * AR_THREADS + threadIdx.x; i0 < hi; i0 += PU * stride) {
+            float4 v[PU][AR_MAX_RANKS];
 #pragma unroll
-            for (int r = 0; r < AR_MAX_RANKS; ++r)
-                if (r < world) v[r] = __ldcg(reinterpret_cast<const float4 *>(peers.buf[r]) + i);  // all loads in flight
+            for (int u = 0; u < PU; ++u)
 #pragma unroll
-            for (int r = 0; r < AR_MAX_RANKS; ++r)
-                if (r < world) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
+                for (int r = 0; r < AR_MAX_RANKS; ++r)
+                    if (r < world && i0 + u * stride < hi)
+                        v[u][r] = __ldcg(reinterpret_cast<const float4 *>(peers.buf[r]) + i0 + u * stride);
 #pragma unroll
-            for (int r = 0; r < AR_MAX_RANKS; ++r)
-                if (r < world) __stcg(reinterpret_cast<float4 *>(peers.buf[r]) + i, acc);
+            for (int u = 0; u < PU; ++u) {
+                if (i0 + u * stride >= hi) continue;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int r = 0; r < AR_MAX_RANKS; ++r)   // fixed rank order: every rank computes the same bits
+                    if (r < world) { acc.x += v[u][r].x; acc.y += v[u][r].y; acc.z += v[u][r].z; acc.w += v[u][r].w; }
+#pragma unroll
+                for (int r = 0; r < AR_MAX_RANKS; ++r)
+                    if (r < world) __stcg(reinterpret_cast<float4 *>(peers.buf[r]) + i0 + u * stride, acc);
+            }
         }
     }
     __threadfence_system();
@@ -122,7 +131,8 @@ extern "C" int eg_allreduce_symm(float *const *peer_bufs, float *mc_buf, uint32_
         return 1;
     }
     if (world == 1 || count == 0) return 0;
-    if (grid <= 0) grid = 64;
+    if (grid <= 0) grid = 148;  // nothing else runs at the tail of a step: one CTA per SM
+    static const int unroll = getenv("EG_AR_UNROLL") ? atoi(getenv("EG_AR_UNROLL")) : 8;  // tuning knob (2 / 4 / 8)
     ArPeers peers;
     for (int r = 0; r < AR_MAX_RANKS; ++r) {
         peers.buf[r] = r < world ? peer_bufs[r] : nullptr;
@@ -137,9 +147,12 @@ extern "C" int eg_allreduce_symm(float *const *peer_bufs, float *mc_buf, uint32_
         return 1;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    if (mc_buf != nullptr)
-        allreduce_kernel<true><<<grid, AR_THREADS, 0, s>>>(peers, mc_buf, count / 4, rank, world);
-    else
-        allreduce_kernel<false><<<grid, AR_THREADS, 0, s>>>(peers, nullptr, count / 4, rank, world);
+#define EG_AR_LAUNCH(MC, U) allreduce_kernel<MC, U><<<grid, AR_THREADS, 0, s>>>(peers, mc_buf, count / 4, rank, world)
+    if (mc_buf != nullptr) {
+        if (unroll <= 2) EG_AR_LAUNCH(true, 2); else if (unroll <= 4) EG_AR_LAUNCH(true, 4); else EG_AR_LAUNCH(true, 8);
+    } else {
+        if (unroll <= 2) EG_AR_LAUNCH(false, 2); else EG_AR_LAUNCH(false, 8);
+    }
+#undef EG_AR_LAUNCH
     return eg_check_launch("eg_allreduce_symm");
 }

@@ -153,19 +153,15 @@ __device__ __forceinline__ bool eg_extent(float o, float A, float B, float C, fl
     return true;
 }
 
-// Tile columns of tile row `ty` that the alpha >= 1/255 footprint of a Gaussian can reach (EG_FLAG_CULL_TILES).
-// The footprint is the ellipse  sigma(u, v) = (A u^2 + C v^2) / 2 + B u v <= tau  around the mean, tau = ln(255 o)
-// (+ the safety margin of eg_extent); the pixel-centre rows of the tile row cut a horizontal strip out of it, whose
-// u-extent is attained at the strip's ends or at the ellipse's left / right extreme points.  CONSERVATIVE: only used
-// to skip (tile, Gaussian) pairs in which the exact per-pixel alpha test of the raster kernels could never pass.
-// hu, hv = eg_extent's half extents, (x0, x1) the tile-column range of gsplat's rectangle.  Returns false when the
-// row holds no tile; else [j0, j1] (inclusive).
-__device__ __forceinline__ bool eg_tile_row_cols(float mx, float my, float A, float B, float C, float tau, float hu,
-                                                 float hv, int ty, int x0, int x1, int &j0, int &j1) {
-    j0 = x0;
-    j1 = x1 - 1;
-    if (!(hu < 1e29f)) return j1 >= j0;  // degenerate conic: eg_extent gave up, keep the whole row
-    const float va = (float)(ty * EG_TILE) + 0.5f - my, vb = va + (float)(EG_TILE - 1);
+// Conservative x-range (pixel-CENTRE coordinates) of the alpha >= 1/255 footprint of a Gaussian inside the horizontal
+// strip of pixel-centre rows [ya, yb].  The footprint is the ellipse  sigma(u, v) = (A u^2 + C v^2) / 2 + B u v <= tau
+// around the mean, tau = ln(255 o) (+ the safety margin of eg_extent); the strip cuts a slab out of it whose u-extent
+// is attained at the slab's ends or at the ellipse's left / right extreme points.  hu, hv = eg_extent's half extents
+// (a degenerate conic, hu >= 1e29, must be handled by the caller).  Only ever used to skip (tile / sub-tile,
+// Gaussian) pairs in which the exact per-pixel alpha test of the raster kernels could never pass.
+__device__ __forceinline__ bool eg_strip_xrange(float mx, float my, float A, float B, float C, float tau, float hu,
+                                                float hv, float ya, float yb, float &xlo, float &xhi) {
+    const float va = ya - my, vb = yb - my;
     if (vb < -hv || va > hv) return false;
     const float v1 = fmaxf(va, -hv), v2 = fminf(vb, hv);
     const float det = A * C - B * B, iA = 1.0f / A;
@@ -175,15 +171,48 @@ __device__ __forceinline__ bool eg_tile_row_cols(float mx, float my, float A, fl
     const float vr = -B * hu / C;  // v of the right-most point (u = +hu); the left-most one is at -vr
     if (vr >= v1 && vr <= v2) umax = hu;
     if (-vr >= v1 && -vr <= v2) umin = -hu;
-    umax = umax + fabsf(umax) * 1e-4f + 0.02f;
-    umin = umin - fabsf(umin) * 1e-4f - 0.02f;
-    // pixel columns whose centre px + 0.5 lies in [mx + umin, mx + umax]
-    const float pa = ceilf(mx + umin - 0.5f), pb = floorf(mx + umax - 0.5f);
+    xhi = mx + (umax + fabsf(umax) * 1e-4f + 0.02f);
+    xlo = mx + (umin - fabsf(umin) * 1e-4f - 0.02f);
+    return true;
+}
+
+// Tile columns of tile row `ty` that the footprint can reach (EG_FLAG_CULL_TILES); (x0, x1) = the tile-column range
+// of gsplat's rectangle.  Returns false when the row holds no tile; else [j0, j1] (inclusive).
+__device__ __forceinline__ bool eg_tile_row_cols(float mx, float my, float A, float B, float C, float tau, float hu,
+                                                 float hv, int ty, int x0, int x1, int &j0, int &j1) {
+    j0 = x0;
+    j1 = x1 - 1;
+    if (!(hu < 1e29f)) return j1 >= j0;  // degenerate conic: eg_extent gave up, keep the whole row
+    const float ya = (float)(ty * EG_TILE) + 0.5f;
+    float xlo, xhi;
+    if (!eg_strip_xrange(mx, my, A, B, C, tau, hu, hv, ya, ya + (float)(EG_TILE - 1), xlo, xhi)) return false;
+    // pixel columns whose centre px + 0.5 lies in [xlo, xhi]
+    const float pa = ceilf(xlo - 0.5f), pb = floorf(xhi - 0.5f);
     if (!(pb >= pa)) return false;
     const int ja = (int)fmaxf(pa, 0.0f) >> 4, jb = (int)fminf(fmaxf(pb, -1.0f), 1e9f) >> 4;
     j0 = max(j0, ja);
     j1 = min(j1, jb);
     return j1 >= j0 && pb >= 0.0f;
+}
+
+// Which of the eight 8x4-pixel sub-tiles of tile (X0, Y0) the footprint can reach: bit (2 r + c) = sub-tile row r
+// (pixel rows Y0 + 4r .. Y0 + 4r + 3), column half c.  Same conservative strip test, one per sub-tile row.
+__device__ __forceinline__ int eg_subtile_mask(float mx, float my, float A, float B, float C, float o, float X0, float Y0) {
+    float hu, hv, tau;
+    if (!eg_extent(o, A, B, C, hu, hv, tau)) return 0;
+    if (!(hu < 1e29f)) return 0xff;
+    int mask = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        float xlo, xhi;
+        const float ya = Y0 + 4.0f * r + 0.5f;
+        if (!eg_strip_xrange(mx, my, A, B, C, tau, hu, hv, ya, ya + 3.0f, xlo, xhi)) continue;
+        int cx = 0;
+        if (xhi >= X0 + 0.5f && xlo <= X0 + 7.5f) cx |= 1;
+        if (xhi >= X0 + 8.5f && xlo <= X0 + 15.5f) cx |= 2;
+        mask |= cx << (2 * r);
+    }
+    return mask;
 }
 
 // Coefficient of |clamp(render) - gt| at one pixel in the fused projection loss (and of that pixel's backward seed):

@@ -221,20 +221,8 @@ __device__ __forceinline__ void composite_entries(const int n, const int base, c
         if (k < n) {
             const int gid = sids != nullptr ? (int)sids[k] : flat[k];
             const float4 r0 = __ldg(rec + 2 * gid), r1 = __ldg(rec + 2 * gid + 1);
-            int mask = 0;
-            float hx, hy, tau;
-            if (eg_extent(r0.z, r1.x, r1.y, r1.z, hx, hy, tau)) {
-                const float xl = r0.x - hx, xh = r0.x + hx, yl = r0.y - hy, yh = r0.y + hy;
-                int cx = 0, cy = 0;
-                if (xh >= X0 + 0.5f && xl <= X0 + 7.5f) cx |= 1;
-                if (xh >= X0 + 8.5f && xl <= X0 + 15.5f) cx |= 2;
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-                    if (yh >= Y0 + 4.0f * r + 0.5f && yl <= Y0 + 4.0f * r + 3.5f) cy |= 1 << r;
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-                    if (cy & (1 << r)) mask |= cx << (2 * r);
-            }
+            // sub-tiles (8x4 pixels, one per warp) the alpha >= 1/255 ellipse can reach: a warp only walks those
+            const int mask = eg_subtile_mask(r0.x, r0.y, r1.x, r1.y, r1.z, r0.z, X0, Y0);
             const EgFold f = eg_fold(r1.x, r1.y, r1.z, r0.z);
             sAB[2 * tid] = make_float4(r0.x, r0.y, f.lo, __int_as_float(mask));
             sAB[2 * tid + 1] = make_float4(f.fa, f.fb, f.fc, __int_as_float(gid));

@@ -8,6 +8,7 @@ abs-grad statistics.  One process per GPU, ``torch.distributed`` (NCCL on GPUs, 
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -72,7 +73,8 @@ class SymmetricExchange:
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.numel = int(numel)
         assert self.numel % 4 == 0, "the flat gradient buffer is padded to 16 bytes (layout.grad_numel)"
-        self.grid = int(grid) if grid > 0 else 64
+        # one CTA per SM by default (nothing else runs at the tail of a step); EG_AR_GRID overrides for tuning
+        self.grid = int(grid) if grid > 0 else int(os.environ.get("EG_AR_GRID", "148"))
         self.buf = symm_mem.empty(self.numel, dtype=torch.float32, device=device)
         self.buf.zero_()
         self._hdl = symm_mem.rendezvous(self.buf, group)

@@ -257,7 +257,7 @@ int eg_splat_bwd(const eg_config *cfg, const float *means, const float *quats, c
  *   switch) and broadcasts it with multimem.st; without it, 128-bit peer loads / stores.  peer_flags [world] (HOST
  *   array): per rank a zero-initialised symmetric area of eg_allreduce_flag_words(grid) u32 used by the in-kernel
  *   rank barriers (self-resetting: no host work between calls; capturable in a CUDA graph).  Every rank must
- *   enqueue the call with the same count / grid; `grid` <= 0 picks the default.
+ *   enqueue the call with the same count / grid; `grid` <= 0 picks the default.  At most 8 ranks (one NVSwitch domain).
  * eg_comm_* -- the same sum through NCCL (resolved at run time with dlopen, no link dependency), kept as the A/B
  *   baseline: eg_comm_unique_id on rank 0 (128-byte id in host memory, broadcast by the caller), eg_comm_init
  *   collectively on the calling thread's current device, eg_comm_allreduce in place on `stream`. */

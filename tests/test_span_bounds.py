@@ -114,13 +114,9 @@ def _extent(o, A, B, C):
     return F(np.sqrt(F(k * C)) * F(1.0001) + F(1e-3)), F(np.sqrt(F(k * A)) * F(1.0001) + F(1e-3)), tau
 
 
-def _tile_row_cols(mx, my, A, B, C, tau, hu, hv, ty, x0, x1):
-    """eg_tile_row_cols -> (j0, j1) inclusive or None"""
-    j0, j1 = x0, x1 - 1
-    if not (hu < F(1e29)):
-        return (j0, j1) if j1 >= j0 else None
-    va = F(F(ty * 16) + F(0.5) - my)
-    vb = F(va + F(15.0))
+def _strip_xrange(mx, my, A, B, C, tau, hu, hv, ya, yb):
+    """eg_strip_xrange -> (xlo, xhi) in pixel-centre coordinates, or None"""
+    va, vb = F(ya - my), F(yb - my)
     if vb < -hv or va > hv:
         return None
     v1, v2 = max(va, -hv), min(vb, hv)
@@ -134,14 +130,47 @@ def _tile_row_cols(mx, my, A, B, C, tau, hu, hv, ty, x0, x1):
         umax = hu
     if v1 <= -vr <= v2:
         umin = -hu
-    umax = F(umax + abs(umax) * F(1e-4) + F(0.02))
-    umin = F(umin - abs(umin) * F(1e-4) - F(0.02))
-    pa, pb = np.ceil(F(mx + umin - F(0.5))), np.floor(F(mx + umax - F(0.5)))
+    return F(mx + F(umin - abs(umin) * F(1e-4) - F(0.02))), F(mx + F(umax + abs(umax) * F(1e-4) + F(0.02)))
+
+
+def _tile_row_cols(mx, my, A, B, C, tau, hu, hv, ty, x0, x1):
+    """eg_tile_row_cols -> (j0, j1) inclusive or None"""
+    j0, j1 = x0, x1 - 1
+    if not (hu < F(1e29)):
+        return (j0, j1) if j1 >= j0 else None
+    ya = F(F(ty * 16) + F(0.5))
+    rng = _strip_xrange(mx, my, A, B, C, tau, hu, hv, ya, F(ya + F(15.0)))
+    if rng is None:
+        return None
+    pa, pb = np.ceil(F(rng[0] - F(0.5))), np.floor(F(rng[1] - F(0.5)))
     if not (pb >= pa) or pb < 0:
         return None
     ja, jb = int(max(pa, 0.0)) >> 4, int(min(max(pb, -1.0), 1e9)) >> 4
     j0, j1 = max(j0, ja), min(j1, jb)
     return (j0, j1) if j1 >= j0 else None
+
+
+def _subtile_mask(mx, my, A, B, C, o, X0, Y0):
+    """eg_subtile_mask: bit (2 r + c) = 8x4 sub-tile (row r, column half c) of tile (X0, Y0)"""
+    ext = _extent(o, A, B, C)
+    if ext is None:
+        return 0
+    hu, hv, tau = ext
+    if not (hu < F(1e29)):
+        return 0xff
+    mask = 0
+    for r in range(4):
+        ya = F(Y0 + 4.0 * r + 0.5)
+        rng = _strip_xrange(mx, my, A, B, C, tau, hu, hv, ya, F(ya + F(3.0)))
+        if rng is None:
+            continue
+        cx = 0
+        if rng[1] >= X0 + 0.5 and rng[0] <= X0 + 7.5:
+            cx |= 1
+        if rng[1] >= X0 + 8.5 and rng[0] <= X0 + 15.5:
+            cx |= 2
+        mask |= cx << (2 * r)
+    return mask
 
 
 @pytest.mark.parametrize("regime,N,W,H,bs,seed", CASES + [("trained", 400, 320, 240, 0.02, 5)])
@@ -151,7 +180,7 @@ def test_tile_culling_keeps_every_tile_with_a_passing_pair(regime, N, W, H, bs, 
     vms, Ks = synth.make_cameras(3, W, H)
     st = oracle.rasterization(m, q, sc, op, vms[seed % 3], Ks[seed % 3], W, H, forward_raster=False)
     rects = tile_rects_from_state(st)
-    n_rect = n_kept = n_needed = 0
+    n_rect = n_kept = n_needed = n_sub_kept = n_sub_needed = 0
     for g in np.nonzero(st["radii"] > 0)[0]:
         A, B, C = (F(v) for v in st["conics"][g])
         oo = F(st["opacities"][g])
@@ -178,8 +207,20 @@ def test_tile_culling_keeps_every_tile_with_a_passing_pair(regime, N, W, H, bs, 
         py, px = np.nonzero(passing)
         needed[(py + Y0) // 16 - y0, (px + X0) // 16 - x0] = True
         assert not (needed & ~kept).any(), f"Gaussian {g}: culled a tile that holds a passing pixel"
+        # the 8x4 sub-tile masks of the tile forward (eg_subtile_mask) keep every sub-tile with a passing pixel
+        for (ty_, tx_) in zip(*np.nonzero(needed)):
+            TX, TY = 16 * (tx_ + x0), 16 * (ty_ + y0)
+            sm = _subtile_mask(mx, my, A, B, C, oo, TX, TY)
+            sel = (py + Y0 >= TY) & (py + Y0 < TY + 16) & (px + X0 >= TX) & (px + X0 < TX + 16)
+            bits = 2 * ((py[sel] + Y0 - TY) // 4) + ((px[sel] + X0 - TX) // 8)
+            need_mask = int(np.bitwise_or.reduce(1 << bits))
+            assert need_mask & ~sm == 0, f"Gaussian {g}, tile ({tx_ + x0}, {ty_ + y0}): sub-tile mask {sm:08b} misses {need_mask:08b}"
+            n_sub_kept += bin(sm).count("1")
+            n_sub_needed += bin(need_mask).count("1")
         n_kept += int(kept.sum())
         n_needed += int(needed.sum())
-    print(f"[{regime}] tiles in gsplat's rectangles {n_rect}, kept {n_kept}, with a passing pixel {n_needed}")
+    print(f"[{regime}] tiles in gsplat's rectangles {n_rect}, kept {n_kept}, with a passing pixel {n_needed}; "
+          f"sub-tiles kept {n_sub_kept}, with a passing pixel {n_sub_needed}")
+    assert n_sub_kept <= 1.3 * n_sub_needed + 8
     assert n_needed > 0 and n_kept <= n_rect
     assert n_kept <= 1.35 * n_needed + 8        # and the test is tight: few kept tiles are empty
