@@ -230,8 +230,8 @@ __device__ __forceinline__ void finish_gaussian(const eg_config &cfg, const int 
     float vm[3] = {0.f, 0.f, 0.f}, vs[3] = {0.f, 0.f, 0.f}, vq[4] = {0.f, 0.f, 0.f, 0.f}, vo = 0.f;
     float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
     if (has_pairs) {
-        const float4 a0 = *reinterpret_cast<const float4 *>(acc);
-        const float4 a1 = *reinterpret_cast<const float4 *>(acc + 4);
+        const float4 a0 = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        const float4 a1 = make_float4(acc[4], acc[5], acc[6], acc[7]);
         const float sc = seed_scale, asc = fabsf(seed_scale);
         g0 = make_float4(a0.x * sc, a0.y * sc, a0.z * asc, a0.w * asc);
         // v_opacity' = sum vis * v_alpha = -(sum v_sigma) / opacity'
@@ -264,9 +264,10 @@ __global__ void __launch_bounds__(SB_WARPS * 32, EG_SB_MINBLOCKS) splat_bwd_kern
     const int *__restrict__ last_gid, const int *__restrict__ tile_stop, const int32_t *__restrict__ status,
     float4 *__restrict__ grad2d_out,
     float *__restrict__ v_means, float *__restrict__ v_quats, float *__restrict__ v_scales,
-    float *__restrict__ v_opacities, float *__restrict__ absgrad_accum) {
+    float *__restrict__ v_opacities, float *__restrict__ absgrad_accum, const int opts) {
     __shared__ EgSplatG s_g[SB_WARPS][32];                   // compacted over the Gaussians that have rows
     __shared__ __align__(16) float s_acc[SB_WARPS][32][8];   // same (compact) index
+    __shared__ __align__(16) float s_slot[SB_WARPS][32][8];  // per lane: the contribution of its work item
 
     if (status[EG_ST_OVERFLOW]) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -311,14 +312,48 @@ __global__ void __launch_bounds__(SB_WARPS * 32, EG_SB_MINBLOCKS) splat_bwd_kern
         if (item >= R) owner = 32;
         if (item < R) {
             const EgSplatG Go = s_g[warp][owner];
-            const int r0 = EG_ROWS_PER_ITEM * (item - Go.start);
+            // the EG_ROWS_PER_ITEM rows of an item: consecutive ones, or (opts & 1) rows half a footprint apart -- a
+            // short row near the rim of the ellipse then shares a lane with a long one near its middle
+            const int t = item - Go.start;
+            const int n_items = (Go.nrows + EG_ROWS_PER_ITEM - 1) / EG_ROWS_PER_ITEM;
 #pragma unroll
             for (int r = 0; r < EG_ROWS_PER_ITEM; ++r) {
-                if (r0 + r >= Go.nrows) break;
-                const int y = Go.ylo + r0 + r;
+                const int ry = (opts & 1) ? t + r * n_items : EG_ROWS_PER_ITEM * t + r;
+                if (ry >= Go.nrows) break;
+                const int y = Go.ylo + ry;
                 if (use_last) walk_row_bwd<true, ALIGNED>(Go, y, cfg.width, tw, wpix, last_depth, last_gid, tile_stop, v);
                 else walk_row_bwd<false, ALIGNED>(Go, y, cfg.width, tw, wpix, nullptr, nullptr, nullptr, v);
             }
+        }
+        if (opts & 2) {
+            // the items of one Gaussian sit in adjacent lanes: every lane parks its 8 values in shared memory and the first
+            // lane of each run adds up the others (a handful of LDS.128 instead of a 5-step segmented shuffle reduction)
+            float4 *slot = reinterpret_cast<float4 *>(&s_slot[warp][lane][0]);
+            slot[0] = make_float4(v[0], v[1], v[2], v[3]);
+            slot[1] = make_float4(v[4], v[5], v[6], v[7]);
+            const int prev = __shfl_up_sync(0xffffffffu, owner, 1);
+            const bool head = item < R && (lane == 0 || prev != owner);
+            const unsigned head_m = __ballot_sync(0xffffffffu, head);
+            __syncwarp();
+            if (head) {
+                const unsigned above = lane == 31 ? 0u : (head_m & ~((2u << lane) - 1u));
+                const int end = above ? __ffs(above) - 1 : min(32, R - base);
+                float4 q0 = make_float4(v[0], v[1], v[2], v[3]), q1 = make_float4(v[4], v[5], v[6], v[7]);
+                for (int t = lane + 1; t < end; ++t) {
+                    const float4 b0 = *reinterpret_cast<const float4 *>(&s_slot[warp][t][0]);
+                    const float4 b1 = *reinterpret_cast<const float4 *>(&s_slot[warp][t][4]);
+                    q0.x += b0.x; q0.y += b0.y; q0.z += b0.z; q0.w += b0.w;
+                    q1.x += b1.x; q1.y += b1.y; q1.z += b1.z; q1.w += b1.w;
+                }
+                float4 *dst = reinterpret_cast<float4 *>(&s_acc[warp][owner][0]);
+                float4 a0 = dst[0], a1 = dst[1];
+                a0.x += q0.x; a0.y += q0.y; a0.z += q0.z; a0.w += q0.w;
+                a1.x += q1.x; a1.y += q1.y; a1.z += q1.z; a1.w += q1.w;
+                dst[0] = a0;
+                dst[1] = a1;
+            }
+            __syncwarp();
+            continue;
         }
         // segmented sum over the (contiguous) lanes that share an owner
 #pragma unroll
@@ -347,6 +382,39 @@ __global__ void __launch_bounds__(SB_WARPS * 32, EG_SB_MINBLOCKS) splat_bwd_kern
     if (!live) return;
     finish_gaussian<RAW>(cfg, g, nrows > 0, nrows > 0 ? &s_acc[warp][kc][0] : nullptr, seed_scale, opac_eff, r1, means, quats, scales,
                          opacities, viewmat, Kmat, grad2d_out, v_means, v_quats, v_scales, v_opacities, absgrad_accum);
+}
+
+// =====================================================================================================================
+// Lane = Gaussian variant (W % 4 == 0): every lane walks ALL rows of its own Gaussian.  No owner look-up, no shared
+// memory, no reduction: the 2D gradients stay in registers from the first pair to the projection VJP.  Row r of the
+// 32 footprints is walked in lock-step, so the warp is as busy as its Gaussians are alike (same row count, same row
+// lengths): ideal after a Morton sort of equally sized Gaussians, poor for a mix of sizes.
+// =====================================================================================================================
+template <bool RAW>
+__global__ void __launch_bounds__(SB_WARPS * 32, EG_SB_MINBLOCKS) splat_bwd_gauss_kernel(
+    const eg_config cfg, const int g_begin, const int g_end, const int tw, const int th, const float *__restrict__ means,
+    const float *__restrict__ quats, const float *__restrict__ scales, const float *__restrict__ opacities,
+    const float *__restrict__ viewmat, const float *__restrict__ Kmat, const float4 *__restrict__ rec,
+    const int2 *__restrict__ gint, const float *__restrict__ wpix, const float seed_scale,
+    const unsigned *__restrict__ last_depth, const int *__restrict__ last_gid, const int *__restrict__ tile_stop,
+    const int32_t *__restrict__ status, float4 *__restrict__ grad2d_out, float *__restrict__ v_means,
+    float *__restrict__ v_quats, float *__restrict__ v_scales, float *__restrict__ v_opacities,
+    float *__restrict__ absgrad_accum) {
+    if (status[EG_ST_OVERFLOW]) return;
+    const int g = g_begin + blockIdx.x * (SB_WARPS * 32) + threadIdx.x;
+    if (g >= g_end) return;
+    const bool use_last = last_depth != nullptr && last_gid != nullptr && status[EG_ST_STOPPED] != 0;
+    EgSplatG G;
+    const int2 gi = __ldg(gint + g);
+    const float4 r0 = __ldg(rec + 2 * g), r1 = __ldg(rec + 2 * g + 1);
+    eg_splat_setup(cfg, tw, th, g, r0, r1, gi.x, G);
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int r = 0; r < G.nrows; ++r) {
+        if (use_last) walk_row_bwd<true, true>(G, G.ylo + r, cfg.width, tw, wpix, last_depth, last_gid, tile_stop, v);
+        else walk_row_bwd<false, true>(G, G.ylo + r, cfg.width, tw, wpix, nullptr, nullptr, nullptr, v);
+    }
+    finish_gaussian<RAW>(cfg, g, G.nrows > 0, v, seed_scale, r0.z, r1, means, quats, scales, opacities, viewmat, Kmat, grad2d_out,
+                         v_means, v_quats, v_scales, v_opacities, absgrad_accum);
 }
 
 // =====================================================================================================================
@@ -789,7 +857,7 @@ extern "C" int eg_splat_bwd(const eg_config *cfg, const float *means, const floa
                                                       (const float4 *)rec, (const int2 *)gint, wpix, seed_scale,    \
                                                       last_depth, last_gid, tile_stop, status,                      \
                                                       (float4 *)grad2d_out, v_means,                                \
-                                                      v_quats, v_scales, v_opacities, absgrad_accum)
+                                                      v_quats, v_scales, v_opacities, absgrad_accum, opts)
 #define EG_SP_LAUNCH(RAWP)                                                                                           \
     splat_bwd_parts_kernel<RAWP><<<grid, block, 0, s>>>(*cfg, g_begin, g_end, tw, th, means, quats, scales, opacities, viewmat, K,  \
                                                         (const float4 *)rec, (const int2 *)gint, wpix, seed_scale,  \
@@ -798,9 +866,21 @@ extern "C" int eg_splat_bwd(const eg_config *cfg, const float *means, const floa
                                                         v_quats, v_scales, v_opacities, absgrad_accum, plen_min)
     // part length of small footprints (chunks); EG_SP_PLEN overrides for tuning
     static const int plen_min = getenv("EG_SP_PLEN") != nullptr ? max(1, min(32, atoi(getenv("EG_SP_PLEN")))) : 8;
-    // EG_BWD_ROWS=1 selects the row-per-lane walk on aligned images too (A/B measurements)
-    static const bool rows_only = getenv("EG_BWD_ROWS") != nullptr && getenv("EG_BWD_ROWS")[0] == '1';
-    if (aligned && !rows_only) {
+    // rows kernel options (bit 0: rows of an item half a footprint apart, bit 1: shared-memory slot reduction)
+    static const int opts = getenv("EG_BWD_OPTS") != nullptr ? atoi(getenv("EG_BWD_OPTS")) : 0;
+    // EG_BWD_MODE selects the enumeration on aligned images (A/B measurements): rows (default) | parts | gauss
+    static const char *mode_env = getenv("EG_BWD_MODE");
+    static const int mode = mode_env == nullptr ? 0 : (mode_env[0] == 'p' ? 1 : (mode_env[0] == 'g' ? 2 : 0));
+    if (aligned && mode == 2) {
+        if (cfg->raw_params)
+            splat_bwd_gauss_kernel<true><<<grid, block, 0, s>>>(*cfg, g_begin, g_end, tw, th, means, quats, scales, opacities, viewmat, K,
+                (const float4 *)rec, (const int2 *)gint, wpix, seed_scale, last_depth, last_gid, tile_stop, status,
+                (float4 *)grad2d_out, v_means, v_quats, v_scales, v_opacities, absgrad_accum);
+        else
+            splat_bwd_gauss_kernel<false><<<grid, block, 0, s>>>(*cfg, g_begin, g_end, tw, th, means, quats, scales, opacities, viewmat, K,
+                (const float4 *)rec, (const int2 *)gint, wpix, seed_scale, last_depth, last_gid, tile_stop, status,
+                (float4 *)grad2d_out, v_means, v_quats, v_scales, v_opacities, absgrad_accum);
+    } else if (aligned && mode == 1) {
         static_assert(SP_WARPS == SB_WARPS, "both kernels own 128 Gaussians per CTA");
         if (cfg->raw_params) EG_SP_LAUNCH(true); else EG_SP_LAUNCH(false);
     } else if (cfg->raw_params) {
