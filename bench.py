@@ -53,7 +53,9 @@ def parse_args():
     ap.add_argument("--no-lazy-sort", action="store_true", help="always sort every tile (gsplat order) in the tile pipelines")
     ap.add_argument("--no-cull", action="store_true", help="emit keys to every tile of gsplat's rectangle (no footprint culling)")
     ap.add_argument("--no-front-sort", action="store_true", help="sort whole tile lists (no depth-sliced early stop)")
-    ap.add_argument("--morton", action="store_true", help="Morton-order the Gaussians once before the run (as after a densify)")
+    ap.add_argument("--no-morton", action="store_true",
+                    help="keep the Gaussians in creation order (default: Morton-ordered once before the run, as the trainer does after "
+                         "populate / densify: EdgeGaussianSplatting.sort_gaussians_morton)")
     ap.add_argument("--pipeline", default="auto", choices=["auto", "splat", "tiles+splat", "tiles"],
                     help="fused-step pipeline (edge_gs.enqueue_raster_step); auto = what training would run")
     ap.add_argument("--exchange", default="auto", choices=["auto", "symm", "symm-p2p", "nccl", "native-nccl"],
@@ -271,7 +273,7 @@ def bench_regime(args, regime, ctx):
     model.cull_tiles = not args.no_cull
     model.front_sort = not args.no_front_sort
     perm = None
-    if args.morton:
+    if not args.no_morton:
         perm = model.sort_gaussians_morton()   # once, like after a densify; parity below maps back through `perm`
 
     step = GraphedRasterStep(model, W, H, n_slots=V, gt_dtype=torch.uint8, allreduce=world > 1, exchange=args.exchange)
@@ -498,7 +500,7 @@ def bench_regime(args, regime, ctx):
         "pipeline": ws.pipeline, "stopped_tiles": int(ws.status[5]),
         "tile_sort": ("n/a" if ws.pipeline == "splat" else "lazy (only tiles near the transmittance stop threshold)" if model._use_lazy() else
                       ("front-to-back depth slices, early stop" if model.front_sort else "every tile")),
-        "tile_culling": bool(model.cull_tiles), "morton_order": bool(args.morton),
+        "tile_culling": bool(model.cull_tiles), "morton_order": not args.no_morton,
         "execution": f"CUDA graph replay per iteration (1 memset + {n_launch} kernels; stages: {', '.join(kernels)}"
                      + (", exchange" if step.exchange is not None else "") + ")",
         "exchange": step.exchange_name(),

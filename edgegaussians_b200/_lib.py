@@ -99,7 +99,7 @@ def load(build_if_missing: bool = True):
     lib.eg_reg_fwd_bwd.argtypes = [c_int, P, P, P, P, c_int, c_int, c_int, c_float, c_float, P, P, P, P, P]
     lib.eg_knn_workspace_bytes.argtypes = [c_int]
     lib.eg_knn.argtypes = [c_int, P, c_int, c_int, P, P, ctypes.c_size_t, P]
-    lib.eg_projecting_fraction.argtypes = [c_int, P, c_int, P, P, P, P, P, P, P]
+    lib.eg_projecting_fraction.argtypes = [c_int, P, c_int, P, P, P, P, P, c_int, P, P]
     lib.eg_adam_step.argtypes = [c_int64, P, P, P, P] + [c_double] * 6 + [c_int, P]
     lib.eg_adam_multi.argtypes = [c_int, POINTER(EgAdamSegment), P, P, c_double, c_double, c_double, c_int, P, P]
     lib.eg_gather_rows.argtypes = [c_int64, P, c_int, POINTER(EgRowArray), P]

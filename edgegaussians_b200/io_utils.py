@@ -4,8 +4,9 @@ Mirrors write_gaussian_params_as_ply / read_gaussian_params_from_ply of
 /root/reference/edgegaussians/utils/io_utils.py:4-39: one `vertex` element with eleven little-endian float32
 properties x, y, z, scale1-3, quat1-4, opacity holding ACTIVATED values (exp of the log-scales, sigmoid of the
 logits; edge_gs.py:635-642).  The reference goes through the third-party `plyfile` package, which is absent from
-this image, so the bytes are written directly (PLY 1.0 binary_little_endian, the header `plyfile` emits for that
-dtype); NOT pinned against `plyfile` output -- the reader below and any PLY 1.0 parser accept it."""
+this image, so the bytes are written directly: PLY 1.0 binary_little_endian with exactly the header `plyfile` emits
+for that dtype ("property float <name>" per 'f4' field, "\\n" line ends, no comment lines) and the packed records.
+tests/test_io_ply.py holds the expected file byte by byte (known-answer test)."""
 from __future__ import annotations
 
 import numpy as np

@@ -32,15 +32,17 @@ class PackedViews:
                 raise ValueError("edge mask shape must be (height, width) of its camera")
             sizes.append([c.width, c.height])
             offs.append(o)
-            flat.append(m.to(device=device, dtype=torch.uint8).reshape(-1))
+            flat.append(m.to(device=device, dtype=torch.uint8).reshape(-1))   # bool mask -> 0/1; uint8 edge map kept
             o += c.width * c.height
         self.sizes = torch.tensor(sizes, dtype=torch.int32, device=device)
         self.offsets = torch.tensor(offs, dtype=torch.int64, device=device)
         self.masks = torch.cat(flat).contiguous()
 
 
-def projecting_fraction(means: torch.Tensor, views: PackedViews) -> torch.Tensor:
-    """[N] fp32: fraction of the views in which each mean projects inside the image and onto an edge pixel."""
+def projecting_fraction(means: torch.Tensor, views: PackedViews, mode: int = 0) -> torch.Tensor:
+    """[N] fp32.  mode 0: fraction of the views in which each mean projects inside the image and onto an edge pixel
+    (``views.masks`` = bool masks).  mode 1: SUM over the views of the uint8 edge map's value at the projection
+    (``views.masks`` = uint8 edge maps; an exact integer -- filter_by_projection divides it by 255 V in float64)."""
     _lib.require_cuda(means, "means")
     lib = _lib.load()
     x = means.detach().float().contiguous()
@@ -51,8 +53,8 @@ def projecting_fraction(means: torch.Tensor, views: PackedViews) -> torch.Tensor
         v1 = min(views.n, v0 + MAX_VIEWS_PER_CALL)
         _lib.check(lib.eg_projecting_fraction(N, _p(x), v1 - v0, _p(views.viewmats[v0:v1]), _p(views.Ks[v0:v1]),
                                               _p(views.sizes[v0:v1]), _p(views.masks), _p(views.offsets[v0:v1]),
-                                              _p(part), _stream()), "eg_projecting_fraction")
+                                              int(mode), _p(part), _stream()), "eg_projecting_fraction")
         if v0 == 0 and v1 == views.n:
             return part
-        total += part * float(v1 - v0)
-    return total / float(views.n)
+        total += part * (float(v1 - v0) if mode == 0 else 1.0)
+    return total / float(views.n) if mode == 0 else total

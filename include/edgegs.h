@@ -300,9 +300,12 @@ int eg_knn(int n, const float *points, int kk, int skip, int32_t *out, void *wor
  * n_views views in which the Gaussian's mean projects (P = K @ viewmat[:3,:4], round half to even, no depth test --
  * the reference's arithmetic) inside the image and onto a non-zero pixel of that view's edge mask.
  * viewmats [V,16], Ks [V,9], sizes [V,2] i32 = (width, height), masks u8 = the views' [H,W] masks back to back,
- * mask_offsets [V] i64 = start of each view's mask in `masks`.  At most 1024 views per call. */
+ * mask_offsets [V] i64 = start of each view's mask in `masks`.  At most 1024 views per call.
+ * mode 0: the hit fraction above.  mode 1: `masks` holds the uint8 EDGE MAPS and fraction = SUM over the views of
+ * the edge value at the projected pixel (0 outside the image; an integer, exact in fp32) -- divided by 255 V it is the
+ * statistic of the post-processing filter filter_by_projection (edge_extraction/filtering.py:80-123). */
 int eg_projecting_fraction(int n, const float *means, int n_views, const float *viewmats, const float *Ks,
-                           const int32_t *sizes, const uint8_t *masks, const int64_t *mask_offsets,
+                           const int32_t *sizes, const uint8_t *masks, const int64_t *mask_offsets, int mode,
                            float *fraction, void *stream);
 
 /* a13 ("next"): fused Adam update of one parameter tensor, torch.optim.Adam

@@ -67,3 +67,25 @@ def test_projecting_fraction_large_and_timing():
     print(f"N={N} V={V}: kernel {ms * 1e3:.1f} us ({N * V / ms / 1e6:.1f} G projections/s), numpy port {t_cpu:.2f} s; "
           f"entries differing {n_bad} (max {diff.max():.3f})")
     assert n_bad <= max(2, int(2e-5 * N)) and diff.max() <= 1.0 / V + 1e-6   # rounding ties only, one view each
+
+
+def test_filter_by_projection_matches_reference_golden(golden_dir):
+    """edgegaussians_b200.filtering.filter_by_projection (one kernel over all views, eg_projecting_fraction mode 1)
+    against the inlier masks of the REAL reference function (edge_extraction/filtering.py:80-123), with the edge maps
+    given as uint8 / 255 floats (what the reference holds) and as the raw uint8 images."""
+    from edgegaussians_b200.filtering import filter_by_projection, projection_visibility
+    g = np.load(os.path.join(golden_dir, "filtering.npz"))
+    cams = [{"K": g["Ks"][v], "R": g["Rs"][v], "t": g["ts"][v], "w": int(w), "h": int(h)} for v, (w, h) in enumerate(g["sizes"])]
+    u8 = [g[f"edge{v}"] for v in range(len(cams))]
+    as_float = [torch.tensor(e, dtype=torch.float32) / 255.0 for e in u8]
+    for thr in (0.02, 0.1, 0.3):
+        exp = g[f"inliers_{thr}"]
+        for imgs in (as_float, u8):
+            got = filter_by_projection(g["means"], imgs, cams, visib_thresh=thr, device=DEV)
+            bad = int((got != exp).sum())
+            print(f"threshold {thr}: kept {int(got.sum())} / {exp.size}, mismatches vs reference {bad}")
+            assert got.dtype == np.bool_ and bad <= 2   # a projection on a rounding tie (x.5) may round the other way
+    vis = projection_visibility(g["means"], u8, cams, DEV)
+    assert vis.dtype == torch.float64 and float(vis.min()) >= 0.0 and float(vis.max()) <= 1.0
+    with pytest.raises(NotImplementedError):
+        filter_by_projection(g["means"], [a * 0.37 for a in as_float], cams, device=DEV)

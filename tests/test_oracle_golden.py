@@ -91,3 +91,17 @@ def test_projecting_fraction_matches_reference(golden_dir):
     assert frac.shape == (g["means"].shape[0],) and 0.0 <= frac.min() and frac.max() <= 1.0
     for thr in (0.1, 0.3, 0.5):
         np.testing.assert_array_equal(frac < np.float32(thr), g[f"cull_mask_{thr}"])
+
+
+def test_filter_by_projection_port_matches_reference(golden_dir):
+    """oracle.reference_ports.filter_by_projection against the REAL reference function
+    (edge_extraction/filtering.py:80-123; tests/golden/make_golden_filtering.py)."""
+    from oracle import reference_ports as rp
+    g = np.load(os.path.join(golden_dir, "filtering.npz"))
+    cams = [{"K": g["Ks"][v], "R": g["Rs"][v], "t": g["ts"][v], "w": int(w), "h": int(h)} for v, (w, h) in enumerate(g["sizes"])]
+    imgs = [g[f"edge{v}"].astype(np.float32) / np.float32(255.0) for v in range(len(cams))]
+    for thr in (0.02, 0.1, 0.3):
+        got = rp.filter_by_projection(g["means"], imgs, cams, thr)
+        exp = g[f"inliers_{thr}"]
+        assert 0 < exp.sum() < exp.size
+        np.testing.assert_array_equal(got, exp)
