@@ -318,7 +318,8 @@ __global__ void __launch_bounds__(SB_WARPS * 32, EG_SB_MINBLOCKS) splat_bwd_kern
         const int wmax = __reduce_max_sync(0xffffffffu, work), wsum = __reduce_add_sync(0xffffffffu, min(work, 1 << 20));
         if (wmax <= (1 << 20) && 2ll * wmax * __popc(ne) <= 3ll * wsum) {
             float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            for (int r = 0; r < G.nrows; ++r) {
+            const int my_rows = nrows > 0 ? G.nrows : 0;  // (G is only defined for lanes that own a visible Gaussian)
+            for (int r = 0; r < my_rows; ++r) {
                 if (use_last) walk_row_bwd<true, ALIGNED>(G, G.ylo + r, cfg.width, tw, wpix, last_depth, last_gid, tile_stop, v);
                 else walk_row_bwd<false, ALIGNED>(G, G.ylo + r, cfg.width, tw, wpix, nullptr, nullptr, nullptr, v);
             }
