@@ -58,6 +58,8 @@ def parse_args():
                          "populate / densify: EdgeGaussianSplatting.sort_gaussians_morton)")
     ap.add_argument("--pipeline", default="auto", choices=["auto", "splat", "tiles+splat", "tiles"],
                     help="fused-step pipeline (edge_gs.enqueue_raster_step); auto = what training would run")
+    ap.add_argument("--exchange-ranges", type=int, default=1,
+                    help="N > 1: Gaussian ranges of the backward whose exchange overlaps the next range (library exchange only)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "symm", "symm-p2p", "nccl", "native-nccl"],
                     help="N > 1: gradient exchange -- the library's symmetric-memory kernel (default) or NCCL (A/B)")
     return ap.parse_args()
@@ -276,7 +278,8 @@ def bench_regime(args, regime, ctx):
     if not args.no_morton:
         perm = model.sort_gaussians_morton()   # once, like after a densify; parity below maps back through `perm`
 
-    step = GraphedRasterStep(model, W, H, n_slots=V, gt_dtype=torch.uint8, allreduce=world > 1, exchange=args.exchange)
+    step = GraphedRasterStep(model, W, H, n_slots=V, gt_dtype=torch.uint8, allreduce=world > 1, exchange=args.exchange,
+                             exchange_ranges=args.exchange_ranges)
     host_vm = [torch.from_numpy(vms[v]).pin_memory() for v in my_views]
     host_K = [torch.from_numpy(Ks[v]).pin_memory() for v in my_views]
     host_gt = [torch.from_numpy(g).pin_memory() for g in gts_u8]

@@ -23,7 +23,7 @@ EG_FLAG_FRONT_SORT = 16
 
 EXPORTS = ["eg_last_error", "eg_abi_version", "eg_tile_grid", "eg_project_fwd", "eg_bin", "eg_raster_fwd",
            "eg_raster_bwd", "eg_project_bwd", "eg_splat_bwd", "eg_make_seed", "eg_splat_fwd", "eg_splat_resolve", "eg_emit_flagged",
-           "eg_comm_unique_id", "eg_comm_init", "eg_comm_destroy", "eg_comm_allreduce", "eg_allreduce_symm", "eg_allreduce_flag_words",
+           "eg_comm_unique_id", "eg_comm_init", "eg_comm_destroy", "eg_comm_allreduce", "eg_allreduce_symm", "eg_allreduce_symm_segs", "eg_allreduce_flag_words",
            "eg_grad_layout", "eg_adam_multi", "eg_gather_rows", "eg_tile_capacity_for", "eg_workspace_sizes_for", "eg_workspace_bytes", "eg_reg_fwd_bwd", "eg_knn_workspace_bytes", "eg_knn", "eg_adam_step",
            "eg_projecting_fraction"]
 
@@ -91,6 +91,7 @@ def load(build_if_missing: bool = True):
     lib.eg_comm_allreduce.argtypes = [P, c_int64, P, P]
     lib.eg_allreduce_symm.argtypes = [P, P, P, c_int64, c_int, c_int, c_int, P]
     lib.eg_allreduce_flag_words.argtypes = [c_int]
+    lib.eg_allreduce_symm_segs.argtypes = [P, P, P, c_int, POINTER(c_int64), POINTER(c_int64), c_int, c_int, c_int, P]
     lib.eg_grad_layout.argtypes = [c_int, POINTER(c_int64)]
     lib.eg_tile_capacity_for.argtypes = [c_int64, c_int, c_int]
     lib.eg_workspace_sizes_for.argtypes = [cfgp, c_int, c_int, POINTER(EgWorkspaceSizes)]

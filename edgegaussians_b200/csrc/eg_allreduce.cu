@@ -33,6 +33,21 @@ struct ArPeers {
     uint32_t *flags[AR_MAX_RANKS];  // peer-mapped flag areas, by rank: [grid][AR_MAX_RANKS] words
 };
 
+// The reduced index space: up to 4 segments of the buffer (the slices of means | scales | quats | opacities that hold a
+// Gaussian range), concatenated, in float4 units.
+struct ArSegs {
+    long long off4[4];    // first float4 of each segment in the buffer
+    long long first4[5];  // prefix of the segment lengths (float4)
+    int n;
+};
+__device__ __forceinline__ long long seg_index(const ArSegs &sg, const long long i) {
+    int s = 0;
+#pragma unroll
+    for (int k = 1; k < 4; ++k)
+        if (k < sg.n && i >= sg.first4[k]) s = k;
+    return sg.off4[s] + (i - sg.first4[s]);
+}
+
 __device__ __forceinline__ uint32_t cas_release_sys(uint32_t *addr, uint32_t cmp, uint32_t val) {
     uint32_t old;
     asm volatile("atom.global.release.sys.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(addr), "r"(cmp), "r"(val) : "memory");
@@ -73,7 +88,8 @@ __device__ __forceinline__ void mc_st(float *mc_addr, const float4 v) {
 // microseconds, so the bytes in flight (threads x UNROLL x 16 B) are what sets the rate, not the instruction count.
 template <bool MULTICAST, int UNROLL>
 __global__ void __launch_bounds__(AR_THREADS) allreduce_kernel(const ArPeers peers, float *__restrict__ mc_buf,
-                                                               const long long n4, const int rank, const int world) {
+                                                               const ArSegs sg, const int rank, const int world) {
+    const long long n4 = sg.first4[sg.n];
     rank_barrier(peers, rank, world);
     const long long per = (n4 + world - 1) / world;
     const long long lo = (long long)rank * per, hi = (lo + per < n4) ? lo + per : n4;
@@ -84,10 +100,10 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_kernel(const ArPeers pee
             float4 v[UNROLL];
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u)
-                if (i0 + u * stride < hi) v[u] = mc_ld_reduce(reinterpret_cast<const float *>(mc4 + i0 + u * stride));
+                if (i0 + u * stride < hi) v[u] = mc_ld_reduce(reinterpret_cast<const float *>(mc4 + seg_index(sg, i0 + u * stride)));
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u)
-                if (i0 + u * stride < hi) mc_st(reinterpret_cast<float *>(mc4 + i0 + u * stride), v[u]);
+                if (i0 + u * stride < hi) mc_st(reinterpret_cast<float *>(mc4 + seg_index(sg, i0 + u * stride)), v[u]);
         }
     } else {
         constexpr int PU = UNROLL >= 4 ? 2 : 1;  // elements per thread and iteration: PU x world loads in flight
@@ -98,7 +114,7 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_kernel(const ArPeers pee
 #pragma unroll
                 for (int r = 0; r < AR_MAX_RANKS; ++r)
                     if (r < world && i0 + u * stride < hi)
-                        v[u][r] = __ldcg(reinterpret_cast<const float4 *>(peers.buf[r]) + i0 + u * stride);
+                        v[u][r] = __ldcg(reinterpret_cast<const float4 *>(peers.buf[r]) + seg_index(sg, i0 + u * stride));
 #pragma unroll
             for (int u = 0; u < PU; ++u) {
                 if (i0 + u * stride >= hi) continue;
@@ -108,7 +124,7 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_kernel(const ArPeers pee
                     if (r < world) { acc.x += v[u][r].x; acc.y += v[u][r].y; acc.z += v[u][r].z; acc.w += v[u][r].w; }
 #pragma unroll
                 for (int r = 0; r < AR_MAX_RANKS; ++r)
-                    if (r < world) __stcg(reinterpret_cast<float4 *>(peers.buf[r]) + i0 + u * stride, acc);
+                    if (r < world) __stcg(reinterpret_cast<float4 *>(peers.buf[r]) + seg_index(sg, i0 + u * stride), acc);
             }
         }
     }
@@ -120,17 +136,30 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_kernel(const ArPeers pee
 
 extern "C" int eg_allreduce_flag_words(int grid) { return (grid > 0 ? grid : 0) * AR_MAX_RANKS; }
 
-extern "C" int eg_allreduce_symm(float *const *peer_bufs, float *mc_buf, uint32_t *const *peer_flags, int64_t count,
-                                 int rank, int world, int grid, void *stream) {
+extern "C" int eg_allreduce_symm_segs(float *const *peer_bufs, float *mc_buf, uint32_t *const *peer_flags, int n_segs,
+                                      const int64_t *seg_offsets, const int64_t *seg_counts, int rank, int world, int grid,
+                                      void *stream) {
     if (peer_bufs == nullptr || peer_flags == nullptr || world < 1 || world > AR_MAX_RANKS || rank < 0 || rank >= world) {
         eg_set_error("eg_allreduce_symm: bad arguments (world %d, rank %d; at most %d ranks)", world, rank, AR_MAX_RANKS);
         return 1;
     }
-    if (count < 0 || (count & 3) != 0) {
-        eg_set_error("eg_allreduce_symm: count must be a multiple of 4 floats (eg_grad_layout pads to that)");
+    if (n_segs < 1 || n_segs > 4 || seg_offsets == nullptr || seg_counts == nullptr) {
+        eg_set_error("eg_allreduce_symm: 1..4 segments");
         return 1;
     }
-    if (world == 1 || count == 0) return 0;
+    ArSegs sg;
+    sg.n = n_segs;
+    sg.first4[0] = 0;
+    for (int k = 0; k < 4; ++k) {
+        const long long off = k < n_segs ? seg_offsets[k] : 0, cnt = k < n_segs ? seg_counts[k] : 0;
+        if (off < 0 || cnt < 0 || (off & 3) != 0 || (cnt & 3) != 0) {
+            eg_set_error("eg_allreduce_symm: segment offsets and counts must be multiples of 4 floats (eg_grad_layout pads to that)");
+            return 1;
+        }
+        sg.off4[k] = off / 4;
+        sg.first4[k + 1] = sg.first4[k] + cnt / 4;
+    }
+    if (world == 1 || sg.first4[n_segs] == 0) return 0;
     if (grid <= 0) grid = 148;  // nothing else runs at the tail of a step: one CTA per SM
     static const int unroll = getenv("EG_AR_UNROLL") ? atoi(getenv("EG_AR_UNROLL")) : 8;  // tuning knob (2 / 4 / 8)
     ArPeers peers;
@@ -147,7 +176,7 @@ extern "C" int eg_allreduce_symm(float *const *peer_bufs, float *mc_buf, uint32_
         return 1;
     }
     cudaStream_t s = (cudaStream_t)stream;
-#define EG_AR_LAUNCH(MC, U) allreduce_kernel<MC, U><<<grid, AR_THREADS, 0, s>>>(peers, mc_buf, count / 4, rank, world)
+#define EG_AR_LAUNCH(MC, U) allreduce_kernel<MC, U><<<grid, AR_THREADS, 0, s>>>(peers, mc_buf, sg, rank, world)
     if (mc_buf != nullptr) {
         if (unroll <= 2) EG_AR_LAUNCH(true, 2); else if (unroll <= 4) EG_AR_LAUNCH(true, 4); else EG_AR_LAUNCH(true, 8);
     } else {
@@ -155,4 +184,10 @@ extern "C" int eg_allreduce_symm(float *const *peer_bufs, float *mc_buf, uint32_
     }
 #undef EG_AR_LAUNCH
     return eg_check_launch("eg_allreduce_symm");
+}
+
+extern "C" int eg_allreduce_symm(float *const *peer_bufs, float *mc_buf, uint32_t *const *peer_flags, int64_t count,
+                                 int rank, int world, int grid, void *stream) {
+    const int64_t off = 0;
+    return eg_allreduce_symm_segs(peer_bufs, mc_buf, peer_flags, 1, &off, &count, rank, world, grid, stream);
 }

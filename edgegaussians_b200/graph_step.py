@@ -29,7 +29,7 @@ PIPELINES = ["splat", "tiles+splat", "tiles"]
 class GraphedRasterStep:
     def __init__(self, model: EdgeGaussianSplatting, width: int, height: int, n_slots: int, gt_dtype=torch.uint8,
                  loss_weight: float = 1.0, accumulate_absgrad: bool = True, allreduce_group=None, allreduce: bool = False,
-                 exchange: str = "auto", loss_mode: str = "whole"):
+                 exchange: str = "auto", loss_mode: str = "whole", exchange_ranges: int = 1):
         dev = model.means.device
         self.model, self.W, self.H, self.n_slots = model, width, height, n_slots
         self.loss_weight, self.accumulate_absgrad = loss_weight, accumulate_absgrad
@@ -41,6 +41,14 @@ class GraphedRasterStep:
         if exchange not in ("auto", "symm", "symm-p2p", "nccl", "native-nccl"):
             raise ValueError(f"unknown exchange {exchange!r}")
         self.exchange_mode = exchange
+        # Gaussian-major backward: gradients become final range by range, so with exchange_ranges > 1 the backward is
+        # launched in that many Gaussian ranges and the exchange kernel of a finished range runs on a (high-priority)
+        # side stream while the next range is computed -- all inside the captured graph; only the last range's
+        # exchange is exposed.  (Round 1 tried this with NCCL collectives and lost: an NCCL kernel per range costs its
+        # fixed latency and takes the SMs it wants; the library kernel is one small launch per range.)
+        self.exchange_ranges = max(1, int(exchange_ranges))
+        self.comm_stream = torch.cuda.Stream(device=dev, priority=-1) if allreduce else None
+        self.ranged = False
         self.exchange = None      # parallel.SymmetricExchange (owns ws.grads) when the library kernel carries the sum
         self.native_comm = None   # parallel.NativeComm for exchange="native-nccl"
         self.graphs: Dict[int, torch.cuda.CUDAGraph] = {}
@@ -60,12 +68,12 @@ class GraphedRasterStep:
         import torch.distributed as dist
         return dist.is_initialized() and dist.get_world_size(self.allreduce_group) > 1
 
-    def _enqueue(self, slot: int, stage_cb=None, accumulate_absgrad=None):
+    def _enqueue(self, slot: int, stage_cb=None, accumulate_absgrad=None, parts="all"):
         acc = self.accumulate_absgrad if accumulate_absgrad is None else accumulate_absgrad
         return self.model.enqueue_raster_step(self.viewmats[slot], self.Ks[slot], self.W, self.H, self.gts[slot],
                                               loss_weight=self.loss_weight, accumulate_absgrad=acc,
                                               capacity=self._capacity, stage_cb=stage_cb, loss_mode=self.loss_mode,
-                                              view_slot=slot)
+                                              view_slot=slot, parts=parts)
 
     # ------------------------------------------------------------------ exchange
     def _setup_exchange(self) -> None:
@@ -94,7 +102,9 @@ class GraphedRasterStep:
         if not self._distributed():
             return "none"
         if self.exchange is not None:
-            return f"eg_allreduce_symm inside the graph ({self.exchange.kind}, {self.exchange.grid} CTAs)"
+            how = (f"{self.exchange_ranges} Gaussian ranges, each exchanged on a side stream while the next range's backward runs"
+                   if self.ranged else "one launch behind the backward")
+            return f"eg_allreduce_symm inside the graph ({self.exchange.kind}, {self.exchange.grid} CTAs; {how})"
         if self.native_comm is not None:
             return "ncclAllReduce through libedgegs' communicator, after the replay"
         return "torch.distributed all_reduce (NCCL), after the replay"
@@ -139,10 +149,26 @@ class GraphedRasterStep:
             self.calibrate()
         g = torch.cuda.CUDAGraph()
         torch.cuda.synchronize()
+        self.ranged = (self.exchange is not None and self.exchange_ranges > 1 and stage_cb is None
+                       and self.model.current_pipeline() != "tiles")
         with torch.cuda.graph(g):
-            ws = self._enqueue(slot, stage_cb=stage_cb)
-            if self.exchange is not None and stage_cb is None:
-                self.exchange.allreduce_()
+            if self.ranged:
+                ws = self._enqueue(slot, parts="forward")
+                main, side = torch.cuda.current_stream(), self.comm_stream
+                for g0, g1 in self.exchange.gaussian_ranges(ws.N, self.exchange_ranges):
+                    self.model.enqueue_backward_range(ws, g0, g1)
+                    ev = torch.cuda.Event()
+                    ev.record(main)
+                    side.wait_event(ev)
+                    with torch.cuda.stream(side):
+                        self.exchange.allreduce_range_(ws.N, g0, g1, grid=self.exchange.grid_ranged)
+                done = torch.cuda.Event()
+                done.record(side)
+                main.wait_event(done)   # the optimizer / next step needs the reduced gradients
+            else:
+                ws = self._enqueue(slot, stage_cb=stage_cb)
+                if self.exchange is not None and stage_cb is None:
+                    self.exchange.allreduce_()
         assert ws is self.ws, "workspace changed during capture"
         if stage_cb is None:
             self.graphs[slot] = g

@@ -75,6 +75,8 @@ class SymmetricExchange:
         assert self.numel % 4 == 0, "the flat gradient buffer is padded to 16 bytes (layout.grad_numel)"
         # one CTA per SM by default (nothing else runs at the tail of a step); EG_AR_GRID overrides for tuning
         self.grid = int(grid) if grid > 0 else int(os.environ.get("EG_AR_GRID", "148"))
+        # the ranged exchange shares the SMs with the backward of the next range: fewer CTAs
+        self.grid_ranged = min(self.grid, int(os.environ.get("EG_AR_GRID_RANGED", "74")))
         self.buf = symm_mem.empty(self.numel, dtype=torch.float32, device=device)
         self.buf.zero_()
         self._hdl = symm_mem.rendezvous(self.buf, group)
@@ -95,6 +97,32 @@ class SymmetricExchange:
             mc += delta
         self.multicast_ptr = mc
         self.kind = "multimem (switch-side reduction)" if mc else "peer loads/stores"
+
+    @staticmethod
+    def gaussian_ranges(n: int, n_ranges: int, align: int = 128):
+        """[0, n) in at most ``n_ranges`` contiguous Gaussian ranges whose inner boundaries are multiples of ``align``
+        (the Gaussians one CTA of eg_splat_bwd owns; also keeps every slice 16-byte aligned)."""
+        n_ranges = max(1, int(n_ranges))
+        per = -(-n // n_ranges)
+        per = -(-per // align) * align
+        return [(b, min(n, b + per)) for b in range(0, n, per)]
+
+    def allreduce_range_(self, n: int, g0: int, g1: int, grid: int = 0) -> None:
+        """In-place sum over the ranks of the gradients of the Gaussians [g0, g1) only: the four slices of the flat buffer
+        (means | scales | quats | opacities, layout.grad_layout) as ONE launch (eg_allreduce_symm_segs).  ``g0`` must be a
+        multiple of 4; a range that ends at ``n`` is extended over the layout's zero padding."""
+        import ctypes
+        from . import _lib
+        from .layout import padded
+        assert g0 % 4 == 0 and (g1 == n or g1 % 4 == 0), "range boundaries must keep the slices 16-byte aligned"
+        offs = grad_layout(n)
+        g1p = padded(n) if g1 == n else g1
+        seg_off = (ctypes.c_int64 * 4)(*[offs[k] + w * g0 for k, w in enumerate((3, 3, 4, 1))])
+        seg_cnt = (ctypes.c_int64 * 4)(*[w * (g1p - g0) for w in (3, 3, 4, 1)])
+        _lib.check(self.lib.eg_allreduce_symm_segs(self._bufs, ctypes.c_void_p(self.multicast_ptr or None), self._flagp, 4,
+                                                   seg_off, seg_cnt, self.rank, self.world, int(grid) if grid > 0 else self.grid,
+                                                   ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                   "eg_allreduce_symm_segs")
 
     def allreduce_(self, count: Optional[int] = None) -> None:
         """In-place sum of the first ``count`` floats (default: all) over the ranks, enqueued on the current stream."""

@@ -264,6 +264,12 @@ int eg_splat_bwd(const eg_config *cfg, const float *means, const float *quats, c
 int eg_allreduce_flag_words(int grid);
 int eg_allreduce_symm(float *const *peer_bufs, float *mc_buf, uint32_t *const *peer_flags, int64_t count, int rank,
                       int world, int grid, void *stream);
+/* the same over 1..4 segments (offset, count in floats, multiples of 4; HOST arrays) of the buffer: the slices of
+ * means | scales | quats | opacities that hold one Gaussian range -- eg_splat_bwd finishes its gradients range by
+ * range, so the exchange of a finished range can run on a side stream while the next range is computed. */
+int eg_allreduce_symm_segs(float *const *peer_bufs, float *mc_buf, uint32_t *const *peer_flags, int n_segs,
+                           const int64_t *seg_offsets, const int64_t *seg_counts, int rank, int world, int grid,
+                           void *stream);
 int eg_comm_unique_id(void *id128);
 int eg_comm_init(const void *id128, int rank, int world, void **comm_out);
 int eg_comm_destroy(void *comm);

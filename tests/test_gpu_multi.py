@@ -109,7 +109,11 @@ def _step_worker(rank, world, port, out_dir, exchange):
         gts = [synth.make_edge_map_u8(W, H, v) for v in range(world)]
         model = EdgeGaussianSplatting(device=dev)
         model.set_params(m, s, q, o, viewcams=[OpenCVCamera.from_matrices(H, W, Ks[v], vms[v]).to(dev) for v in range(world)])
-        step = GraphedRasterStep(model, W, H, n_slots=1, allreduce=True, exchange=exchange)
+        ranges = 1
+        if "-ranged" in exchange:   # e.g. "symm-ranged4": backward in 4 Gaussian ranges, exchanges on a side stream
+            exchange, r = exchange.split("-ranged")
+            ranges = int(r)
+        step = GraphedRasterStep(model, W, H, n_slots=1, allreduce=True, exchange=exchange, exchange_ranges=ranges)
         step.set_view(0, torch.from_numpy(vms[rank]), torch.from_numpy(Ks[rank]), torch.from_numpy(gts[rank]), non_blocking=False)
         step.calibrate()
         for _ in range(3):      # graph replays: forward + backward + exchange
@@ -136,7 +140,7 @@ def _step_worker(rank, world, port, out_dir, exchange):
 
 @pytest.mark.skipif(N_GPUS < 2, reason="needs >= 2 GPUs")
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("exchange", ["symm", "symm-p2p", "nccl"])
+@pytest.mark.parametrize("exchange", ["symm", "symm-p2p", "nccl", "symm-ranged4", "symm-p2p-ranged3"])
 def test_sharded_step_gradients_equal_sum_of_views(tmp_path, exchange):
     import torch.multiprocessing as mp
     world = min(N_GPUS, 8)
@@ -146,3 +150,5 @@ def test_sharded_step_gradients_equal_sum_of_views(tmp_path, exchange):
         print(f"rank {r}: {res['kind'][0]}: max err {res['err'][0]:.3e} of {res['err'][1]:.3e}")
         assert int(res["bad"][0]) == 0
         assert float(res["factor"][0]) == 4.0      # three replays advanced the abs-grad normaliser on every rank
+        if "ranged" in exchange:
+            assert "Gaussian ranges" in str(res["kind"][0])
