@@ -60,8 +60,9 @@ def parse_args():
                     help="fused-step pipeline (edge_gs.enqueue_raster_step); auto = what training would run")
     ap.add_argument("--exchange-ranges", type=int, default=1,
                     help="N > 1: Gaussian ranges of the backward whose exchange overlaps the next range (library exchange only)")
-    ap.add_argument("--exchange", default="auto", choices=["auto", "symm", "symm-p2p", "nccl", "native-nccl"],
-                    help="N > 1: gradient exchange -- the library's symmetric-memory kernel (default) or NCCL (A/B)")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "push", "push-p2p", "symm", "symm-p2p", "nccl", "native-nccl"],
+                    help="N > 1: gradient exchange -- push form fused into the backward's stores (default), the library's "
+                         "all-reduce kernel over symmetric memory (symm*), or NCCL (A/B)")
     return ap.parse_args()
 
 
@@ -418,7 +419,12 @@ def bench_regime(args, regime, ctx):
         if step.exchange is not None:
             # exchange kernel alone (all ranks enter together: its own in-kernel barriers line the ranks up)
             ex0, ex1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ex0.record(); step.exchange.allreduce_(); ex1.record()
+            ex0.record()
+            if step.exchange.push is not None:
+                step.exchange.reduce_bcast_()   # the part of the push form that is not hidden behind the backward
+            else:
+                step.exchange.allreduce_()
+            ex1.record()
         torch.cuda.synchronize()
         if names is None:
             names = [k for k in evs if k != "begin"]   # stage order as enqueued (dicts keep insertion order)

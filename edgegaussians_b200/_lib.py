@@ -25,7 +25,8 @@ EXPORTS = ["eg_last_error", "eg_abi_version", "eg_tile_grid", "eg_project_fwd", 
            "eg_raster_bwd", "eg_project_bwd", "eg_splat_bwd", "eg_make_seed", "eg_splat_fwd", "eg_splat_resolve", "eg_emit_flagged",
            "eg_comm_unique_id", "eg_comm_init", "eg_comm_destroy", "eg_comm_allreduce", "eg_allreduce_symm", "eg_allreduce_symm_segs", "eg_allreduce_flag_words",
            "eg_grad_layout", "eg_adam_multi", "eg_gather_rows", "eg_tile_capacity_for", "eg_workspace_sizes_for", "eg_workspace_bytes", "eg_reg_fwd_bwd", "eg_knn_workspace_bytes", "eg_knn", "eg_adam_step",
-           "eg_projecting_fraction"]
+           "eg_projecting_fraction", "eg_exchange_push_per", "eg_exchange_stage_floats", "eg_splat_bwd_push", "eg_project_bwd_push",
+           "eg_exchange_reduce_bcast", "eg_exchange_push_zero"]
 
 
 class EgConfig(Structure):
@@ -48,6 +49,11 @@ EG_PIPE = {"splat": 0, "tiles+splat": 1, "tiles": 2}
 class EgAdamSegment(Structure):
     _fields_ = [("param", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p), ("grad_offset", c_int64),
                 ("count", c_int64)]
+
+
+class EgPushTarget(Structure):
+    """eg_push_target (include/edgegs.h): where the push form of the exchange stores a rank's gradients."""
+    _fields_ = [("stage", c_void_p * 8), ("per", c_int32), ("rank", c_int32), ("world", c_int32), ("reserved", c_int32)]
 
 
 class EgRowArray(Structure):
@@ -92,6 +98,13 @@ def load(build_if_missing: bool = True):
     lib.eg_allreduce_symm.argtypes = [P, P, P, c_int64, c_int, c_int, c_int, P]
     lib.eg_allreduce_flag_words.argtypes = [c_int]
     lib.eg_allreduce_symm_segs.argtypes = [P, P, P, c_int, POINTER(c_int64), POINTER(c_int64), c_int, c_int, c_int, P]
+    pushp = POINTER(EgPushTarget)
+    lib.eg_exchange_push_per.argtypes = [c_int, c_int]
+    lib.eg_exchange_stage_floats.argtypes = [c_int, c_int]
+    lib.eg_splat_bwd_push.argtypes = [cfgp] + [P] * 9 + [c_float] + [P] * 4 + [c_int, c_int, pushp, P, P]
+    lib.eg_project_bwd_push.argtypes = [cfgp] + [P] * 9 + [c_int, pushp, P, P]
+    lib.eg_exchange_reduce_bcast.argtypes = [pushp, P, P, P, c_int, c_int, P]
+    lib.eg_exchange_push_zero.argtypes = [pushp, c_int, P]
     lib.eg_grad_layout.argtypes = [c_int, POINTER(c_int64)]
     lib.eg_tile_capacity_for.argtypes = [c_int64, c_int, c_int]
     lib.eg_workspace_sizes_for.argtypes = [cfgp, c_int, c_int, POINTER(EgWorkspaceSizes)]
@@ -108,6 +121,7 @@ def load(build_if_missing: bool = True):
         getattr(lib, name).restype = c_int
     lib.eg_knn_workspace_bytes.restype = ctypes.c_size_t
     lib.eg_workspace_bytes.restype = ctypes.c_size_t
+    lib.eg_exchange_stage_floats.restype = c_int64
     _lib = lib
     return lib
 

@@ -132,6 +132,79 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_kernel(const ArPeers pee
     rank_barrier(peers, rank, world);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Push form (eg_push_target, include/edgegs.h): the backward's own gradient stores carry the reduce-scatter.
+// Rank o OWNS the Gaussians [o * per, (o + 1) * per); its staging area holds one slot per source rank,
+//     slot s = means [3 per] | scales [3 per] | quats [4 per] | opacities [per]   (floats, Gaussian index relative to o * per),
+// and eg_splat_bwd_push / eg_project_bwd_push of rank s store the gradients of an owned Gaussian straight into slot s of
+// its owner (plain 128-byte-coalesced peer stores, fire-and-forget, spread over the whole backward).  What is left for
+// this kernel, after a rank barrier: the owner adds its `world` LOCAL slots in rank order (one rank computes each sum:
+// every replica receives the same bits) and broadcasts the sum into the flat gradient buffer of every rank
+// (multimem.st through the switch, or `world` peer stores).  Per GPU the links carry one buffer length inbound
+// during the backward (hidden) and one inbound here, against two exposed lengths each way for the pull form above.
+// ---------------------------------------------------------------------------------------------------------------
+struct PushSegs {
+    long long src4[4];    // first float4 of each segment inside a slot
+    long long dst4[4];    // first float4 of the owner's part of each segment in the flat buffer
+    long long first4[5];  // prefix of the segment lengths (float4) of the owner's range
+    long long slot4;      // slot stride (float4)
+};
+
+template <bool MULTICAST, int PU>
+__global__ void __launch_bounds__(AR_THREADS) push_reduce_kernel(const ArPeers peers, float *__restrict__ mc_buf,
+                                                                 const float *__restrict__ stage, const PushSegs sg,
+                                                                 const int rank, const int world) {
+    rank_barrier(peers, rank, world);   // every peer's backward (earlier on its stream) has stored into my slots
+    const long long n4 = sg.first4[4];
+    const long long stride = (long long)gridDim.x * AR_THREADS;
+    const float4 *st4 = reinterpret_cast<const float4 *>(stage);
+    for (long long i0 = (long long)blockIdx.x * AR_THREADS + threadIdx.x; i0 < n4; i0 += PU * stride) {
+        float4 v[PU][AR_MAX_RANKS];
+        long long dst[PU];
+#pragma unroll
+        for (int u = 0; u < PU; ++u) {
+            const long long i = i0 + u * stride;
+            if (i >= n4) continue;
+            int s = 0;
+#pragma unroll
+            for (int k = 1; k < 4; ++k)
+                if (i >= sg.first4[k]) s = k;
+            const long long j = i - sg.first4[s];
+            dst[u] = sg.dst4[s] + j;
+#pragma unroll
+            for (int r = 0; r < AR_MAX_RANKS; ++r)
+                if (r < world) v[u][r] = __ldcg(st4 + r * sg.slot4 + sg.src4[s] + j);
+        }
+#pragma unroll
+        for (int u = 0; u < PU; ++u) {
+            if (i0 + u * stride >= n4) continue;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int r = 0; r < AR_MAX_RANKS; ++r)   // fixed rank order, summed once (by the owner)
+                if (r < world) { acc.x += v[u][r].x; acc.y += v[u][r].y; acc.z += v[u][r].z; acc.w += v[u][r].w; }
+            if (MULTICAST) {
+                mc_st(reinterpret_cast<float *>(reinterpret_cast<float4 *>(mc_buf) + dst[u]), acc);
+            } else {
+#pragma unroll
+                for (int r = 0; r < AR_MAX_RANKS; ++r)
+                    if (r < world) __stcg(reinterpret_cast<float4 *>(peers.buf[r]) + dst[u], acc);
+            }
+        }
+    }
+    __threadfence_system();
+    rank_barrier(peers, rank, world);   // the slices the peers own have arrived in my buffer
+}
+
+// an idle rank of a ragged step contributes zeros: clear my slot in every owner's staging area
+__global__ void __launch_bounds__(AR_THREADS) push_zero_kernel(const eg_push_target push, const long long slot4) {
+    const long long stride = (long long)gridDim.x * AR_THREADS;
+    for (int o = 0; o < push.world; ++o) {
+        float4 *slot = reinterpret_cast<float4 *>(push.stage[o]) + (long long)push.rank * slot4;
+        for (long long i = (long long)blockIdx.x * AR_THREADS + threadIdx.x; i < slot4; i += stride)
+            __stcg(slot + i, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+}
+
 }  // namespace
 
 extern "C" int eg_allreduce_flag_words(int grid) { return (grid > 0 ? grid : 0) * AR_MAX_RANKS; }
@@ -190,4 +263,82 @@ extern "C" int eg_allreduce_symm(float *const *peer_bufs, float *mc_buf, uint32_
                                  int rank, int world, int grid, void *stream) {
     const int64_t off = 0;
     return eg_allreduce_symm_segs(peer_bufs, mc_buf, peer_flags, 1, &off, &count, rank, world, grid, stream);
+}
+
+// ---- push form: host side ----
+extern "C" int eg_exchange_push_per(int n, int world) {
+    if (n <= 0 || world <= 0) return 0;
+    const long long each = ((long long)n + world - 1) / world;
+    return (int)((each + 127) / 128 * 128);   // whole CTAs of eg_splat_bwd (128 Gaussians): one owner per CTA, 512-byte runs
+}
+
+extern "C" int64_t eg_exchange_stage_floats(int n, int world) {
+    return (int64_t)world * 11 * (int64_t)eg_exchange_push_per(n, world);
+}
+
+static int push_args_ok(const char *what, const eg_push_target *push, int n) {
+    if (push == nullptr || push->world < 1 || push->world > AR_MAX_RANKS || push->rank < 0 || push->rank >= push->world ||
+        push->per <= 0 || (push->per & 3) != 0 || (long long)push->per * push->world < n) {
+        eg_set_error("%s: bad push target (world, rank, per must cover n = %d Gaussians; per a multiple of 4)", what, n);
+        return 0;
+    }
+    for (int r = 0; r < push->world; ++r)
+        if (push->stage[r] == nullptr || ((uintptr_t)push->stage[r] & 15)) {
+            eg_set_error("%s: staging pointer %d missing or not 16-byte aligned", what, r);
+            return 0;
+        }
+    return 1;
+}
+int eg_push_target_ok(const char *what, const eg_push_target *push, int n) { return push_args_ok(what, push, n); }
+
+extern "C" int eg_exchange_reduce_bcast(const eg_push_target *push, float *const *peer_bufs, float *mc_buf,
+                                        uint32_t *const *peer_flags, int n, int grid, void *stream) {
+    if (!push_args_ok("eg_exchange_reduce_bcast", push, n)) return 1;
+    const int world = push->world, rank = push->rank;
+    if (peer_bufs == nullptr || peer_flags == nullptr) {
+        eg_set_error("eg_exchange_reduce_bcast: peer_bufs and peer_flags are required");
+        return 1;
+    }
+    if (world == 1) return 0;
+    if (grid <= 0) grid = 148;
+    ArPeers peers;
+    for (int r = 0; r < AR_MAX_RANKS; ++r) {
+        peers.buf[r] = r < world ? peer_bufs[r] : nullptr;
+        peers.flags[r] = r < world ? peer_flags[r] : nullptr;
+        if (r < world && (peers.buf[r] == nullptr || peers.flags[r] == nullptr || ((uintptr_t)peers.buf[r] & 15))) {
+            eg_set_error("eg_exchange_reduce_bcast: peer pointer %d missing or not 16-byte aligned", r);
+            return 1;
+        }
+    }
+    if (mc_buf != nullptr && ((uintptr_t)mc_buf & 15)) {
+        eg_set_error("eg_exchange_reduce_bcast: multicast pointer not 16-byte aligned");
+        return 1;
+    }
+    int64_t offs[5];
+    eg_grad_layout(n, offs);
+    const long long per = push->per, np = (n + 3) / 4 * 4;
+    long long cnt = np - (long long)rank * per;   // Gaussians (padded to 4) of my range
+    cnt = cnt < 0 ? 0 : (cnt > per ? per : cnt);
+    const int w[4] = {3, 3, 4, 1};
+    const long long src[4] = {0, 3 * per, 6 * per, 10 * per};
+    PushSegs sg;
+    sg.first4[0] = 0;
+    for (int k = 0; k < 4; ++k) {
+        sg.src4[k] = src[k] / 4;
+        sg.dst4[k] = (offs[k] + (long long)w[k] * rank * per) / 4;
+        sg.first4[k + 1] = sg.first4[k] + (long long)w[k] * cnt / 4;
+    }
+    sg.slot4 = 11 * per / 4;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (mc_buf != nullptr)
+        push_reduce_kernel<true, 2><<<grid, AR_THREADS, 0, s>>>(peers, mc_buf, push->stage[rank], sg, rank, world);
+    else
+        push_reduce_kernel<false, 2><<<grid, AR_THREADS, 0, s>>>(peers, mc_buf, push->stage[rank], sg, rank, world);
+    return eg_check_launch("eg_exchange_reduce_bcast");
+}
+
+extern "C" int eg_exchange_push_zero(const eg_push_target *push, int n, void *stream) {
+    if (!push_args_ok("eg_exchange_push_zero", push, n)) return 1;
+    push_zero_kernel<<<148, AR_THREADS, 0, (cudaStream_t)stream>>>(*push, 11ll * push->per / 4);
+    return eg_check_launch("eg_exchange_push_zero");
 }

@@ -72,6 +72,33 @@ __device__ __forceinline__ void eg_store_quat_grad(float *__restrict__ v_quats, 
     }
 }
 
+// Push form of the gradient exchange (eg_push_target, include/edgegs.h): where the four gradient outputs of Gaussian g
+// go.  world <= 1: the caller's tensors.  Else slot `rank` of the staging area of g's owner o = g / per, laid out
+// means [3 per] | scales [3 per] | quats [4 per] | opacities [per] and indexed by g - o * per -- returned as pointers
+// that are still indexed by g itself.
+struct EgGradOut {
+    float *means, *scales, *quats, *opac;
+};
+__device__ __forceinline__ EgGradOut eg_grad_out(const eg_push_target &push, const int g, float *v_means, float *v_scales,
+                                                 float *v_quats, float *v_opacities) {
+    EgGradOut o;
+    o.means = v_means; o.scales = v_scales; o.quats = v_quats; o.opac = v_opacities;
+    if (push.world > 1) {
+        const int owner = g / push.per;
+        const long long per = push.per, g0 = (long long)owner * per;
+        float *st = push.stage[0];   // select chain: a dynamically indexed kernel-parameter array would be copied to local memory
+#pragma unroll
+        for (int r = 1; r < 8; ++r) st = (owner == r) ? push.stage[r] : st;
+        float *base = st + (long long)push.rank * 11 * per;
+        o.means = base - 3 * g0;
+        o.scales = base + 3 * per - 3 * g0;
+        o.quats = base + 6 * per - 4 * g0;
+        o.opac = base + 10 * per - g0;
+    }
+    return o;
+}
+int eg_push_target_ok(const char *what, const eg_push_target *push, int n);
+
 // Packed fp32x2 arithmetic (Blackwell FFMA2 / FADD2 / FMUL2: two IEEE-rn fp32 operations per issued instruction,
 // operands in even-aligned register pairs).  Element-wise results are bit-identical to the scalar .rn forms.
 typedef unsigned long long eg_f2;

@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(128) project_bwd_kernel(
     const float *__restrict__ Kmat, const float4 *__restrict__ rec, const int2 *__restrict__ gint,
     float4 *__restrict__ grad2d, int zero_grad2d, const float *__restrict__ v_depths, float *__restrict__ v_means,
     float *__restrict__ v_quats, float *__restrict__ v_scales, float *__restrict__ v_opacities,
-    float *__restrict__ absgrad_accum) {
+    float *__restrict__ absgrad_accum, const eg_push_target push) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= cfg.n) return;
     float vm[3] = {0.f, 0.f, 0.f}, vs[3] = {0.f, 0.f, 0.f}, vq[4] = {0.f, 0.f, 0.f, 0.f}, vo = 0.f;
@@ -41,13 +41,35 @@ __global__ void __launch_bounds__(128) project_bwd_kernel(
         eg_project_vjp<RAW>(cfg, cam, r1, g0, g1, mx, my, mz, q4, s, o, v_depths != nullptr ? __ldg(v_depths + g) : 0.0f,
                             vm, vs, vq, vo);
     }
-    v_means[3 * g] = vm[0]; v_means[3 * g + 1] = vm[1]; v_means[3 * g + 2] = vm[2];
-    v_scales[3 * g] = vs[0]; v_scales[3 * g + 1] = vs[1]; v_scales[3 * g + 2] = vs[2];
-    eg_store_quat_grad(v_quats, g, vq);
-    v_opacities[g] = vo;
+    const EgGradOut out = eg_grad_out(push, g, v_means, v_scales, v_quats, v_opacities);  // local tensors, or the owner's slot
+    out.means[3 * g] = vm[0]; out.means[3 * g + 1] = vm[1]; out.means[3 * g + 2] = vm[2];
+    out.scales[3 * g] = vs[0]; out.scales[3 * g + 1] = vs[1]; out.scales[3 * g + 2] = vs[2];
+    eg_store_quat_grad(out.quats, g, vq);
+    out.opac[g] = vo;
 }
 
 }  // namespace
+
+static int project_bwd_launch(const eg_config *cfg, const float *means, const float *quats, const float *scales,
+                              const float *opacities, const float *viewmat, const float *K, const float *rec,
+                              const int32_t *gint, float *grad2d, int zero_grad2d, const float *v_depths,
+                              float *v_means, float *v_quats, float *v_scales, float *v_opacities,
+                              float *absgrad_accum, const eg_push_target &push, void *stream) {
+    if (cfg->n <= 0) return 0;
+    const int block = 128, grid = (cfg->n + block - 1) / block;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (cfg->raw_params)
+        project_bwd_kernel<true><<<grid, block, 0, s>>>(*cfg, means, quats, scales, opacities, viewmat, K,
+                                                        (const float4 *)rec, (const int2 *)gint, (float4 *)grad2d,
+                                                        zero_grad2d, v_depths, v_means, v_quats, v_scales, v_opacities,
+                                                        absgrad_accum, push);
+    else
+        project_bwd_kernel<false><<<grid, block, 0, s>>>(*cfg, means, quats, scales, opacities, viewmat, K,
+                                                         (const float4 *)rec, (const int2 *)gint, (float4 *)grad2d,
+                                                         zero_grad2d, v_depths, v_means, v_quats, v_scales, v_opacities,
+                                                         absgrad_accum, push);
+    return eg_check_launch("eg_project_bwd");
+}
 
 extern "C" int eg_project_bwd(const eg_config *cfg, const float *means, const float *quats, const float *scales,
                               const float *opacities, const float *viewmat, const float *K, const float *rec,
@@ -58,18 +80,21 @@ extern "C" int eg_project_bwd(const eg_config *cfg, const float *means, const fl
         eg_set_error("eg_project_bwd: null config");
         return 1;
     }
-    if (cfg->n <= 0) return 0;
-    const int block = 128, grid = (cfg->n + block - 1) / block;
-    cudaStream_t s = (cudaStream_t)stream;
-    if (cfg->raw_params)
-        project_bwd_kernel<true><<<grid, block, 0, s>>>(*cfg, means, quats, scales, opacities, viewmat, K,
-                                                        (const float4 *)rec, (const int2 *)gint, (float4 *)grad2d,
-                                                        zero_grad2d, v_depths, v_means, v_quats, v_scales, v_opacities,
-                                                        absgrad_accum);
-    else
-        project_bwd_kernel<false><<<grid, block, 0, s>>>(*cfg, means, quats, scales, opacities, viewmat, K,
-                                                         (const float4 *)rec, (const int2 *)gint, (float4 *)grad2d,
-                                                         zero_grad2d, v_depths, v_means, v_quats, v_scales, v_opacities,
-                                                         absgrad_accum);
-    return eg_check_launch("eg_project_bwd");
+    eg_push_target none = {};
+    return project_bwd_launch(cfg, means, quats, scales, opacities, viewmat, K, rec, gint, grad2d, zero_grad2d, v_depths,
+                              v_means, v_quats, v_scales, v_opacities, absgrad_accum, none, stream);
+}
+
+// the same kernel with its gradient stores redirected into the owners' staging slots (eg_push_target)
+extern "C" int eg_project_bwd_push(const eg_config *cfg, const float *means, const float *quats, const float *scales,
+                                   const float *opacities, const float *viewmat, const float *K, const float *rec,
+                                   const int32_t *gint, float *grad2d, int zero_grad2d, const eg_push_target *push,
+                                   float *absgrad_accum, void *stream) {
+    if (cfg == nullptr || !eg_push_target_ok("eg_project_bwd_push", push, cfg->n)) return 1;
+    if (push->world < 2) {
+        eg_set_error("eg_project_bwd_push: needs world >= 2 (a single rank calls eg_project_bwd)");
+        return 1;
+    }
+    return project_bwd_launch(cfg, means, quats, scales, opacities, viewmat, K, rec, gint, grad2d, zero_grad2d, nullptr,
+                              nullptr, nullptr, nullptr, nullptr, absgrad_accum, *push, stream);
 }

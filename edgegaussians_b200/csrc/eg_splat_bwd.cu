@@ -226,7 +226,8 @@ __device__ __forceinline__ void finish_gaussian(const eg_config &cfg, const int 
                                                 const float *__restrict__ viewmat, const float *__restrict__ Kmat,
                                                 float4 *__restrict__ grad2d_out, float *__restrict__ v_means,
                                                 float *__restrict__ v_quats, float *__restrict__ v_scales,
-                                                float *__restrict__ v_opacities, float *__restrict__ absgrad_accum) {
+                                                float *__restrict__ v_opacities, float *__restrict__ absgrad_accum,
+                                                float *stage = nullptr) {
     float vm[3] = {0.f, 0.f, 0.f}, vs[3] = {0.f, 0.f, 0.f}, vq[4] = {0.f, 0.f, 0.f, 0.f}, vo = 0.f;
     float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
     if (has_pairs) {
@@ -249,13 +250,28 @@ __device__ __forceinline__ void finish_gaussian(const eg_config &cfg, const int 
         grad2d_out[2 * g] = g0;
         grad2d_out[2 * g + 1] = g1;
     }
-    v_means[3 * g] = vm[0]; v_means[3 * g + 1] = vm[1]; v_means[3 * g + 2] = vm[2];
-    v_scales[3 * g] = vs[0]; v_scales[3 * g + 1] = vs[1]; v_scales[3 * g + 2] = vs[2];
+    if (stage != nullptr) {
+        // Whole warp, 32 consecutive Gaussians (push form: the stores cross NVLink): transpose the [32,3] means / scales
+        // gradients through `stage` (192 floats of this warp's shared memory) and write them as 24 + 24 full 16-byte
+        // vectors, 384 contiguous bytes each, instead of 6 strided 4-byte stores per lane.
+        const int lane = threadIdx.x & 31;
+        stage[3 * lane] = vm[0]; stage[3 * lane + 1] = vm[1]; stage[3 * lane + 2] = vm[2];
+        stage[96 + 3 * lane] = vs[0]; stage[96 + 3 * lane + 1] = vs[1]; stage[96 + 3 * lane + 2] = vs[2];
+        __syncwarp();
+        if (lane < 24) {
+            const int g0 = g - lane;   // the warp's first Gaussian (a multiple of 32: the vectors are 16-byte aligned)
+            reinterpret_cast<float4 *>(v_means + 3 * g0)[lane] = reinterpret_cast<const float4 *>(stage)[lane];
+            reinterpret_cast<float4 *>(v_scales + 3 * g0)[lane] = reinterpret_cast<const float4 *>(stage + 96)[lane];
+        }
+    } else {
+        v_means[3 * g] = vm[0]; v_means[3 * g + 1] = vm[1]; v_means[3 * g + 2] = vm[2];
+        v_scales[3 * g] = vs[0]; v_scales[3 * g + 1] = vs[1]; v_scales[3 * g + 2] = vs[2];
+    }
     eg_store_quat_grad(v_quats, g, vq);
     v_opacities[g] = vo;
 }
 
-template <bool RAW, bool ALIGNED>
+template <bool RAW, bool ALIGNED, bool PUSH>
 __global__ void __launch_bounds__(SB_WARPS * 32, EG_SB_MINBLOCKS) splat_bwd_kernel(
     const eg_config cfg, const int g_begin, const int g_end, const int tw, const int th, const float *__restrict__ means, const float *__restrict__ quats,
     const float *__restrict__ scales, const float *__restrict__ opacities, const float *__restrict__ viewmat,
@@ -264,7 +280,7 @@ __global__ void __launch_bounds__(SB_WARPS * 32, EG_SB_MINBLOCKS) splat_bwd_kern
     const int *__restrict__ last_gid, const int *__restrict__ tile_stop, const int32_t *__restrict__ status,
     float4 *__restrict__ grad2d_out,
     float *__restrict__ v_means, float *__restrict__ v_quats, float *__restrict__ v_scales,
-    float *__restrict__ v_opacities, float *__restrict__ absgrad_accum, const int opts) {
+    float *__restrict__ v_opacities, float *__restrict__ absgrad_accum, const int opts, const eg_push_target push) {
     __shared__ EgSplatG s_g[SB_WARPS][32];                   // compacted over the Gaussians that have rows
     __shared__ __align__(16) float s_acc[SB_WARPS][32][8];   // same (compact) index
 
@@ -373,9 +389,15 @@ __global__ void __launch_bounds__(SB_WARPS * 32, EG_SB_MINBLOCKS) splat_bwd_kern
     }
 
     // ---------------- phase 3: lane = Gaussian ----------------
+    // (PUSH) vectorised stores need the whole warp on 32 consecutive Gaussians of ONE owner (per is a multiple of 128)
+    const bool vec_out = PUSH && __all_sync(0xffffffffu, live) && ((g - lane) & 31) == 0;
     if (!live) return;
+    EgGradOut out;   // the caller's tensors, or (PUSH) this rank's slot in the staging area of the Gaussian's owner
+    if (PUSH) out = eg_grad_out(push, g, v_means, v_scales, v_quats, v_opacities);
+    else { out.means = v_means; out.scales = v_scales; out.quats = v_quats; out.opac = v_opacities; }
     finish_gaussian<RAW>(cfg, g, nrows > 0, nrows > 0 ? &s_acc[warp][kc][0] : nullptr, seed_scale, opac_eff, r1, means, quats, scales,
-                         opacities, viewmat, Kmat, grad2d_out, v_means, v_quats, v_scales, v_opacities, absgrad_accum);
+                         opacities, viewmat, Kmat, grad2d_out, out.means, out.quats, out.scales, out.opac, absgrad_accum,
+                         vec_out ? reinterpret_cast<float *>(&s_g[warp][0]) : nullptr);  // s_g is dead after phase 2
 }
 
 // per-pixel backward seed of the gsplat-shaped autograd path:  w_p = (sum_ch v_render[p,ch] + v_alpha[p]) * (1 - alpha[p])
@@ -393,12 +415,13 @@ __global__ void __launch_bounds__(256) seed_kernel(long long P, const float *__r
 
 }  // namespace
 
-extern "C" int eg_splat_bwd(const eg_config *cfg, const float *means, const float *quats, const float *scales,
+static int splat_bwd_launch(const eg_config *cfg, const float *means, const float *quats, const float *scales,
                             const float *opacities, const float *viewmat, const float *K, const float *rec,
                             const int32_t *gint, const float *wpix, float seed_scale, const uint32_t *last_depth,
                             const int32_t *last_gid, const int32_t *tile_stop, const int32_t *status,
                             int g_begin, int g_end, float *grad2d_out, float *v_means,
-                            float *v_quats, float *v_scales, float *v_opacities, float *absgrad_accum, void *stream) {
+                            float *v_quats, float *v_scales, float *v_opacities, float *absgrad_accum,
+                            const eg_push_target &push, void *stream) {
     if (cfg == nullptr || cfg->tile_size != EG_TILE) {
         eg_set_error("eg_splat_bwd: tile_size must be %d", EG_TILE);
         return 1;
@@ -424,21 +447,55 @@ extern "C" int eg_splat_bwd(const eg_config *cfg, const float *means, const floa
     cudaStream_t s = (cudaStream_t)stream;
     const bool aligned = (cfg->width % 4 == 0) && (((uintptr_t)wpix & 15) == 0) &&
                          (last_depth == nullptr || ((uintptr_t)last_depth & 15) == 0);
-#define EG_SB_LAUNCH(RAWP, AL)                                                                                       \
-    splat_bwd_kernel<RAWP, AL><<<grid, block, 0, s>>>(*cfg, g_begin, g_end, tw, th, means, quats, scales, opacities, viewmat, K,    \
+#define EG_SB_LAUNCH(RAWP, AL, PU)                                                                                     \
+    splat_bwd_kernel<RAWP, AL, PU><<<grid, block, 0, s>>>(*cfg, g_begin, g_end, tw, th, means, quats, scales, opacities, viewmat, K,    \
                                                       (const float4 *)rec, (const int2 *)gint, wpix, seed_scale,    \
                                                       last_depth, last_gid, tile_stop, status,                      \
                                                       (float4 *)grad2d_out, v_means,                                \
-                                                      v_quats, v_scales, v_opacities, absgrad_accum, opts)
+                                                      v_quats, v_scales, v_opacities, absgrad_accum, opts, push)
     // EG_BWD_OPTS=1 switches the lane = Gaussian path of uniform warps off (A/B measurements)
     static const int opts = getenv("EG_BWD_OPTS") != nullptr ? atoi(getenv("EG_BWD_OPTS")) : 0;
-    if (cfg->raw_params) {
-        if (aligned) EG_SB_LAUNCH(true, true); else EG_SB_LAUNCH(true, false);
+    if (push.world > 1) {
+        if (cfg->raw_params) {
+            if (aligned) EG_SB_LAUNCH(true, true, true); else EG_SB_LAUNCH(true, false, true);
+        } else {
+            if (aligned) EG_SB_LAUNCH(false, true, true); else EG_SB_LAUNCH(false, false, true);
+        }
+    } else if (cfg->raw_params) {
+        if (aligned) EG_SB_LAUNCH(true, true, false); else EG_SB_LAUNCH(true, false, false);
     } else {
-        if (aligned) EG_SB_LAUNCH(false, true); else EG_SB_LAUNCH(false, false);
+        if (aligned) EG_SB_LAUNCH(false, true, false); else EG_SB_LAUNCH(false, false, false);
     }
 #undef EG_SB_LAUNCH
     return eg_check_launch("eg_splat_bwd");
+}
+
+extern "C" int eg_splat_bwd(const eg_config *cfg, const float *means, const float *quats, const float *scales,
+                            const float *opacities, const float *viewmat, const float *K, const float *rec,
+                            const int32_t *gint, const float *wpix, float seed_scale, const uint32_t *last_depth,
+                            const int32_t *last_gid, const int32_t *tile_stop, const int32_t *status,
+                            int g_begin, int g_end, float *grad2d_out, float *v_means,
+                            float *v_quats, float *v_scales, float *v_opacities, float *absgrad_accum, void *stream) {
+    eg_push_target none = {};
+    return splat_bwd_launch(cfg, means, quats, scales, opacities, viewmat, K, rec, gint, wpix, seed_scale, last_depth, last_gid,
+                            tile_stop, status, g_begin, g_end, grad2d_out, v_means, v_quats, v_scales, v_opacities,
+                            absgrad_accum, none, stream);
+}
+
+// the same backward with its gradient stores redirected into the owners' staging slots (eg_push_target)
+extern "C" int eg_splat_bwd_push(const eg_config *cfg, const float *means, const float *quats, const float *scales,
+                                 const float *opacities, const float *viewmat, const float *K, const float *rec,
+                                 const int32_t *gint, const float *wpix, float seed_scale, const uint32_t *last_depth,
+                                 const int32_t *last_gid, const int32_t *tile_stop, const int32_t *status, int g_begin,
+                                 int g_end, const eg_push_target *push, float *absgrad_accum, void *stream) {
+    if (cfg == nullptr || !eg_push_target_ok("eg_splat_bwd_push", push, cfg->n)) return 1;
+    if (push->world < 2) {
+        eg_set_error("eg_splat_bwd_push: needs world >= 2 (a single rank calls eg_splat_bwd)");
+        return 1;
+    }
+    return splat_bwd_launch(cfg, means, quats, scales, opacities, viewmat, K, rec, gint, wpix, seed_scale, last_depth, last_gid,
+                            tile_stop, status, g_begin, g_end, nullptr, nullptr, nullptr, nullptr, nullptr, absgrad_accum,
+                            *push, stream);
 }
 
 extern "C" int eg_make_seed(int64_t n_pixels, const float *alpha, const float *v_render, int v_render_channels,

@@ -584,7 +584,7 @@ class EdgeGaussianSplatting(torch.nn.Module):
 
     def enqueue_raster_step(self, viewmat, K, W, H, gt, *, loss_weight=1.0, accumulate_absgrad=True, capacity=None,
                             want_render=False, stage_cb=None, lazy_sort=None, pipeline=None, parts="all",
-                            loss_mode: str = "whole", view_slot=None) -> RasterStepWorkspace:
+                            loss_mode: str = "whole", view_slot=None, push=None) -> RasterStepWorkspace:
         """Enqueue one fused forward+backward iteration on the current stream. No host sync, no
         allocation after the first call for a given (N, W, H): CUDA-graph capturable.
 
@@ -602,7 +602,11 @@ class EdgeGaussianSplatting(torch.nn.Module):
           "tiles"        eg_raster_fwd with contribution masks + eg_raster_bwd + eg_project_bwd.
 
         ``parts="forward"`` stops after the forward (loss, backward seed); the backward is then issued with
-        :meth:`enqueue_backward_range`."""
+        :meth:`enqueue_backward_range`.
+
+        ``push`` (an ``_lib.EgPushTarget`` of parallel.SymmetricExchange, view-sharded runs only): the backward stores
+        its gradients into the owner ranks' staging slots instead of ws.grads (eg_splat_bwd_push / eg_project_bwd_push);
+        ws.grads then holds the sum over the ranks after ``SymmetricExchange.reduce_bcast_()``."""
         lib = get_engine(self.means.device).lib
         ws = self._workspace(W, H, capacity)
         N = ws.N
@@ -698,13 +702,17 @@ class EdgeGaussianSplatting(torch.nn.Module):
             chk(lib.eg_raster_bwd(c, _p(ws.rec), _p(ws.tile_offsets), _p(ws.flatten_ids), _p(ws.cmask), _p(ws.tile_cnt),
                                   None, None, 0, None, _p(ws.wpix), seed, _p(ws.grad2d), _p(ws.status), s), "eg_raster_bwd")
             cb("raster_bwd")
-            gm, gs, gq, go = split_grads(g, N)
-            chk(lib.eg_project_bwd(c, _p(means), _p(quats), _p(scales), _p(opac), _p(viewmat), _p(K), _p(ws.rec),
-                                   _p(ws.gint), _p(ws.grad2d), 1, None, _p(gm), _p(gq), _p(gs), _p(go), absg, s),
-                "eg_project_bwd")
+            if push is not None:
+                chk(lib.eg_project_bwd_push(c, _p(means), _p(quats), _p(scales), _p(opac), _p(viewmat), _p(K), _p(ws.rec),
+                                            _p(ws.gint), _p(ws.grad2d), 1, ctypes.byref(push), absg, s), "eg_project_bwd_push")
+            else:
+                gm, gs, gq, go = split_grads(g, N)
+                chk(lib.eg_project_bwd(c, _p(means), _p(quats), _p(scales), _p(opac), _p(viewmat), _p(K), _p(ws.rec),
+                                       _p(ws.gint), _p(ws.grad2d), 1, None, _p(gm), _p(gq), _p(gs), _p(go), absg, s),
+                    "eg_project_bwd")
             cb("project_bwd")
         else:
-            self.enqueue_backward_range(ws, 0, N)
+            self.enqueue_backward_range(ws, 0, N, push=push)
             cb("splat_bwd")
         return ws
 
@@ -712,13 +720,21 @@ class EdgeGaussianSplatting(torch.nn.Module):
         """The projection loss of the step that just ran, as a 0-dim device tensor (no sync)."""
         return (ws.loss_sum[0] * ws.loss_scale).float()
 
-    def enqueue_backward_range(self, ws: RasterStepWorkspace, g_begin: int, g_end: int) -> None:
+    def enqueue_backward_range(self, ws: RasterStepWorkspace, g_begin: int, g_end: int, push=None) -> None:
         """eg_splat_bwd for the Gaussians [g_begin, g_end) of the step whose forward was just enqueued: their
-        slices of ws.grads (and of self.absgrads) are final when this launch completes."""
+        slices of ws.grads (and of self.absgrads) are final when this launch completes.  With ``push`` the gradients
+        go to the owner ranks' staging slots instead (eg_splat_bwd_push)."""
         cfg, viewmat, K, seed, accumulate_absgrad = ws.bwd_args
         lib = get_engine(self.means.device).lib
-        gm, gs, gq, go = split_grads(ws.grads, ws.N)
         means, quats, scales, opac = self.means.data, self.quats.data, self.scales.data, self.opacities.data
+        if push is not None:
+            _lib.check(lib.eg_splat_bwd_push(ctypes.byref(cfg), _p(means), _p(quats), _p(scales), _p(opac), _p(viewmat), _p(K),
+                                             _p(ws.rec), _p(ws.gint), _p(ws.wpix), seed, _p(ws.last_depth), _p(ws.last_gid),
+                                             _p(ws.tile_stop) if ws.pipeline == "splat" else None, _p(ws.status),
+                                             int(g_begin), int(g_end), ctypes.byref(push),
+                                             _p(self.absgrads) if accumulate_absgrad else None, _stream()), "eg_splat_bwd_push")
+            return
+        gm, gs, gq, go = split_grads(ws.grads, ws.N)
         _lib.check(lib.eg_splat_bwd(ctypes.byref(cfg), _p(means), _p(quats), _p(scales), _p(opac), _p(viewmat), _p(K),
                                     _p(ws.rec), _p(ws.gint), _p(ws.wpix), seed, _p(ws.last_depth), _p(ws.last_gid),
                                     _p(ws.tile_stop) if ws.pipeline == "splat" else None, _p(ws.status),

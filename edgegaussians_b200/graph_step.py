@@ -6,10 +6,14 @@ training replays a captured graph instead of re-issuing launches from Python.  E
 reads that changes from step to step -- camera matrices and the edge map of the view -- lives in
 static per-slot device buffers that are refreshed by (async) copies before the replay.
 
-View-sharded multi-GPU: the gradient exchange is a kernel of this library over
-symmetric memory (parallel.SymmetricExchange / eg_allreduce_symm) and is captured INSIDE the graph, so one
-replay = forward + backward + exchange.  ``exchange="nccl"`` keeps round 1's torch.distributed all-reduce
-issued behind the replay as the A/B baseline (capturing NCCL inside the graph hangs on this stack).
+View-sharded multi-GPU: the gradient exchange runs on kernels of this library over
+symmetric memory (parallel.SymmetricExchange) and is captured INSIDE the graph, so one replay = forward +
+backward + exchange.  Default ("auto" / "push"): the PUSH form -- the backward kernel itself stores every Gaussian's
+gradients into its owner rank's staging slot over NVLink (the reduce-scatter rides on the backward), and one
+kernel behind it sums the slots and broadcasts the result (eg_exchange_reduce_bcast).  ``"symm"`` / ``"symm-p2p"``:
+the pull form, one all-reduce kernel behind the backward (eg_allreduce_symm).  ``exchange="nccl"`` keeps round 1's
+torch.distributed all-reduce issued behind the replay as the A/B baseline (capturing NCCL inside the graph hangs
+on this stack).
 """
 from __future__ import annotations
 
@@ -38,7 +42,7 @@ class GraphedRasterStep:
         self.Ks = torch.zeros((n_slots, 3, 3), dtype=torch.float32, device=dev)
         self.gts = torch.zeros((n_slots, height, width), dtype=gt_dtype, device=dev)
         self.allreduce, self.allreduce_group = allreduce, allreduce_group
-        if exchange not in ("auto", "symm", "symm-p2p", "nccl", "native-nccl"):
+        if exchange not in ("auto", "push", "push-p2p", "symm", "symm-p2p", "nccl", "native-nccl"):
             raise ValueError(f"unknown exchange {exchange!r}")
         self.exchange_mode = exchange
         # Gaussian-major backward: gradients become final range by range, so with exchange_ranges > 1 the backward is
@@ -68,12 +72,12 @@ class GraphedRasterStep:
         import torch.distributed as dist
         return dist.is_initialized() and dist.get_world_size(self.allreduce_group) > 1
 
-    def _enqueue(self, slot: int, stage_cb=None, accumulate_absgrad=None, parts="all"):
+    def _enqueue(self, slot: int, stage_cb=None, accumulate_absgrad=None, parts="all", push=None):
         acc = self.accumulate_absgrad if accumulate_absgrad is None else accumulate_absgrad
         return self.model.enqueue_raster_step(self.viewmats[slot], self.Ks[slot], self.W, self.H, self.gts[slot],
                                               loss_weight=self.loss_weight, accumulate_absgrad=acc,
                                               capacity=self._capacity, stage_cb=stage_cb, loss_mode=self.loss_mode,
-                                              view_slot=slot, parts=parts)
+                                              view_slot=slot, parts=parts, push=push)
 
     # ------------------------------------------------------------------ exchange
     def _setup_exchange(self) -> None:
@@ -82,11 +86,15 @@ class GraphedRasterStep:
             return
         dev, n = self.model.means.device, grad_numel(self.model.num_points)
         mode = self.exchange_mode
-        if mode in ("auto", "symm", "symm-p2p"):
+        if mode in ("auto", "push", "push-p2p", "symm", "symm-p2p"):
             if self.exchange is None or self.exchange.numel != n:
                 from .parallel import SymmetricExchange
                 try:
-                    self.exchange = SymmetricExchange(n, dev, self.allreduce_group, multicast=mode != "symm-p2p")
+                    self.exchange = SymmetricExchange(n, dev, self.allreduce_group, multicast=not mode.endswith("-p2p"))
+                    # default: the push form -- the backward's own stores carry the reduce-scatter, one reduce +
+                    # broadcast kernel behind it; "symm*": the pull form (one all-reduce kernel behind the backward)
+                    if mode in ("auto", "push", "push-p2p") and self.exchange_ranges <= 1:
+                        self.exchange.enable_push(self.model.num_points)
                 except Exception as e:  # symmetric memory unavailable on this box: say so, fall back to NCCL
                     if mode != "auto":
                         raise
@@ -98,9 +106,18 @@ class GraphedRasterStep:
             from .parallel import NativeComm
             self.native_comm = NativeComm(dev, self.allreduce_group)
 
+    def _ranged(self) -> bool:
+        return (self.exchange is not None and self.exchange.push is None and self.exchange_ranges > 1
+                and self.model.current_pipeline() != "tiles")
+
     def exchange_name(self) -> str:
         if not self._distributed():
             return "none"
+        if self.exchange is not None and self.exchange.push is not None:
+            bc = "multimem.st broadcast" if self.exchange.multicast_ptr else "peer-store broadcast"
+            return (f"push form inside the graph: the backward stores each Gaussian's gradients into its owner rank's staging slot "
+                    f"over NVLink (eg_splat_bwd_push / eg_project_bwd_push), then eg_exchange_reduce_bcast "
+                    f"({bc}, {self.exchange.grid} CTAs)")
         if self.exchange is not None:
             how = (f"{self.exchange_ranges} Gaussian ranges, each exchanged on a side stream while the next range's backward runs"
                    if self.ranged else "one launch behind the backward")
@@ -149,8 +166,7 @@ class GraphedRasterStep:
             self.calibrate()
         g = torch.cuda.CUDAGraph()
         torch.cuda.synchronize()
-        self.ranged = (self.exchange is not None and self.exchange_ranges > 1 and stage_cb is None
-                       and self.model.current_pipeline() != "tiles")
+        self.ranged = self._ranged() and stage_cb is None
         with torch.cuda.graph(g):
             if self.ranged:
                 ws = self._enqueue(slot, parts="forward")
@@ -165,6 +181,9 @@ class GraphedRasterStep:
                 done = torch.cuda.Event()
                 done.record(side)
                 main.wait_event(done)   # the optimizer / next step needs the reduced gradients
+            elif self.exchange is not None and self.exchange.push is not None and stage_cb is None:
+                ws = self._enqueue(slot, push=self.exchange.push)   # gradients go to the owners' staging slots ...
+                self.exchange.reduce_bcast_()                       # ... and come back summed in ws.grads
             else:
                 ws = self._enqueue(slot, stage_cb=stage_cb)
                 if self.exchange is not None and stage_cb is None:
@@ -202,7 +221,13 @@ class GraphedRasterStep:
             self.calibrate()
         self.ws.grads.zero_()
         if self._distributed():
-            if self.exchange is not None:
+            if self.exchange is not None and self.exchange.push is not None:
+                self.exchange.push_zero_()
+                self.exchange.reduce_bcast_()
+            elif self._ranged():   # the same launches (grid, barriers) as the working ranks' captured graphs
+                for g0, g1 in self.exchange.gaussian_ranges(self.ws.N, self.exchange_ranges):
+                    self.exchange.allreduce_range_(self.ws.N, g0, g1, grid=self.exchange.grid_ranged)
+            elif self.exchange is not None:
                 self.exchange.allreduce_()
             elif self.native_comm is not None:
                 self.native_comm.allreduce_(self.ws.grads)

@@ -70,6 +70,8 @@ class SymmetricExchange:
         from . import _lib
         self.lib = _lib.load()
         group = group if group is not None else dist.group.WORLD
+        self._group = group
+        self.push = None       # eg_push_target once enable_push() has run
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.numel = int(numel)
         assert self.numel % 4 == 0, "the flat gradient buffer is padded to 16 bytes (layout.grad_numel)"
@@ -97,6 +99,49 @@ class SymmetricExchange:
             mc += delta
         self.multicast_ptr = mc
         self.kind = "multimem (switch-side reduction)" if mc else "peer loads/stores"
+
+    # ------------------------------------------------------------------ push form (eg_push_target)
+    def enable_push(self, n_gaussians: int) -> None:
+        """Allocate the symmetric staging area of the push form for ``n_gaussians`` (collective): afterwards
+        ``self.push`` is the eg_push_target the backward kernels store through (eg_splat_bwd_push /
+        eg_project_bwd_push) and :meth:`reduce_bcast_` finishes the sum.  The backward's gradient stores then ARE
+        the reduce-scatter: they travel over NVLink while the backward is still running."""
+        import ctypes
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        n = int(n_gaussians)
+        assert grad_numel(n) == self.numel, "the exchange was sized for another Gaussian count"
+        per = int(self.lib.eg_exchange_push_per(n, self.world))
+        floats = int(self.lib.eg_exchange_stage_floats(n, self.world))
+        self.stage = symm_mem.empty(floats, dtype=torch.float32, device=self.buf.device)
+        self.stage.zero_()     # rows past N in the last owner's range are never written: they must add zeros
+        self._shdl = symm_mem.rendezvous(self.stage, self._group)
+        torch.cuda.synchronize(self.buf.device)
+        dist.barrier(self._group)
+        delta = self.stage.data_ptr() - int(self._shdl.buffer_ptrs[self.rank])
+        tgt = _lib.EgPushTarget()
+        for r in range(self.world):
+            tgt.stage[r] = int(self._shdl.buffer_ptrs[r]) + delta
+        tgt.per, tgt.rank, tgt.world = per, self.rank, self.world
+        self.push, self.push_n = tgt, n
+
+    def reduce_bcast_(self) -> None:
+        """Second half of the push form, enqueued on the current stream behind the pushing backward: rank barrier, sum
+        of this rank's ``world`` local slots, broadcast into every rank's ``buf`` (multimem.st / peer stores)."""
+        import ctypes
+        from . import _lib
+        _lib.check(self.lib.eg_exchange_reduce_bcast(ctypes.byref(self.push), self._bufs, ctypes.c_void_p(self.multicast_ptr or None),
+                                                     self._flagp, self.push_n, self.grid,
+                                                     ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                   "eg_exchange_reduce_bcast")
+
+    def push_zero_(self) -> None:
+        """What a rank without a view does instead of a pushing backward: zeros into its slot of every owner."""
+        import ctypes
+        from . import _lib
+        _lib.check(self.lib.eg_exchange_push_zero(ctypes.byref(self.push), self.push_n,
+                                                  ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                   "eg_exchange_push_zero")
 
     @staticmethod
     def gaussian_ranges(n: int, n_ranges: int, align: int = 128):

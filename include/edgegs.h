@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define EG_ABI_VERSION 9
+#define EG_ABI_VERSION 10
 #define EG_CNT_STRIDE 32
 
 enum {
@@ -270,6 +270,41 @@ int eg_allreduce_symm(float *const *peer_bufs, float *mc_buf, uint32_t *const *p
 int eg_allreduce_symm_segs(float *const *peer_bufs, float *mc_buf, uint32_t *const *peer_flags, int n_segs,
                            const int64_t *seg_offsets, const int64_t *seg_counts, int rank, int world, int grid,
                            void *stream);
+/* Push form of the exchange -- the backward's gradient stores ARE the reduce-scatter ("K7
+ * writing into the all-reduce buffer"; no reference counterpart).  Rank o owns the Gaussians [o * per, (o + 1) * per),
+ * per = eg_exchange_push_per(n, world).  Every rank holds a SYMMETRIC staging area of eg_exchange_stage_floats(n, world)
+ * floats (zero-initialised once): `world` slots, slot s = what rank s computed for the owned range, laid out
+ *     means [3 per] | scales [3 per] | quats [4 per] | opacities [per].
+ *   eg_splat_bwd_push / eg_project_bwd_push   the backward kernels of eg_splat_bwd / eg_project_bwd with their four
+ *       gradient outputs redirected: the gradients of Gaussian g go to slot `rank` of stage[g / per] (peer stores over
+ *       NVLink, issued as the Gaussians finish -- the transfer overlaps the backward itself);
+ *   eg_exchange_reduce_bcast   one kernel behind it on the same stream: rank barrier, the owner sums its `world` local
+ *       slots in rank order and broadcasts the result into the flat gradient buffer (eg_grad_layout) of EVERY rank
+ *       (multimem.st through mc_buf when given, else peer stores), rank barrier.  peer_bufs / mc_buf / peer_flags /
+ *       grid as eg_allreduce_symm.  Every rank receives bit-identical sums;
+ *   eg_exchange_push_zero      a rank without a view (ragged last step) contributes zeros instead of a backward.
+ * All calls are asynchronous on `stream`, self-resetting and CUDA-graph capturable. */
+typedef struct eg_push_target {
+    float *stage[8]; /* by owner rank: that rank's staging area as mapped into this process (stage[rank] = local) */
+    int32_t per;     /* Gaussians per owner, a multiple of 128 */
+    int32_t rank;    /* this rank: the slot it writes in every staging area */
+    int32_t world;
+    int32_t reserved;
+} eg_push_target;
+int eg_exchange_push_per(int n, int world);
+int64_t eg_exchange_stage_floats(int n, int world);
+int eg_splat_bwd_push(const eg_config *cfg, const float *means, const float *quats, const float *scales,
+                      const float *opacities, const float *viewmat, const float *K, const float *rec,
+                      const int32_t *gint, const float *wpix, float seed_scale, const uint32_t *last_depth,
+                      const int32_t *last_gid, const int32_t *tile_stop, const int32_t *status, int g_begin, int g_end,
+                      const eg_push_target *push, float *absgrad_accum, void *stream);
+int eg_project_bwd_push(const eg_config *cfg, const float *means, const float *quats, const float *scales,
+                        const float *opacities, const float *viewmat, const float *K, const float *rec,
+                        const int32_t *gint, float *grad2d, int zero_grad2d, const eg_push_target *push,
+                        float *absgrad_accum, void *stream);
+int eg_exchange_reduce_bcast(const eg_push_target *push, float *const *peer_bufs, float *mc_buf,
+                             uint32_t *const *peer_flags, int n, int grid, void *stream);
+int eg_exchange_push_zero(const eg_push_target *push, int n, void *stream);
 int eg_comm_unique_id(void *id128);
 int eg_comm_init(const void *id128, int rank, int world, void **comm_out);
 int eg_comm_destroy(void *comm);

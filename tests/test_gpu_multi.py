@@ -3,9 +3,10 @@
 
   * eg_allreduce_symm (this library's kernel over symmetric memory: multimem switch reduction, and the peer
     load/store variant) == sum over ranks, repeated calls (self-resetting rank barriers), inside a CUDA graph;
-  * GraphedRasterStep with the exchange captured in the graph: every rank ends with the SUM of the ranks'
-    single-GPU per-view gradients (computed again, view by view, on rank 0) -- the multi-GPU parity definition of
-    SURVEY.md section 4 / 8e.
+  * GraphedRasterStep with the exchange captured in the graph -- the push form fused into the backward's stores
+    (eg_splat_bwd_push / eg_project_bwd_push + eg_exchange_reduce_bcast), the pull form, NCCL: every rank ends with
+    the SUM of the ranks' single-GPU per-view gradients (computed again, view by view, on every rank) -- the
+    multi-GPU parity definition of SURVEY.md section 4 / 8e; a ragged step with idle ranks gives rank 0's gradients.
 """
 import os
 import socket
@@ -110,6 +111,9 @@ def _step_worker(rank, world, port, out_dir, exchange):
         model = EdgeGaussianSplatting(device=dev)
         model.set_params(m, s, q, o, viewcams=[OpenCVCamera.from_matrices(H, W, Ks[v], vms[v]).to(dev) for v in range(world)])
         ranges = 1
+        if exchange.endswith("-tiles"):    # the tile pipeline's backward (eg_project_bwd_push) instead of eg_splat_bwd_push
+            exchange = exchange[:-len("-tiles")]
+            model.pipeline = "tiles"
         if "-ranged" in exchange:   # e.g. "symm-ranged4": backward in 4 Gaussian ranges, exchanges on a side stream
             exchange, r = exchange.split("-ranged")
             ranges = int(r)
@@ -131,8 +135,22 @@ def _step_worker(rank, world, port, out_dir, exchange):
         scale = float(acc.abs().max())
         err = (got.double() - acc).abs()
         bad = int((err > 1e-5 * acc.abs() + 1e-6 * scale).sum())
+        # ragged last step: only rank 0 has a view, the others contribute zeros (GraphedRasterStep.idle_step)
+        step.set_view(0, torch.from_numpy(vms[rank]), torch.from_numpy(Ks[rank]), torch.from_numpy(gts[rank]), non_blocking=False)
+        torch.cuda.synchronize()
+        dist.barrier()
+        ws = step.replay(0) if rank == 0 else step.idle_step()
+        torch.cuda.synchronize()
+        got1 = ws.grads.clone()
+        dist.barrier()
+        step.set_view(0, torch.from_numpy(vms[0]), torch.from_numpy(Ks[0]), torch.from_numpy(gts[0]), non_blocking=False)
+        w = step._enqueue(0, accumulate_absgrad=False)
+        torch.cuda.synchronize()
+        ref1 = w.grads.double()
+        bad_idle = int(((got1.double() - ref1).abs() > 1e-5 * ref1.abs() + 1e-6 * float(ref1.abs().max())).sum())
         np.savez(os.path.join(out_dir, f"st{rank}.npz"), bad=np.array([bad]), err=np.array([float(err.max()), scale]),
-                 factor=np.array([float(model.absgrads_normalize_factor)]), kind=np.array([step.exchange_name()]))
+                 factor=np.array([float(model.absgrads_normalize_factor)]), kind=np.array([step.exchange_name()]),
+                 bad_idle=np.array([bad_idle]))
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -140,7 +158,7 @@ def _step_worker(rank, world, port, out_dir, exchange):
 
 @pytest.mark.skipif(N_GPUS < 2, reason="needs >= 2 GPUs")
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("exchange", ["symm", "symm-p2p", "nccl", "symm-ranged4", "symm-p2p-ranged3"])
+@pytest.mark.parametrize("exchange", ["push", "push-p2p", "push-tiles", "symm", "symm-p2p", "nccl", "symm-ranged4", "symm-p2p-ranged3"])
 def test_sharded_step_gradients_equal_sum_of_views(tmp_path, exchange):
     import torch.multiprocessing as mp
     world = min(N_GPUS, 8)
@@ -149,6 +167,9 @@ def test_sharded_step_gradients_equal_sum_of_views(tmp_path, exchange):
         res = np.load(tmp_path / f"st{r}.npz")
         print(f"rank {r}: {res['kind'][0]}: max err {res['err'][0]:.3e} of {res['err'][1]:.3e}")
         assert int(res["bad"][0]) == 0
-        assert float(res["factor"][0]) == 4.0      # three replays advanced the abs-grad normaliser on every rank
+        assert int(res["bad_idle"][0]) == 0        # a step in which only rank 0 had a view
+        assert float(res["factor"][0]) == 5.0      # four steps advanced the abs-grad normaliser on every rank (idle ones too)
+        if exchange.startswith("push"):
+            assert "push form" in str(res["kind"][0])
         if "ranged" in exchange:
             assert "Gaussian ranges" in str(res["kind"][0])
