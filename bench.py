@@ -87,12 +87,15 @@ def workload_name(args, regime="init"):
     return f"{args.n} Gaussians x {args.width}x{args.height}, 1 view/iter/GPU, regime={regime}"
 
 
-def ncu_traffic_bytes(kernel):
+def ncu_traffic_bytes(kernel, regime="init"):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the newest committed
-    `ncu --set full` summary under profiles/ (written by scripts/summarise_profiles.py from a capture of this
-    same bench command); None if no capture of that kernel is committed."""
+    `ncu --set full` summary of that regime under profiles/ (written by scripts/summarise_profiles.py from a capture
+    of the same workload, scripts/profile_step.py); None if no capture of that kernel is committed.  (ncu cannot run
+    inside the timed bench: a number measured under a profiler is never a bench value.)"""
     pdir = os.path.join(ROOT, "profiles")
-    cands = sorted((f for f in os.listdir(pdir) if f.endswith("ncu_full_summary.txt")), reverse=True) if os.path.isdir(pdir) else []
+    want = "trained_ncu_full_summary.txt" if regime == "trained" else "ncu_full_summary.txt"
+    cands = sorted((f for f in os.listdir(pdir) if f.endswith(want) and (regime == "trained" or "trained" not in f)),
+                   reverse=True) if os.path.isdir(pdir) else []
     mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     for fn in cands:
         cur, rd, wr, best = None, None, None, None
@@ -501,7 +504,7 @@ def bench_regime(args, regime, ctx):
     kernels = [k for k in names if k != "memset"]
     dom = max(kernels, key=lambda k: kern_ms[k])
     achieved = stages[dom] / (kern_ms[dom] * 1e-3) / 1e9
-    traffic, traffic_src = ncu_traffic_bytes(dom + "_kernel") if regime == "init" else (None, None)
+    traffic, traffic_src = ncu_traffic_bytes(dom + "_kernel", regime)
     n_launch = ws.n_kernels + (1 if step.exchange is not None else 0)
     out = {
         "workload": workload_name(args, regime), "value": value, "unit": UNIT, "ms_per_step": ms_per_step,
@@ -570,9 +573,9 @@ def aux_timings(args, ctx):
     # ---- regularisers fwd + bwd in one pass
     out["reg_fwd_bwd_ms"] = timed(lambda: reg_run(model.means.data, model.quats.data, model.scales.data, nn_idx, k, False, 1.0, 1.0))
     # ---- Adam: one launch (eg_adam_multi) vs the reference's four torch.optim.Adam on the same GPU
-    for k in NAMES:
-        model.gauss_params[k].grad = torch.randn_like(model.gauss_params[k]) * 1e-3
-    group = FusedAdamGroup(model, {k: 1e-3 for k in NAMES})
+    for nm in NAMES:
+        model.gauss_params[nm].grad = torch.randn_like(model.gauss_params[nm]) * 1e-3
+    group = FusedAdamGroup(model, {nm: 1e-3 for nm in NAMES})
     out["adam_ms"] = timed(lambda: group.step(zero_grad=False))
     ref_params = [torch.nn.Parameter(model.gauss_params[k].detach().clone()) for k in NAMES]
     for p in ref_params:

@@ -10,7 +10,8 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_C", "libedgegs.so")
+# EG_LIB: another build of the same library (A/B measurements of compile-time variants); default: the in-tree build
+LIB_PATH = os.environ.get("EG_LIB") or os.path.join(HERE, "_C", "libedgegs.so")
 
 EG_ST_NISECT, EG_ST_OVERFLOW, EG_ST_BADCOLOR, EG_ST_MAXTILE, EG_ST_REDO, EG_ST_STOPPED, EG_ST_NKEYS, EG_ST_WORDS = 0, 1, 2, 3, 4, 5, 6, 8
 EG_GT_NONE, EG_GT_F32, EG_GT_U8 = 0, 1, 2

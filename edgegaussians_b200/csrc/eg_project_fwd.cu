@@ -176,15 +176,26 @@ __global__ void __launch_bounds__(256, EG_PF_MINBLOCKS) project_fwd_kernel(
             }
         return;
     }
+    // The slot a key goes to is the RETURN value of the tile counter's atomic: keep three atomics in flight and store
+    // the key of the oldest one (a store right behind its own atomic would expose every atomic's full latency in turn).
+    int p1 = -1, p2 = -1, p3 = -1;
+    size_t t1 = 0, t2 = 0, t3 = 0;
     for (uint32_t i = y0; i < y1; ++i) {
         int j0 = (int)x0, j1 = (int)x1 - 1;
         if (cull && !eg_tile_row_cols(r0.x, r0.y, r1.x, r1.y, r1.z, tau, hu, hv, (int)i, (int)x0, (int)x1, j0, j1)) continue;
         for (int j = j0; j <= j1; ++j) {
             const size_t t = (size_t)(i * tw + j);
             const int pos = atomicAdd(tile_counts + t * EG_CNT_STRIDE, 1);
-            if (!count_only && pos < cfg.tile_capacity) keys[t * (size_t)cfg.tile_capacity + pos] = key;
+            if (count_only) continue;
+            if (p3 >= 0 && p3 < cfg.tile_capacity) keys[t3 * (size_t)cfg.tile_capacity + p3] = key;
+            p3 = p2; t3 = t2;
+            p2 = p1; t2 = t1;
+            p1 = pos; t1 = t;
         }
     }
+    if (p3 >= 0 && p3 < cfg.tile_capacity) keys[t3 * (size_t)cfg.tile_capacity + p3] = key;
+    if (p2 >= 0 && p2 < cfg.tile_capacity) keys[t2 * (size_t)cfg.tile_capacity + p2] = key;
+    if (p1 >= 0 && p1 < cfg.tile_capacity) keys[t1 * (size_t)cfg.tile_capacity + p1] = key;
 }
 
 }  // namespace

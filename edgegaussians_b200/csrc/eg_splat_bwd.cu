@@ -61,6 +61,28 @@ struct RowAcc {
     float S0, S1, S2, ax, ay;
 };
 
+// Raw sums over every pair a lane visited, of vs = -v_sigma and its moments (dx = mean.x - pixel.x, dy likewise):
+//   T0 = sum vs, T1 = sum vs dx, T2 = sum vs dx^2, U0 = sum vs dy, U1 = sum vs dx dy, W0 = sum vs dy^2, and the two abs-sums.
+// They are linear in the pairs, so they are summed over rows (and lanes) as they are and only turned into the eight 2D
+// gradients once per Gaussian (finish_gaussian).  The dx^2 moment and the abs-sums of aligned rows are carried in the
+// pair loop's own registers from row to row (S2p, ax0 ..) and folded in at the end (gacc_store).
+struct GaussAcc {
+    float T0, T1, T2, U0, U1, W0, ax, ay;
+    eg_f2 S2p;
+    float ax0, ax1, ay0, ay1;
+};
+__device__ __forceinline__ void gacc_zero(GaussAcc &a) {
+    a.T0 = a.T1 = a.T2 = a.U0 = a.U1 = a.W0 = a.ax = a.ay = 0.0f;
+    a.S2p = f2_dup(0.0f);
+    a.ax0 = a.ax1 = a.ay0 = a.ay1 = 0.0f;
+}
+__device__ __forceinline__ void gacc_store(const GaussAcc &a, float (&v)[8]) {
+    float s0, s1;
+    f2_unpack(a.S2p, s0, s1);
+    v[0] = a.T0; v[1] = a.T1; v[2] = a.T2 + (s0 + s1); v[3] = a.U0;
+    v[4] = a.U1; v[5] = a.W0; v[6] = a.ax + (a.ax0 + a.ax1); v[7] = a.ay + (a.ay0 + a.ay1);
+}
+
 template <bool HAS_LAST, bool CLIP>
 __device__ __forceinline__ void pair_bwd(const EgSplatG &G, const float b1, const float c0, const float Bdy,
                                          const float Cdy, const float px, const bool in_span, const float w,
@@ -94,10 +116,12 @@ __device__ __forceinline__ void pair_bwd(const EgSplatG &G, const float b1, cons
 struct RowConst2 {
     eg_f2 mx, fa, b1, c0, A, B, Bdy, Cdy;
 };
-// Loop-carried sums stay SCALAR: ptxas keeps scalar accumulators in place but copies 64-bit asm results around
-// (14 MOVs per chunk on the ALU pipe, which is the busiest pipe of this kernel), and FADD takes |x| for free.
+// Loop-carried sums stay SCALAR (FADD takes |x| for free).  Measured equal (117.4 - 117.6 us, round 2): packed in-place
+// accumulators (FADD2 / FFMA2, 11 fewer instructions per chunk) and a loop unrolled by two that never copies the
+// prefetched seed quad -- the kernel is not bound by its instruction count alone.
 struct RowAcc2 {
-    float S0a, S0b, S1a, S1b, S2a, S2b, ax0, ax1, ay0, ay1;
+    float S0a, S0b, S1a, S1b, S2a, S2b;
+    float ax0, ax1, ay0, ay1;
 };
 
 template <bool HAS_LAST>
@@ -126,8 +150,9 @@ __device__ __forceinline__ void pair2_bwd(const EgSplatG &G, const RowConst2 &k,
         v1 = a1 ? v1 : 0.0f;
     }
     const eg_f2 vs = f2_pack(v0, v1);
+    const eg_f2 d = f2_mul(vs, dx);
     float d0, d1, e0, e1;
-    f2_unpack(f2_mul(vs, dx), d0, d1);
+    f2_unpack(d, d0, d1);
     f2_unpack(dx, e0, e1);
     r.S0a += v0;
     r.S0b += v1;
@@ -148,7 +173,7 @@ template <bool HAS_LAST, bool ALIGNED>
 __device__ __forceinline__ void walk_row_bwd(const EgSplatG &G, const int y, const int W, const int tw,
                                              const float *__restrict__ wpix, const unsigned *__restrict__ last_depth,
                                              const int *__restrict__ last_gid, const int *__restrict__ tile_stop,
-                                             float (&v)[8]) {
+                                             GaussAcc &acc) {
     const float dy = G.my - ((float)y + 0.5f);
     const float b1 = eg_pow2row_b1(G.fb, dy), c0 = eg_pow2row_c0(G.fc, G.lo, dy);
     int xa, xb;
@@ -168,26 +193,35 @@ __device__ __forceinline__ void walk_row_bwd(const EgSplatG &G, const int y, con
             k2.mx = f2_dup(G.mx); k2.fa = f2_dup(G.fa); k2.b1 = f2_dup(b1); k2.c0 = f2_dup(c0);
             k2.A = f2_dup(G.A); k2.B = f2_dup(G.B); k2.Bdy = f2_dup(Bdy); k2.Cdy = f2_dup(Cdy);
             RowAcc2 r2;
-            r2.S0a = r2.S0b = r2.S1a = r2.S1b = r2.S2a = r2.S2b = 0.0f;
-            r2.ax0 = r2.ax1 = r2.ay0 = r2.ay1 = 0.0f;
+            r2.S0a = r2.S0b = r2.S1a = r2.S1b = 0.0f;
+            f2_unpack(acc.S2p, r2.S2a, r2.S2b);
+            r2.ax0 = acc.ax0; r2.ax1 = acc.ax1; r2.ay0 = acc.ay0; r2.ay1 = acc.ay1;
             // negated pixel centres of the chunk: -(x + 0.5), -(x + 1.5) | -(x + 2.5), -(x + 3.5)   (exact in fp32)
-            float nb = -((float)(4 * c) + 0.5f);
-            for (; c <= cend; ++c) {
-                const eg_f2 npa = f2_pack(nb, nb - 1.0f), npb = f2_pack(nb - 2.0f, nb - 3.0f);
-                nb -= 4.0f;
-                float4 wn = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (c < cend) wn = ld_f4<true>(wrow, c + 1, W);  // next chunk in flight while this one is evaluated
-                const int x = 4 * c;
+            const float nb = -((float)(4 * c) + 0.5f);
+            eg_f2 npa = f2_pack(nb, nb - 1.0f), npb = f2_pack(nb - 2.0f, nb - 3.0f);
+            const eg_f2 m4 = f2_dup(-4.0f);
+            // one chunk: 4 pairs on the packed pipe; the seed of the NEXT chunk is in flight meanwhile, into the other of
+            // two register quads (the loop is unrolled by two so that no quad is ever copied)
+            auto chunk = [&](const float4 &w, const int cc) {
+                const int x = 4 * cc;
                 uint4 d4 = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
                 if (HAS_LAST) {  // the planes are only defined in tiles where some pixel stopped
-                    if (srow == nullptr || __ldg(srow + (x >> 4)) != 0) d4 = ld_u4<true>(drow, c, W);
+                    if (srow == nullptr || __ldg(srow + (x >> 4)) != 0) d4 = ld_u4<true>(drow, cc, W);
                 }
-                pair2_bwd<HAS_LAST>(G, k2, npa, w4.x, w4.y, d4.x, d4.y, grow + x, r2);
-                pair2_bwd<HAS_LAST>(G, k2, npb, w4.z, w4.w, d4.z, d4.w, grow + x + 2, r2);
+                pair2_bwd<HAS_LAST>(G, k2, npa, w.x, w.y, d4.x, d4.y, grow + x, r2);
+                pair2_bwd<HAS_LAST>(G, k2, npb, w.z, w.w, d4.z, d4.w, grow + x + 2, r2);
+                npa = f2_add(npa, m4);
+                npb = f2_add(npb, m4);
+            };
+            for (; c <= cend; ++c) {
+                float4 wn = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c < cend) wn = ld_f4<true>(wrow, c + 1, W);  // next chunk in flight while this one is evaluated
+                chunk(w4, c);
                 w4 = wn;
             }
-            r.S0 = r2.S0a + r2.S0b; r.S1 = r2.S1a + r2.S1b; r.S2 = r2.S2a + r2.S2b;
-            r.ax = r2.ax0 + r2.ax1; r.ay = r2.ay0 + r2.ay1;
+            r.S0 = r2.S0a + r2.S0b; r.S1 = r2.S1a + r2.S1b;
+            acc.S2p = f2_pack(r2.S2a, r2.S2b);
+            acc.ax0 = r2.ax0; acc.ax1 = r2.ax1; acc.ay0 = r2.ay0; acc.ay1 = r2.ay1;
         } else
         for (; c <= cend; ++c) {
             float4 wn = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -205,15 +239,16 @@ __device__ __forceinline__ void walk_row_bwd(const EgSplatG &G, const int y, con
             w4 = wn;
         }
     }
-    // row moments (of -v_sigma) -> (v_mean2d.x, .y, absgrad.x, .y, v_conic.a, .b, .c, sum v_sigma), accumulated
-    v[0] -= fmaf(G.A, r.S1, Bdy * r.S0);
-    v[1] -= fmaf(G.B, r.S1, Cdy * r.S0);
-    v[2] += r.ax;
-    v[3] += r.ay;
-    v[4] -= 0.5f * r.S2;
-    v[5] -= dy * r.S1;
-    v[6] -= 0.5f * dy * dy * r.S0;
-    v[7] -= r.S0;
+    // the row's moments join the Gaussian's (r.S2 / r.ax / r.ay are zero for aligned rows: carried in acc instead)
+    const float d0 = dy * r.S0;
+    acc.T0 += r.S0;
+    acc.T1 += r.S1;
+    acc.T2 += r.S2;
+    acc.U0 += d0;
+    acc.U1 = fmaf(dy, r.S1, acc.U1);
+    acc.W0 = fmaf(dy, d0, acc.W0);
+    acc.ax += r.ax;
+    acc.ay += r.ay;
 }
 
 // phase 3 of both kernels (lane = Gaussian): the accumulated 2D gradients -> projection VJP + exp / sigmoid VJP +
@@ -231,8 +266,12 @@ __device__ __forceinline__ void finish_gaussian(const eg_config &cfg, const int 
     float vm[3] = {0.f, 0.f, 0.f}, vs[3] = {0.f, 0.f, 0.f}, vq[4] = {0.f, 0.f, 0.f, 0.f}, vo = 0.f;
     float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
     if (has_pairs) {
-        const float4 a0 = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        const float4 a1 = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        // raw moments (GaussAcc: T0, T1, T2, U0 | U1, W0, ax, ay; of vs = -v_sigma) -> 2D gradients:
+        //   v_mean2d = -(A T1 + B U0, B T1 + C U0), v_conic = -(T2 / 2, U1, W0 / 2), sum v_sigma = -T0
+        const float4 m0 = *reinterpret_cast<const float4 *>(acc), m1 = *reinterpret_cast<const float4 *>(acc + 4);
+        const float A = r1.x, B = r1.y, C = r1.z;
+        const float4 a0 = make_float4(-fmaf(A, m0.y, B * m0.w), -fmaf(B, m0.y, C * m0.w), m1.z, m1.w);
+        const float4 a1 = make_float4(-0.5f * m0.z, -m1.x, -0.5f * m1.y, -m0.x);
         const float sc = seed_scale, asc = fabsf(seed_scale);
         g0 = make_float4(a0.x * sc, a0.y * sc, a0.z * asc, a0.w * asc);
         // v_opacity' = sum vis * v_alpha = -(sum v_sigma) / opacity'
@@ -333,13 +372,16 @@ __global__ void __launch_bounds__(SB_WARPS * 32, EG_SB_MINBLOCKS) splat_bwd_kern
         }
         const int wmax = __reduce_max_sync(0xffffffffu, work), wsum = __reduce_add_sync(0xffffffffu, min(work, 1 << 20));
         if (wmax <= (1 << 20) && 2ll * wmax * __popc(ne) <= 3ll * wsum) {
-            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            GaussAcc ga;
+            gacc_zero(ga);
             const int my_rows = nrows > 0 ? G.nrows : 0;  // (G is only defined for lanes that own a visible Gaussian)
             for (int r = 0; r < my_rows; ++r) {
-                if (use_last) walk_row_bwd<true, ALIGNED>(G, G.ylo + r, cfg.width, tw, wpix, last_depth, last_gid, tile_stop, v);
-                else walk_row_bwd<false, ALIGNED>(G, G.ylo + r, cfg.width, tw, wpix, nullptr, nullptr, nullptr, v);
+                if (use_last) walk_row_bwd<true, ALIGNED>(G, G.ylo + r, cfg.width, tw, wpix, last_depth, last_gid, tile_stop, ga);
+                else walk_row_bwd<false, ALIGNED>(G, G.ylo + r, cfg.width, tw, wpix, nullptr, nullptr, nullptr, ga);
             }
             if (nrows > 0) {
+                float v[8];
+                gacc_store(ga, v);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) s_acc[warp][kc][k] = v[k];
             }
@@ -357,13 +399,16 @@ __global__ void __launch_bounds__(SB_WARPS * 32, EG_SB_MINBLOCKS) splat_bwd_kern
         if (item < R) {
             const EgSplatG Go = s_g[warp][owner];
             const int r0 = EG_ROWS_PER_ITEM * (item - Go.start);
+            GaussAcc ga;
+            gacc_zero(ga);
 #pragma unroll
             for (int r = 0; r < EG_ROWS_PER_ITEM; ++r) {
                 if (r0 + r >= Go.nrows) break;
                 const int y = Go.ylo + r0 + r;
-                if (use_last) walk_row_bwd<true, ALIGNED>(Go, y, cfg.width, tw, wpix, last_depth, last_gid, tile_stop, v);
-                else walk_row_bwd<false, ALIGNED>(Go, y, cfg.width, tw, wpix, nullptr, nullptr, nullptr, v);
+                if (use_last) walk_row_bwd<true, ALIGNED>(Go, y, cfg.width, tw, wpix, last_depth, last_gid, tile_stop, ga);
+                else walk_row_bwd<false, ALIGNED>(Go, y, cfg.width, tw, wpix, nullptr, nullptr, nullptr, ga);
             }
+            gacc_store(ga, v);
         }
         // segmented sum over the (contiguous) lanes that share an owner
 #pragma unroll

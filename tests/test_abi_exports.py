@@ -105,4 +105,4 @@ def test_sizing_helpers_without_gpu():
         assert (s.logT > 0) == (name == "splat") and (s.cmask > 0) == (name == "tiles")
     cfg.tile_size = 8
     assert lib.eg_workspace_sizes_for(ctypes.byref(cfg), 0, 0, ctypes.byref(s)) != 0
-    assert lib.eg_allreduce_flag_words(64) == 64 * 8
+    assert lib.eg_allreduce_flag_words(64) == (64 + 2) * 16   # 2 leader blocks + per CTA: 8 arrival counters + 8 epochs
