@@ -42,7 +42,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=500_000, help="Gaussians")
+    ap.add_argument("--n", "--gaussians", dest="n", type=int, default=500_000,
+                    help="Gaussians (use --gaussians under torchrun: its own parser trips over the prefix --n)")
     ap.add_argument("--width", type=int, default=1600)
     ap.add_argument("--height", type=int, default=1200)
     ap.add_argument("--regime", default="both", choices=["both", "init", "trained"])
@@ -382,6 +383,8 @@ def bench_regime(args, regime, ctx):
     t_wall = time.perf_counter() - t_wall0
     per_step_ms = [a.elapsed_time(b) for a, b in zip(ev0, ev1)]
     total_ms = sum(per_step_ms)
+    # this rank's mean step time per view slot: the spread is what a view-sharded step pays as rank skew (max over ranks)
+    slot_ms = [float(np.mean(per_step_ms[v::V])) for v in range(min(V, args.steps))]
     # informational: the same K steps back to back WITHOUT the L2 flush (parameters / records stay L2-resident,
     # as they would between optimizer steps); not the headline
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -526,6 +529,7 @@ def bench_regime(args, regime, ctx):
                 "steps": n_e2e, "l2": "not flushed (back-to-back steps, as in training)",
                 "api": "GraphedRasterStep.set_view(pinned host) + replay + loss readback"},
         "value_no_l2_flush": world * args.steps / (hot_ms * 1e-3),
+        "ms_per_view_slot_rank0": slot_ms,
         "gpu_launches": n_launch * args.steps,
         "clocks": clocks, "wall_s_timed_region": t_wall,
     }

@@ -90,7 +90,11 @@ class GraphedRasterStep:
             if self.exchange is None or self.exchange.numel != n:
                 from .parallel import SymmetricExchange
                 try:
-                    self.exchange = SymmetricExchange(n, dev, self.allreduce_group, multicast=not mode.endswith("-p2p"))
+                    import torch.distributed as dist
+                    # "auto": broadcast through the NVSwitch multicast object from 3 ranks up; between two GPUs plain
+                    # peer stores are faster (measured: profiles/r2_exchange.md)
+                    mc = not mode.endswith("-p2p") and not (mode == "auto" and dist.get_world_size(self.allreduce_group) <= 2)
+                    self.exchange = SymmetricExchange(n, dev, self.allreduce_group, multicast=mc)
                     # default: the push form -- the backward's own stores carry the reduce-scatter, one reduce +
                     # broadcast kernel behind it; "symm*": the pull form (one all-reduce kernel behind the backward)
                     if mode in ("auto", "push", "push-p2p") and self.exchange_ranges <= 1:

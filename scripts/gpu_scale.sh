@@ -14,6 +14,6 @@ python scripts/show_bench.py gpurun_out/r2_scale_n$N.json
 if [ "$2" == "full" ]; then
   timeout 200 $TR bench.py --gpus $N --width 1200 --height 680 --steps 40 --warmup 5 --no-aux --no-cpu-baseline 2> gpurun_out/r2_cfg4_n$N.err | grep '^{' > gpurun_out/r2_cfg4_n$N.json
   python scripts/show_bench.py gpurun_out/r2_cfg4_n$N.json
-  timeout 200 $TR bench.py --gpus $N --n 2000000 --width 1920 --height 1080 --steps 30 --warmup 5 --no-aux --no-cpu-baseline 2> gpurun_out/r2_cfg5_2m_n$N.err | grep '^{' > gpurun_out/r2_cfg5_2m_n$N.json
+  timeout 200 $TR bench.py --gpus $N --gaussians 2000000 --width 1920 --height 1080 --steps 30 --warmup 5 --no-aux --no-cpu-baseline 2> gpurun_out/r2_cfg5_2m_n$N.err | grep '^{' > gpurun_out/r2_cfg5_2m_n$N.json
   python scripts/show_bench.py gpurun_out/r2_cfg5_2m_n$N.json
 fi

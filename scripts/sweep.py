@@ -15,7 +15,7 @@ ap.add_argument("--quick", action="store_true", help="fewer sweep sizes (multi-G
 ap.add_argument("--regime", default="both")
 a = ap.parse_args()
 rows = [("cfg3 DTU-like", 200_000, 1600, 1200), ("cfg4 Replica-like", 500_000, 1200, 680)]
-sizes = [100_000, 1_000_000, 2_000_000] if a.quick else [10_000, 30_000, 100_000, 300_000, 1_000_000, 2_000_000]
+sizes = [100_000, 1_000_000, 2_000_000] if a.quick else [10_000, 100_000, 300_000, 1_000_000, 2_000_000]
 rows += [(f"cfg5 sweep", n, 1920, 1080) for n in sizes]
 out_path = os.path.join(ROOT, "gpurun_out", f"r2_sweep_g{a.gpus}.jsonl")
 os.makedirs(os.path.dirname(out_path), exist_ok=True)
@@ -27,7 +27,7 @@ for name, n, w, h in rows:
     if a.gpus > 1:
         cmd += ["-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={a.gpus}", "--master-addr", "127.0.0.1",
                 "--master-port", "29571"]
-    cmd += [os.path.join(ROOT, "bench.py"), "--gpus", str(a.gpus), "--n", str(n), "--width", str(w), "--height", str(h),
+    cmd += [os.path.join(ROOT, "bench.py"), "--gpus", str(a.gpus), "--gaussians", str(n), "--width", str(w), "--height", str(h),
             "--steps", "30", "--warmup", "5", "--no-cpu-baseline", "--no-aux", "--regime", a.regime]
     try:
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
