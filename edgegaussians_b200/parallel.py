@@ -182,7 +182,7 @@ class SymmetricExchange:
 
 class NativeComm:
     """Communicator of libedgegs.so (eg_comm_*, NCCL underneath) over the ranks of ``group``: what
-    ``eg_splat_bwd_allreduce`` exchanges gradients through.  torch.distributed only carries the 128-byte
+    ``exchange="native-nccl"`` (A/B baseline) all-reduces through.  torch.distributed only carries the 128-byte
     rendezvous id.  Collective: every rank of the group must construct it at the same point."""
 
     def __init__(self, device: torch.device, group=None):
