@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(RB_THREADS) raster_bwd_kernel(
     __shared__ __align__(16) uint32_t s_cm[RB_THREADS * 8];  // contribution masks of the batch
     __shared__ int s_off[RB_THREADS + 1];              // exclusive prefix of the mask popcounts
     __shared__ unsigned char s_nz[RB_THREADS];         // which of the 8 mask words are non-zero
-    __shared__ int s_wsum[RB_THREADS / 32];
+    __shared__ __align__(16) int s_wsum[RB_THREADS / 32];  // 16-byte aligned: read back as two 128-bit loads (unaligned, ptxas widens them over the tail of s_nz: a racecheck false positive)
 
     if (status[EG_ST_OVERFLOW]) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
