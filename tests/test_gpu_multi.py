@@ -82,7 +82,7 @@ def _exchange_worker(rank, world, port, out_dir):
 
 
 @pytest.mark.skipif(N_GPUS < 2, reason="needs >= 2 GPUs")
-@pytest.mark.timeout(120)
+@pytest.mark.timeout(240)
 def test_symmetric_allreduce_equals_sum(tmp_path):
     import torch.multiprocessing as mp
     world = min(N_GPUS, 8)
@@ -157,7 +157,7 @@ def _step_worker(rank, world, port, out_dir, exchange):
 
 
 @pytest.mark.skipif(N_GPUS < 2, reason="needs >= 2 GPUs")
-@pytest.mark.timeout(120)
+@pytest.mark.timeout(240)
 @pytest.mark.parametrize("exchange", ["push", "push-p2p", "push-tiles", "symm", "symm-p2p", "nccl", "symm-ranged4", "symm-p2p-ranged3"])
 def test_sharded_step_gradients_equal_sum_of_views(tmp_path, exchange):
     import torch.multiprocessing as mp
