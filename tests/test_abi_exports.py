@@ -106,3 +106,23 @@ def test_sizing_helpers_without_gpu():
     cfg.tile_size = 8
     assert lib.eg_workspace_sizes_for(ctypes.byref(cfg), 0, 0, ctypes.byref(s)) != 0
     assert lib.eg_allreduce_flag_words(64) == (64 + 2) * 16   # 2 leader blocks + per CTA: 8 arrival counters + 8 epochs
+
+
+def test_push_exchange_sizing_without_gpu():
+    """eg_exchange_push_per / eg_exchange_stage_floats (include/edgegs.h, push form of the exchange): rank o owns the
+    Gaussians [o * per, (o + 1) * per), per a multiple of the backward's 128 Gaussians per CTA, the `world` slots of
+    11 * per floats cover every Gaussian exactly once -- the arithmetic eg_grad_out (csrc/eg_common.cuh) and
+    eg_exchange_reduce_bcast share."""
+    from edgegaussians_b200 import _lib
+    lib = _lib.load()
+    for n in (1, 127, 128, 1001, 30_001, 500_000, 2_000_000):
+        for world in (2, 3, 4, 8):
+            per = lib.eg_exchange_push_per(n, world)
+            assert per % 128 == 0 and per * world >= n and (per - 128) * world < n + 128 * world
+            assert lib.eg_exchange_stage_floats(n, world) == world * 11 * per
+            # owner and in-slot row of the first / last Gaussian, and of the last Gaussian of every backward CTA
+            for g in (0, n - 1, *range(127, n, 128 * 61)):
+                owner, row = g // per, g % per
+                assert 0 <= owner < world and row < per
+                assert (g // 128 * 128) // per == owner     # a CTA's 128 Gaussians have one owner
+    assert lib.eg_exchange_push_per(0, 8) == 0 and lib.eg_exchange_stage_floats(0, 8) == 0
